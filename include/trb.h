@@ -1,0 +1,197 @@
+/*
+ * trb.h -- C ABI of the B200-native mesh-rendering hot path (libtrb.so).
+ *
+ * This is the drop-in boundary for the four native entry points the reference scripts reach
+ * through PyTorch3D's pybind11 module `pytorch3d._C` (un-vendored dependency of
+ * YufengJin/torch_renderer; call sites: torch_renderer.py:113,120,158,
+ * camera_pose_optimizer.py:244-250, mesh_deformer.py:153,197, batch_rendering_test.py:252,274,
+ * myrenderer.py:103-105, renderer.py:100-101), plus the fused shading/blending that PyTorch3D
+ * expresses as ~40 ATen ops (renderer/mesh/shading.py, renderer/blending.py, renderer/lighting.py):
+ *
+ *   _C.rasterize_meshes            -> trb_raster_forward
+ *   _C.rasterize_meshes_backward   -> trb_raster_backward
+ *   _C.interp_face_attrs_forward   -> trb_interp_forward
+ *   _C.interp_face_attrs_backward  -> trb_interp_backward
+ *   phong_shading + softmax_rgb_blend / sigmoid_alpha_blend / hard_rgb_blend
+ *                                  -> trb_shade_forward / trb_shade_backward
+ *   MeshRasterizer.transform (Transform3d bmm + divide)
+ *                                  -> trb_transform_forward / trb_transform_backward
+ *   Meshes.verts_normals_packed    -> trb_vertex_normals_forward / _backward
+ *   MeshRenderer.forward + loss.backward() end to end (fragments never re-read in between)
+ *                                  -> trb_render_forward / trb_render_backward
+ *
+ * Contract:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller allocates every input, output and workspace buffer; the library never
+ *     allocates or frees device memory, keeps no global state and never synchronises;
+ *   - every call takes the CUDA device ordinal and the stream explicitly (autograd's backward
+ *     runs on a different host thread than forward);
+ *   - returns TRB_OK or a trb_status; trb_last_cuda_error() gives the cudaError_t of the
+ *     calling thread's last TRB_ERR_CUDA;
+ *   - layouts are PyTorch3D's: row-major contiguous, int64 pix_to_face, -1 background fill.
+ */
+#ifndef TRB_H_
+#define TRB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRB_ABI_VERSION 1
+#define TRB_MAX_FACES_PER_PIXEL 150
+
+typedef void* trb_stream_t; /* cudaStream_t */
+
+typedef enum trb_status {
+  TRB_OK = 0,
+  TRB_ERR_BAD_ARG = 1,      /* -> ValueError  */
+  TRB_ERR_K_TOO_LARGE = 2,  /* -> ValueError: faces_per_pixel > 150 (PyTorch3D kMaxPointsPerPixel) */
+  TRB_ERR_WORKSPACE = 3,    /* -> RuntimeError: workspace smaller than trb_raster_workspace_bytes */
+  TRB_ERR_CUDA = 4          /* -> RuntimeError: see trb_last_cuda_error() */
+} trb_status;
+
+/* flags for the rasteriser entry points */
+#define TRB_PERSPECTIVE_CORRECT 1u
+#define TRB_CLIP_BARYCENTRIC 2u
+#define TRB_CULL_BACKFACES 4u
+
+/*
+ * One record per view (image) of the batch; int32[8], device memory, `N` records.
+ * A "view" is one (mesh, camera) pair.  Several views may share one mesh (the
+ * `Meshes.extend(N)` pattern of batch_rendering_test.py:326 / mesh_deformer.py:150) without
+ * the mesh being replicated in memory.
+ */
+typedef struct trb_view {
+  int32_t face_start;      /* first row of `faces` drawn by this view */
+  int32_t face_count;      /* number of rows */
+  int32_t vert_delta;      /* faces[r][i] + vert_delta = row of that vertex in `verts_ndc` */
+  int32_t p2f_base;        /* pix_to_face value of row face_start (packed face index) */
+  int32_t world_vert_start;/* first row of this view's mesh in the world-space vertex arrays */
+  int32_t vert_count;      /* number of vertices of that mesh */
+  int32_t ndc_vert_start;  /* first row of this view's block in `verts_ndc` */
+  int32_t reserved;
+} trb_view;
+
+int trb_abi_version(void);
+const char* trb_status_string(int status);
+int trb_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Camera transform (replaces MeshRasterizer.transform):
+ *   X_view = X_world * R + T;  x_ndc = fx*X/Z + px,  y_ndc = fy*Y/Z + py  (perspective)
+ *                               x_ndc = fx*X   + px,  y_ndc = fy*Y   + py  (orthographic)
+ *   z_ndc  = Z_view.
+ * verts_world f32[Vw,3]; R f32[N,3,3]; T f32[N,3]; proj f32[N,4] = (fx,fy,px,py) already in NDC
+ * units; verts_ndc f32[sum_n vert_count,3].
+ * Backward ACCUMULATES into grad_verts_world / grad_R / grad_T / grad_proj (caller zeroes them;
+ * any of the four may be NULL).
+ */
+int trb_transform_forward(const float* verts_world, const float* R, const float* T,
+                          const float* proj, const trb_view* views, int N, int max_vert_count,
+                          int perspective, float* verts_ndc, int device, trb_stream_t stream);
+int trb_transform_backward(const float* verts_world, const float* R, const float* T,
+                           const float* proj, const trb_view* views, int N, int max_vert_count,
+                           int perspective, const float* grad_verts_ndc, float* grad_verts_world,
+                           float* grad_R, float* grad_T, float* grad_proj, int device,
+                           trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rasteriser (replaces _C.rasterize_meshes / _C.rasterize_meshes_backward).
+ *
+ * verts_ndc f32[*,3]: NDC x,y and view-space z of every (view, vertex).
+ * faces     i32[F,3] vertex ids, or NULL: then `verts_ndc` is PyTorch3D's face_verts f32[F,3,3]
+ *           and face row r owns vertices 3r, 3r+1, 3r+2 (vert_delta is ignored).
+ * pair_capacity: number of int32 (tile, face) slots in the workspace; tiles whose list does not
+ *           fit are rasterised by scanning the whole mesh, so the result never depends on it.
+ * stats     i32[4] (may be NULL): [0] pairs needed, [1] tiles that overflowed, [2] pair_capacity.
+ * Outputs   pix_to_face i64[N,H,W,K], zbuf f32[N,H,W,K], bary f32[N,H,W,K,3], dists f32[N,H,W,K];
+ *           every element is written (-1 where no face).
+ */
+int trb_raster_workspace_bytes(int N, int H, int W, int K, int64_t pair_capacity, size_t* bytes);
+int trb_raster_forward(const float* verts_ndc, const int32_t* faces, const trb_view* views, int N,
+                       int max_face_count, int H, int W, int K, float blur_radius, uint32_t flags,
+                       int64_t pair_capacity, void* workspace, size_t workspace_bytes,
+                       int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                       int32_t* stats, int device, trb_stream_t stream);
+/* grad_verts_ndc f32, same shape as verts_ndc; ACCUMULATED into (caller zeroes). */
+int trb_raster_backward(const float* verts_ndc, const int32_t* faces, const trb_view* views, int N,
+                        int H, int W, int K, uint32_t flags, const int64_t* pix_to_face,
+                        const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                        float* grad_verts_ndc, int device, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * interpolate_face_attributes (replaces _C.interp_face_attrs_forward/backward).
+ * pix_to_face i64[P], bary f32[P,3], face_attrs f32[F,3,D] -> out f32[P,D] (0 where face < 0).
+ * Backward writes grad_bary f32[P,3] and ACCUMULATES into grad_face_attrs f32[F,3,D].
+ */
+int trb_interp_forward(const int64_t* pix_to_face, const float* bary, const float* face_attrs,
+                       int64_t P, int64_t F, int D, float* out, int device, trb_stream_t stream);
+int trb_interp_backward(const int64_t* pix_to_face, const float* bary, const float* face_attrs,
+                        const float* grad_out, int64_t P, int64_t F, int D, float* grad_bary,
+                        float* grad_face_attrs, int device, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Area-weighted vertex normals (replaces Meshes.verts_normals_packed).
+ * verts f32[V,3], faces i32[F,3] -> raw f32[V,3] (un-normalised sum, kept for backward) and
+ * normals f32[V,3] = raw / max(|raw|, 1e-6).  Backward ACCUMULATES into grad_verts.
+ */
+int trb_vertex_normals_forward(const float* verts, const int32_t* faces, int64_t V, int64_t F,
+                               float* raw, float* normals, int device, trb_stream_t stream);
+int trb_vertex_normals_backward(const float* verts, const int32_t* faces, int64_t V, int64_t F,
+                                const float* raw, const float* grad_normals, float* grad_raw,
+                                float* grad_verts, int device, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused shading + blending.
+ */
+#define TRB_SHADER_SOFT_PHONG 0      /* phong_shading + softmax_rgb_blend   */
+#define TRB_SHADER_HARD_PHONG 1      /* phong_shading + hard_rgb_blend      */
+#define TRB_SHADER_SOFT_SILHOUETTE 2 /* sigmoid_alpha_blend, RGB = 1        */
+#define TRB_LIGHT_AMBIENT 0
+#define TRB_LIGHT_POINT 1
+#define TRB_LIGHT_DIRECTIONAL 2
+#define TRB_TEX_VERTEX 0 /* per-vertex RGB interpolated in the kernel (TexturesVertex) */
+#define TRB_TEX_TEXELS 1 /* caller supplies texels f32[N,H,W,K,3] (e.g. TexturesUV)    */
+#define TRB_VIEW_PARAM_STRIDE 20
+/* view_params f32[N,20]: [0:3] light location/direction, [3:6] ambient (material*light),
+ * [6:9] diffuse (material*light), [9:12] specular (material*light), [12] shininess,
+ * [13:16] camera centre, [16] znear, [17] zfar, [18:20] reserved. */
+
+typedef struct trb_shade_config {
+  int32_t N, H, W, K;
+  int32_t shader;       /* TRB_SHADER_*  */
+  int32_t light_kind;   /* TRB_LIGHT_*   */
+  int32_t texture_mode; /* TRB_TEX_*     */
+  float sigma, gamma;
+  float background[3];
+} trb_shade_config;
+
+/* faces i32[F,3] index verts_world / vert_normals / vert_colors (all f32[Vw,3]).
+ * images f32[N,H,W,4]. */
+int trb_shade_forward(const trb_shade_config* host_cfg, const trb_view* views,
+                      const float* view_params, const int64_t* pix_to_face, const float* bary,
+                      const float* zbuf, const float* dists, const int32_t* faces,
+                      const float* verts_world, const float* vert_normals,
+                      const float* vert_colors, const float* texels, float* images, int device,
+                      trb_stream_t stream);
+/* Writes grad_bary/grad_zbuf/grad_dists (same shapes as the fragments; any may be NULL) and
+ * ACCUMULATES into grad_verts_world, grad_vert_normals, grad_vert_colors (f32[Vw,3]),
+ * grad_texels is written (f32[N,H,W,K,3]); grad_view_params f32[N,20] accumulates the light
+ * vector and camera-centre gradients.  Any output pointer may be NULL. */
+int trb_shade_backward(const trb_shade_config* host_cfg, const trb_view* views,
+                       const float* view_params, const int64_t* pix_to_face, const float* bary,
+                       const float* zbuf, const float* dists, const int32_t* faces,
+                       const float* verts_world, const float* vert_normals,
+                       const float* vert_colors, const float* texels, const float* grad_images,
+                       float* grad_bary, float* grad_zbuf, float* grad_dists,
+                       float* grad_verts_world, float* grad_vert_normals, float* grad_vert_colors,
+                       float* grad_texels, float* grad_view_params, int device,
+                       trb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRB_H_ */

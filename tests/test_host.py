@@ -1,0 +1,187 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/trb.h declares, the host-side
+containers / settings behave like the PyTorch3D surface the reference uses, and the product path
+fails loudly without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import torch_renderer_b200 as trb
+from torch_renderer_b200 import _lib
+from helpers import load_mesh, uv_sphere
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "trb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 14
+    if not os.path.exists(_lib.LIB_PATH):
+        from torch_renderer_b200 import build
+        build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(handle, s), f"libtrb.so does not export {s}"
+    # the Python binding covers the same set
+    assert set(syms) == set(_lib.declared_symbols())
+    L = _lib.lib()
+    assert L.trb_abi_version() == 1
+    assert L.trb_status_string(2).decode().startswith("faces_per_pixel")
+
+
+def test_workspace_query_and_argument_errors_without_gpu():
+    L = _lib.lib()
+    n = ctypes.c_size_t(0)
+    assert L.trb_raster_workspace_bytes(2, 64, 64, 1, 1000, ctypes.byref(n)) == _lib.TRB_OK
+    assert n.value >= 1000 * 4 + 3 * 2 * 16 * 4
+    assert L.trb_raster_workspace_bytes(2, 64, 64, 151, 1000, ctypes.byref(n)) == _lib.TRB_ERR_K_TOO_LARGE
+    assert L.trb_raster_workspace_bytes(2, 0, 64, 1, 1000, ctypes.byref(n)) == _lib.TRB_ERR_BAD_ARG
+    with pytest.raises(ValueError):
+        _lib.check(_lib.TRB_ERR_K_TOO_LARGE, "x")
+    with pytest.raises(ValueError):
+        _lib.check(_lib.TRB_ERR_BAD_ARG, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.TRB_ERR_WORKSPACE, "x")
+
+
+def test_product_path_has_no_cpu_fallback():
+    v, f = uv_sphere(4, 6)
+    meshes = trb.Meshes(verts=[v], faces=[f], textures=trb.TexturesVertex(torch.ones(1, v.shape[0], 3)))
+    cameras = trb.FoVPerspectiveCameras()
+    rasterizer = trb.MeshRasterizer(cameras=cameras, raster_settings=trb.RasterizationSettings(image_size=16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rasterizer(meshes)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        meshes.verts_normals_packed()
+    # and nothing in the package imports, loads or links the oracle
+    pkg = os.path.join(ROOT, "torch_renderer_b200")
+    pat = re.compile(r"^\s*(import|from)\s+oracle\b|libtrb_oracle|trb_oracle_|#include\s+\"[^\"]*oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, fn)).read()), fn
+
+
+def test_meshes_container():
+    v, f = uv_sphere(4, 6)
+    v2, f2 = uv_sphere(3, 5)
+    m = trb.Meshes(verts=[v, v2], faces=[f, f2])
+    assert len(m) == 2
+    assert m.verts_packed().shape == (v.shape[0] + v2.shape[0], 3)
+    assert torch.equal(m.faces_packed()[f.shape[0]:], f2 + v.shape[0])
+    assert m.mesh_to_faces_packed_first_idx().tolist() == [0, f.shape[0]]
+    assert m.num_verts_per_mesh().tolist() == [v.shape[0], v2.shape[0]]
+    assert m.verts_padded().shape == (2, v.shape[0], 3)
+    assert (m.faces_padded()[1, f2.shape[0]:] == -1).all()
+    t = m.view_table()
+    assert t.N == 2 and not t.shared_mesh and t.max_face_count == f.shape[0]
+    assert t.host[1, 0] == f.shape[0] and t.host[1, 3] == f.shape[0] and t.host[1, 6] == v.shape[0]
+    # lazy extend shares storage but behaves like a replicated batch
+    single = trb.Meshes(verts=[v], faces=[f], textures=trb.TexturesVertex(torch.rand(1, v.shape[0], 3)))
+    e = single.extend(5)
+    assert len(e) == 5 and e.is_shared_replica and len(e.textures) == 5
+    te = e.view_table()
+    assert te.shared_mesh and te.N == 5 and te.total_ndc_verts == 5 * v.shape[0]
+    assert te.host[3].tolist() == [0, f.shape[0], 3 * v.shape[0], 3 * f.shape[0], 0, v.shape[0], 3 * v.shape[0], 0]
+    assert e.verts_packed().shape == (5 * v.shape[0], 3)  # materialises
+    assert torch.equal(e.faces_packed()[f.shape[0]: 2 * f.shape[0]], f + v.shape[0])
+    assert e.textures.verts_features_packed().shape == (5 * v.shape[0], 3)
+    # offsets / scaling / update_padded / clone
+    o = single.offset_verts(torch.ones(v.shape[0], 3))
+    assert torch.allclose(o.verts_packed(), v + 1)
+    o2 = single.offset_verts(torch.tensor([1.0, 0.0, 0.0]))
+    assert torch.allclose(o2.verts_packed()[:, 0], v[:, 0] + 1)
+    c = single.clone()
+    c.scale_verts_(2.0)
+    assert torch.allclose(c.verts_packed(), 2 * v) and torch.allclose(single.verts_packed(), v)
+    u = m.update_padded(m.verts_padded() * 3)
+    assert torch.allclose(u.verts_list()[1], v2 * 3)
+    vv, ff = single.get_mesh_verts_faces(0)
+    assert vv.shape == v.shape and ff.shape == f.shape
+    with pytest.raises(ValueError):
+        trb.Meshes(verts=[v], faces=[f, f2])
+    with pytest.raises(ValueError):
+        trb.Meshes(verts=[v], faces=[f], textures=trb.TexturesVertex(torch.rand(2, v.shape[0], 3)))
+
+
+def test_settings_validation_matches_upstream_errors():
+    from torch_renderer_b200.rasterizer import _check_bin_size, _parse_image_size
+    assert _parse_image_size(64) == (64, 64) and _parse_image_size((180, 320)) == (180, 320)
+    for bad in ((1, 2, 3), (0, 4), "x", (1.5, 2)):
+        with pytest.raises(ValueError):
+            _parse_image_size(bad)
+    with pytest.raises(ValueError):
+        _check_bin_size(8, 512, 512)  # 64 bins per side >= 22
+    _check_bin_size(32, 512, 512)
+    _check_bin_size(None, 512, 512)
+    _check_bin_size(0, 512, 512)
+    s = trb.RasterizationSettings()
+    assert (s.image_size, s.blur_radius, s.faces_per_pixel, s.perspective_correct) == (256, 0.0, 1, None)
+    b = trb.BlendParams()
+    assert (b.sigma, b.gamma, tuple(b.background_color)) == (1e-4, 1e-4, (1.0, 1.0, 1.0))
+
+
+def test_cameras_lights_materials_broadcast_and_defaults():
+    cams = trb.FoVPerspectiveCameras(R=torch.eye(3)[None].repeat(4, 1, 1), T=torch.zeros(4, 3))
+    assert len(cams) == 4 and cams.fov.shape == (4,) and cams.is_perspective() and cams.in_ndc()
+    proj, persp = cams.ndc_projection_params()
+    assert persp and proj.shape == (4, 4)
+    assert torch.allclose(proj[0], torch.tensor([1.7320508, 1.7320508, 0.0, 0.0]))
+    assert torch.allclose(cams[1:3].R, torch.eye(3)[None].repeat(2, 1, 1))
+    pc = trb.PerspectiveCameras(focal_length=torch.tensor([[500.0, 510.0]]), principal_point=torch.tensor([[300.0, 200.0]]),
+                                in_ndc=False, image_size=torch.tensor([[480, 640]]))
+    proj, _ = pc.ndc_projection_params()
+    assert torch.allclose(proj[0], torch.tensor([500 / 240, 510 / 240, -(300 - 320) / 240, -(200 - 240) / 240]))
+    pts = torch.tensor([[0.3, -0.2, 2.0], [0.0, 0.1, 1.5]])
+    ndc = pc.transform_points_ndc(pts)
+    assert torch.allclose(ndc[:, 0], proj[0, 0] * pts[:, 0] / pts[:, 2] + proj[0, 2], atol=1e-6)
+    assert torch.allclose(ndc[:, 1], proj[0, 1] * pts[:, 1] / pts[:, 2] + proj[0, 3], atol=1e-6)
+    # 4x4 K matrix form (reference renderer.py:47-69)
+    K = torch.tensor([[500.0, 0, 300, 0], [0, 510, 200, 0], [0, 0, 0, 1], [0, 0, 1, 0]])[None]
+    pk = trb.PerspectiveCameras(K=K, in_ndc=False, image_size=torch.tensor([[480, 640]]))
+    assert torch.allclose(pk.ndc_projection_params()[0], proj)
+    lights = trb.PointLights(location=[[0.0, 0.0, -3.0]])
+    assert lights.location.shape == (1, 3) and torch.allclose(lights.ambient_color, torch.full((1, 3), 0.5))
+    lights.location = torch.tensor([[1.0, 2.0, 3.0]])
+    assert lights.clone().location[0, 1] == 2.0
+    assert torch.allclose(trb.AmbientLights().ambient_color, torch.ones(1, 3))
+    m = trb.Materials()
+    assert m.shininess.shape == (1,) and float(m.shininess[0]) == 64.0
+    # camera centre: C = -T R^-1
+    R, T = trb.look_at_view_transform(dist=2.0, elev=30.0, azim=40.0)
+    c = trb.FoVPerspectiveCameras(R=R, T=T).get_camera_center()
+    assert abs(float(c.norm()) - 2.0) < 1e-5
+
+
+def test_obj_roundtrip_and_ico_sphere(tmp_path):
+    m = trb.ico_sphere(2)
+    assert m.verts_packed().shape == (162, 3) and m.faces_packed().shape == (320, 3)
+    assert torch.allclose(m.verts_packed().norm(dim=1), torch.ones(162), atol=1e-6)
+    assert trb.ico_sphere(4).faces_packed().shape == (5120, 3)
+    p = tmp_path / "s.obj"
+    trb.save_obj(str(p), m.verts_packed(), m.faces_packed())
+    v, f, aux = trb.load_obj(str(p))
+    assert torch.allclose(v, m.verts_packed(), atol=1e-5) and torch.equal(f.verts_idx, m.faces_packed())
+    # polygons are fan-triangulated, v/vt/vn and negative indices parse
+    q = tmp_path / "q.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                 "f 1/1/1 2/2/1 3/3/1 4/4/1\nf -4//-1 -3//-1 -2//-1\n")
+    v, f, aux = trb.load_obj(str(q))
+    assert f.verts_idx.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+    assert f.textures_idx.tolist()[:2] == [[0, 1, 2], [0, 2, 3]] and f.textures_idx.tolist()[2] == [-1, -1, -1]
+    assert aux.verts_uvs.shape == (4, 2) and aux.normals.shape == (1, 3)
+
+
+def test_golden_meshes_fixture():
+    v, f = load_mesh("teapot")
+    assert v.shape == (1292, 3) and f.shape == (2464, 3)
+    v, f = load_mesh("cow")
+    assert v.shape == (2930, 3) and f.shape == (5856, 3) and int(f.max()) == 2929

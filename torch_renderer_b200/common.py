@@ -1,0 +1,133 @@
+"""Batched-property base class shared by cameras, lights and materials.
+
+Mirrors the behaviour the reference scripts rely on from PyTorch3D's ``TensorProperties``
+(``renderer/utils.py``): constructor keyword values are converted to float tensors with a leading
+batch dimension and broadcast to the largest batch size; ``.to()``, ``.clone()``, ``len()`` and
+integer / slice indexing work (reference usage: ``PointLights(device=..., location=[[0,0,-3]])``
+renderer.py:76, ``lights.location = tensor`` renderer.py:82-83, ``cameras[i]``-style access).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Dict, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+Device = Union[str, torch.device]
+
+
+def make_device(device: Device) -> torch.device:
+    device = torch.device(device) if isinstance(device, str) else device
+    if device.type == "cuda" and device.index is None:
+        device = torch.device(f"cuda:{torch.cuda.current_device() if torch.cuda.is_available() else 0}")
+    return device
+
+
+def format_tensor(value, dtype=torch.float32, device: Device = "cpu") -> torch.Tensor:
+    device = make_device(device)
+    if not torch.is_tensor(value):
+        value = torch.tensor(value, dtype=dtype, device=device)
+    elif value.dim() == 0:
+        value = value.view(1)
+    if value.dim() == 0:
+        value = value.view(1)
+    if value.device != device or value.dtype != dtype:
+        value = value.to(device=device, dtype=dtype)
+    return value
+
+
+def convert_to_tensors_and_broadcast(*args, dtype=torch.float32, device: Device = "cpu"):
+    """Each arg -> tensor with a batch dimension; batch dims of size 1 are expanded to the max."""
+    tensors = [format_tensor(a, dtype, device) for a in args]
+    sizes = [t.shape[0] for t in tensors]
+    N = max(sizes)
+    out = []
+    for t in tensors:
+        if t.shape[0] != 1 and t.shape[0] != N:
+            raise ValueError("Got non-broadcastable sizes %r" % sizes)
+        out.append(t.expand((N,) + tuple(t.shape[1:])) if t.shape[0] != N else t)
+    return out
+
+
+_MODULE_INTERNALS = frozenset(nn.Module().__dict__.keys())
+
+
+class TensorProperties(nn.Module):
+    """Holds named tensors broadcast to a common batch size N."""
+
+    def __init__(self, dtype: torch.dtype = torch.float32, device: Device = "cpu", **kwargs) -> None:
+        super().__init__()
+        self.device = make_device(device)
+        self._N = 0
+        self._prop_names = []
+        if kwargs:
+            values: Dict[str, Any] = {}
+            batch_sizes = []
+            for k, v in kwargs.items():
+                if v is None or isinstance(v, (str, bool)):
+                    setattr(self, k, v)
+                    continue
+                if isinstance(v, (int, float, list, tuple)) or torch.is_tensor(v) or hasattr(v, "__array__"):
+                    t = format_tensor(v, dtype=dtype, device=self.device)
+                    values[k] = t
+                    batch_sizes.append(t.shape[0])
+                else:
+                    raise ValueError(f"Arg {k} must be torch.Tensor or convertible (got {type(v)})")
+            if batch_sizes:
+                N = max(batch_sizes)
+                self._N = N
+                for k, t in values.items():
+                    if t.shape[0] != 1 and t.shape[0] != N:
+                        raise ValueError(f"Expected all inputs to have batch dimension 1 or {N}; "
+                                         f"{k} has {t.shape[0]}")
+                    if t.shape[0] != N:
+                        t = t.expand((N,) + tuple(t.shape[1:]))
+                    setattr(self, k, t)
+                    self._prop_names.append(k)
+
+    def __len__(self) -> int:
+        return self._N
+
+    def isempty(self) -> bool:
+        return self._N == 0
+
+    def _tensor_props(self):
+        return [k for k, v in self.__dict__.items() if torch.is_tensor(v)]
+
+    def to(self, device: Device = "cpu"):
+        device = make_device(device)
+        for k in self._tensor_props():
+            setattr(self, k, self.__dict__[k].to(device))
+        self.device = device
+        return self
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda" if device is None else f"cuda:{device}"))
+
+    def clone(self):
+        other = self.__class__.__new__(self.__class__)
+        nn.Module.__init__(other)
+        for k, v in self.__dict__.items():
+            if k in _MODULE_INTERNALS:
+                continue
+            other.__dict__[k] = v.clone() if torch.is_tensor(v) else copy.copy(v)
+        return other
+
+    def __getitem__(self, index):
+        if isinstance(index, int):
+            index = [index]
+        other = self.clone()
+        n = None
+        for k in self._tensor_props():
+            v = other.__dict__[k]
+            if v.dim() >= 1 and v.shape[0] == self._N:
+                sel = v[index]
+                setattr(other, k, sel)
+                n = sel.shape[0]
+        if n is not None:
+            other._N = n
+        return other

@@ -1,0 +1,469 @@
+// Coarse-to-fine mesh rasteriser for sm_100a: per-tile face binning (count -> allocate -> fill),
+// per-pixel top-K fine pass, and the backward scatter.  Replaces pytorch3d._C.rasterize_meshes /
+// rasterize_meshes_backward (reference call sites: torch_renderer.py:113, camera_pose_optimizer.py:244,
+// batch_rendering_test.py:274); semantics: SURVEY.md Appendix A3-A5, A9.
+//
+// Differences from the upstream design, all deliberate:
+//  * bin lists are compact (a global cursor hands every tile exactly `count` slots) instead of
+//    N*BH*BW*M fixed slots, so the fine pass never scans sentinels;
+//  * a tile whose list does not fit the workspace is rasterised by scanning the whole mesh --
+//    faces are never dropped;
+//  * the per-pixel queue keeps only (z, face) -- 8 B per entry, in registers for K=1 and in
+//    shared memory otherwise -- and barycentrics/distances are recomputed for the K survivors;
+//  * ties are broken by (z, face index), so the result does not depend on list order.
+#include "raster_math.cuh"
+
+namespace trb {
+
+struct TileGrid {
+  int tiles_x, tiles_y, ltx, lty;
+};
+
+__host__ inline TileGrid make_tile_grid(int H, int W, int K) {
+  TileGrid g;
+  if (K <= 24) { g.ltx = 4; g.lty = 4; } else { g.ltx = 3; g.lty = 3; }
+  g.tiles_x = (W + (1 << g.ltx) - 1) >> g.ltx;
+  g.tiles_y = (H + (1 << g.lty) - 1) >> g.lty;
+  return g;
+}
+
+struct WsLayout {
+  size_t header, count, offset, fill, pairs, total;
+};
+
+__host__ inline WsLayout make_ws_layout(int N, const TileGrid& g, int64_t pair_capacity) {
+  WsLayout w;
+  const size_t ntiles = (size_t)N * g.tiles_x * g.tiles_y;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  w.header = 0;
+  w.count = align(64);
+  w.fill = w.count + align(ntiles * 4);
+  w.offset = w.fill + align(ntiles * 4);
+  w.pairs = w.offset + align(ntiles * 4);
+  w.total = w.pairs + align((size_t)pair_capacity * 4);
+  return w;
+}
+
+__device__ __forceinline__ FaceXYZ load_face(const float* __restrict__ verts,
+                                             const int* __restrict__ faces, const trb_view& vd,
+                                             int local_face) {
+  const int r = vd.face_start + local_face;
+  int i0, i1, i2;
+  if (faces != nullptr) {
+    i0 = __ldg(faces + 3 * (size_t)r) + vd.vert_delta;
+    i1 = __ldg(faces + 3 * (size_t)r + 1) + vd.vert_delta;
+    i2 = __ldg(faces + 3 * (size_t)r + 2) + vd.vert_delta;
+  } else {
+    i0 = 3 * r; i1 = i0 + 1; i2 = i0 + 2;
+  }
+  FaceXYZ v;
+  const float* p0 = verts + 3 * (size_t)i0;
+  const float* p1 = verts + 3 * (size_t)i1;
+  const float* p2 = verts + 3 * (size_t)i2;
+  v.x0 = __ldg(p0); v.y0 = __ldg(p0 + 1); v.z0 = __ldg(p0 + 2);
+  v.x1 = __ldg(p1); v.y1 = __ldg(p1 + 1); v.z1 = __ldg(p1 + 2);
+  v.x2 = __ldg(p2); v.y2 = __ldg(p2 + 1); v.z2 = __ldg(p2 + 2);
+  return v;
+}
+
+// Conservative range of pixel indices (in output order) whose centre can lie in [lo, hi].
+// Pixel-centre i' = S-1-i has NDC coordinate -off + (range*i' + off)/S  (A3).
+__device__ __forceinline__ void pixel_range(float lo, float hi, int S1, int S2, int& p_lo, int& p_hi) {
+  float range = 2.0f;
+  if (S1 > S2) range = (float)S1 * 2.0f / (float)S2;
+  const float off = 0.5f * range;
+  const float scale = (float)S1 / range;
+  float a = (lo + off) * scale - 0.5f;  // fractional flipped index of lo
+  float b = (hi + off) * scale - 0.5f;
+  a = fminf(fmaxf(a, -2.0f), (float)S1 + 1.0f);
+  b = fminf(fmaxf(b, -2.0f), (float)S1 + 1.0f);
+  int i_lo = (int)floorf(a) - 1, i_hi = (int)ceilf(b) + 1;  // +-1 px of slack (>> fp error)
+  i_lo = max(i_lo, 0); i_hi = min(i_hi, S1 - 1);
+  p_lo = S1 - 1 - i_hi; p_hi = S1 - 1 - i_lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Binning.  One thread per (view, face): count (FILL=false) or write (FILL=true) the face into
+// every tile its blur-inflated bounding box can touch.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
+                 const trb_view* __restrict__ views, int H, int W, TileGrid tg, float sqrt_blur,
+                 bool cull, int* __restrict__ tile_count, int* __restrict__ tile_fill,
+                 const int* __restrict__ tile_offset, int* __restrict__ pairs) {
+  const int n = blockIdx.y;
+  const trb_view vd = views[n];
+  const int lf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lf >= vd.face_count) return;
+  const FaceXYZ v = load_face(verts, faces, vd, lf);
+  if (!face_is_drawable(v, cull)) return;
+  const float xmin = min3f(v.x0, v.x1, v.x2) - sqrt_blur, xmax = max3f(v.x0, v.x1, v.x2) + sqrt_blur;
+  const float ymin = min3f(v.y0, v.y1, v.y2) - sqrt_blur, ymax = max3f(v.y0, v.y1, v.y2) + sqrt_blur;
+  int px0, px1, py0, py1;
+  pixel_range(xmin, xmax, W, H, px0, px1);
+  pixel_range(ymin, ymax, H, W, py0, py1);
+  if (px0 > px1 || py0 > py1) return;
+  const int tx0 = px0 >> tg.ltx, tx1 = px1 >> tg.ltx, ty0 = py0 >> tg.lty, ty1 = py1 >> tg.lty;
+  const int tbase = n * tg.tiles_x * tg.tiles_y;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const int t = tbase + ty * tg.tiles_x + tx;
+      if (!FILL) {
+        atomicAdd(tile_count + t, 1);
+      } else {
+        const int off = tile_offset[t];
+        if (off >= 0) pairs[off + atomicAdd(tile_fill + t, 1)] = lf;
+      }
+    }
+}
+
+// Hands every non-empty tile a contiguous slice of `pairs` (order between tiles is irrelevant).
+__global__ void __launch_bounds__(256)
+alloc_tiles_kernel(const int* __restrict__ tile_count, int* __restrict__ tile_offset, int ntiles,
+                   int* __restrict__ header, long long pair_capacity) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = t < ntiles ? tile_count[t] : 0;
+  // warp-aggregated reservation
+  const int lane = threadIdx.x & 31;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && warp_total > 0) {
+    // header[0..1] is a 64-bit cursor so that the needed total is exact even past capacity
+    base = (int)min((unsigned long long)0x7fffffff,
+                    atomicAdd((unsigned long long*)header, (unsigned long long)warp_total));
+  }
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (t < ntiles) {
+    const long long off = (long long)base + (incl - c);
+    const bool fits = off + c <= pair_capacity;
+    tile_offset[t] = (c == 0) ? 0 : (fits ? (int)off : -1);
+    if (c > 0 && !fits) atomicAdd(header + 2, 1);
+  }
+}
+
+__global__ void write_stats_kernel(const int* __restrict__ header, long long pair_capacity,
+                                   int* __restrict__ stats) {
+  const unsigned long long need = *(const unsigned long long*)header;
+  stats[0] = (int)min(need, (unsigned long long)0x7fffffff);
+  stats[1] = header[2];
+  stats[2] = (int)min(pair_capacity, (long long)0x7fffffff);
+  stats[3] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fine pass: one CTA per (view, tile), one thread per pixel.  The tile's face list is staged
+// through shared memory NT faces at a time (each thread fetches one face and precomputes its
+// inflated bbox); every thread then walks the staged faces with broadcast LDS reads.
+template <int LTX, int LTY, bool PERSP, bool CLIP, bool K1>
+__global__ void __launch_bounds__((1 << LTX) * (1 << LTY))
+raster_fine_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
+                   const trb_view* __restrict__ views, int H, int W, int K, float blur_radius,
+                   float sqrt_blur, bool cull, TileGrid tg, const int* __restrict__ tile_count,
+                   const int* __restrict__ tile_offset, const int* __restrict__ pairs,
+                   long long* __restrict__ out_p2f, float* __restrict__ out_z,
+                   float* __restrict__ out_bary, float* __restrict__ out_d) {
+  constexpr int TX = 1 << LTX, TY = 1 << LTY, NT = TX * TY;
+  __shared__ float4 s_bb[NT];  // xmin, xmax, ymin, ymax (blur inflated; empty when undrawable)
+  __shared__ float4 s_va[NT];  // x0 y0 z0 x1
+  __shared__ float4 s_vb[NT];  // y1 z1 x2 y2
+  __shared__ float s_vc[NT];   // z2
+  __shared__ int s_id[NT];
+  extern __shared__ unsigned char s_dyn[];  // K>1: float kz[K][NT]; int kf[K][NT]
+  float* kz = reinterpret_cast<float*>(s_dyn);
+  int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)(K1 ? 0 : K) * NT;
+
+  const int n = blockIdx.z;
+  const trb_view vd = views[n];
+  const int tid = threadIdx.x;
+  const int xi = blockIdx.x * TX + (tid & (TX - 1));
+  const int yi = blockIdx.y * TY + (tid >> LTX);
+  const bool live = (xi < W) && (yi < H);
+  const float px = pix_to_ndc(W - 1 - xi, W, H);
+  const float py = pix_to_ndc(H - 1 - yi, H, W);
+
+  const int t = (n * tg.tiles_y + blockIdx.y) * tg.tiles_x + blockIdx.x;
+  int nlist = tile_count[t];
+  const int off = tile_offset[t];
+  const bool overflow = (nlist > 0) && (off < 0);
+  if (overflow) nlist = vd.face_count;
+
+  int cnt = 0;
+  float best_z = 0.0f; int best_f = -1; Sample best_s = {0, 0, 0, 0, 0};
+
+  for (int base = 0; base < nlist; base += NT) {
+    const int j = base + tid;
+    float4 bb = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
+    if (j < nlist) {
+      const int lf = overflow ? j : pairs[off + j];
+      const FaceXYZ v = load_face(verts, faces, vd, lf);
+      const bool ok = overflow ? face_is_drawable(v, cull) : true;
+      if (ok) {
+        bb.x = fsub(min3f(v.x0, v.x1, v.x2), sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), sqrt_blur);
+        bb.z = fsub(min3f(v.y0, v.y1, v.y2), sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), sqrt_blur);
+      }
+      s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
+      s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
+      s_vc[tid] = v.z2;
+      s_id[tid] = lf;
+    }
+    s_bb[tid] = bb;
+    __syncthreads();
+    const int m = min(NT, nlist - base);
+    if (live) {
+      for (int q = 0; q < m; ++q) {
+        const float4 b = s_bb[q];
+        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
+        const float4 a = s_va[q], c = s_vb[q];
+        FaceXYZ v;
+        v.x0 = a.x; v.y0 = a.y; v.z0 = a.z; v.x1 = a.w;
+        v.y1 = c.x; v.z1 = c.y; v.x2 = c.z; v.y2 = c.w; v.z2 = s_vc[q];
+        Sample s;
+        if (!eval_pixel_face<PERSP, CLIP>(v, px, py, blur_radius, s)) continue;
+        const int f = s_id[q];
+        if (K1) {
+          if (best_f < 0 || cand_less(s.z, f, best_z, best_f)) { best_z = s.z; best_f = f; best_s = s; }
+        } else {
+          if (cnt == K && !cand_less(s.z, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
+          int pos = cnt < K ? cnt : K - 1;
+          while (pos > 0 && cand_less(s.z, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
+            kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
+            kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
+            --pos;
+          }
+          kz[pos * NT + tid] = s.z; kf[pos * NT + tid] = f;
+          if (cnt < K) ++cnt;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!live) return;
+
+  const size_t pix = ((size_t)n * H + yi) * W + xi;
+  if (K1) {
+    const bool hit = best_f >= 0;
+    st_cs(out_p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
+    st_cs(out_z + pix, hit ? best_s.z : -1.0f);
+    st_cs(out_d + pix, hit ? best_s.d : -1.0f);
+    st_cs(out_bary + pix * 3 + 0, hit ? best_s.c0 : -1.0f);
+    st_cs(out_bary + pix * 3 + 1, hit ? best_s.c1 : -1.0f);
+    st_cs(out_bary + pix * 3 + 2, hit ? best_s.c2 : -1.0f);
+  } else {
+    const size_t o = pix * K;
+    for (int k = 0; k < K; ++k) {
+      Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+      long long pf = -1;
+      if (k < cnt) {
+        const int f = kf[k * NT + tid];
+        const FaceXYZ v = load_face(verts, faces, vd, f);
+        eval_pixel_face<PERSP, CLIP>(v, px, py, blur_radius, s);
+        pf = (long long)vd.p2f_base + f;
+      }
+      st_cs(out_p2f + o + k, pf);
+      st_cs(out_z + o + k, s.z);
+      st_cs(out_d + o + k, s.d);
+      st_cs(out_bary + (o + k) * 3 + 0, s.c0);
+      st_cs(out_bary + (o + k) * 3 + 1, s.c1);
+      st_cs(out_bary + (o + k) * 3 + 2, s.c2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward: one thread per pixel, k in the inner loop so that the 32 lanes of a warp hold
+// horizontally adjacent pixels of the same layer -- they mostly hit the same face, and
+// warp_aggregated_add turns 32 x 9 atomics into 9.
+template <bool PERSP, bool CLIP>
+__global__ void __launch_bounds__(256)
+raster_backward_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
+                       const trb_view* __restrict__ views, int N, int H, int W, int K,
+                       const long long* __restrict__ p2f, const float* __restrict__ grad_z,
+                       const float* __restrict__ grad_bary, const float* __restrict__ grad_d,
+                       float* __restrict__ grad_verts) {
+  const long long npix = (long long)N * H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = pix < npix;
+  int n = 0, xi = 0, yi = 0;
+  if (live) {
+    n = (int)(pix / ((long long)H * W));
+    const int rem = (int)(pix - (long long)n * H * W);
+    yi = rem / W; xi = rem - yi * W;
+  }
+  const trb_view vd = views[n];
+  const float px = pix_to_ndc(W - 1 - xi, W, H);
+  const float py = pix_to_ndc(H - 1 - yi, H, W);
+  for (int k = 0; k < K; ++k) {
+    const long long f = live ? p2f[pix * K + k] : -1;
+    if (!__any_sync(0xffffffffu, f >= 0)) break;  // layers are sorted: nothing further either
+    float g[9];
+    int i0 = 0, i1 = 0, i2 = 0;
+    int key = -1;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+    if (f >= 0) {
+      const int lf = (int)(f - vd.p2f_base);
+      const int r = vd.face_start + lf;
+      if (faces != nullptr) {
+        i0 = __ldg(faces + 3 * (size_t)r) + vd.vert_delta;
+        i1 = __ldg(faces + 3 * (size_t)r + 1) + vd.vert_delta;
+        i2 = __ldg(faces + 3 * (size_t)r + 2) + vd.vert_delta;
+      } else {
+        i0 = 3 * r; i1 = i0 + 1; i2 = i0 + 2;
+      }
+      const FaceXYZ v = load_face(verts, faces, vd, lf);
+      const long long s = pix * K + k;
+      sample_backward<PERSP, CLIP>(v, px, py, grad_z ? grad_z[s] : 0.0f,
+                                   grad_bary ? grad_bary[s * 3] : 0.0f,
+                                   grad_bary ? grad_bary[s * 3 + 1] : 0.0f,
+                                   grad_bary ? grad_bary[s * 3 + 2] : 0.0f,
+                                   grad_d ? grad_d[s] : 0.0f, g);
+      key = (int)f;
+    }
+    float* const dst[9] = {grad_verts + 3 * (size_t)i0, grad_verts + 3 * (size_t)i0 + 1,
+                           grad_verts + 3 * (size_t)i0 + 2, grad_verts + 3 * (size_t)i1,
+                           grad_verts + 3 * (size_t)i1 + 1, grad_verts + 3 * (size_t)i1 + 2,
+                           grad_verts + 3 * (size_t)i2, grad_verts + 3 * (size_t)i2 + 1,
+                           grad_verts + 3 * (size_t)i2 + 2};
+    warp_aggregated_add<9>(key, g, dst);
+  }
+}
+
+template <int LTX, int LTY, bool K1>
+static int launch_fine(bool persp, bool clip, dim3 grid, size_t dyn_smem, cudaStream_t st,
+                       const float* verts, const int* faces, const trb_view* views, int H, int W,
+                       int K, float blur, float sqrt_blur, bool cull, TileGrid tg, const int* tc,
+                       const int* to, const int* pairs, long long* p2f, float* z, float* bary,
+                       float* d) {
+  constexpr int NT = (1 << LTX) * (1 << LTY);
+#define TRB_FINE(P, C)                                                                           \
+  do {                                                                                           \
+    auto kern = raster_fine_kernel<LTX, LTY, P, C, K1>;                                          \
+    if (dyn_smem > 0)                                                                            \
+      TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                        (int)dyn_smem));                                         \
+    kern<<<grid, NT, dyn_smem, st>>>(verts, faces, views, H, W, K, blur, sqrt_blur, cull, tg, tc, \
+                                     to, pairs, p2f, z, bary, d);                                \
+  } while (0)
+  if (persp && clip) TRB_FINE(true, true);
+  else if (persp) TRB_FINE(true, false);
+  else if (clip) TRB_FINE(false, true);
+  else TRB_FINE(false, false);
+#undef TRB_FINE
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" int trb_raster_workspace_bytes(int N, int H, int W, int K, int64_t pair_capacity,
+                                          size_t* bytes) {
+  if (!bytes || N < 0 || H < 1 || W < 1 || pair_capacity < 0) return TRB_ERR_BAD_ARG;
+  if (K < 1) return TRB_ERR_BAD_ARG;
+  if (K > TRB_MAX_FACES_PER_PIXEL) return TRB_ERR_K_TOO_LARGE;
+  const TileGrid tg = make_tile_grid(H, W, K);
+  *bytes = make_ws_layout(N, tg, pair_capacity).total;
+  return TRB_OK;
+}
+
+extern "C" int trb_raster_forward(const float* verts_ndc, const int32_t* faces, const trb_view* views,
+                                  int N, int max_face_count, int H, int W, int K, float blur_radius,
+                                  uint32_t flags, int64_t pair_capacity, void* workspace,
+                                  size_t workspace_bytes, int64_t* pix_to_face, float* zbuf,
+                                  float* bary, float* dists, int32_t* stats, int device,
+                                  trb_stream_t stream) {
+  if (N < 0 || H < 1 || W < 1 || K < 1 || max_face_count < 0 || pair_capacity < 0 ||
+      !(blur_radius >= 0.0f))
+    return TRB_ERR_BAD_ARG;
+  if (K > TRB_MAX_FACES_PER_PIXEL) return TRB_ERR_K_TOO_LARGE;
+  if (N == 0) return TRB_OK;
+  if (N > 65535) return TRB_ERR_BAD_ARG;
+  if (!views || !pix_to_face || !zbuf || !bary || !dists || !workspace) return TRB_ERR_BAD_ARG;
+  if (max_face_count > 0 && !verts_ndc) return TRB_ERR_BAD_ARG;
+  const TileGrid tg = make_tile_grid(H, W, K);
+  const WsLayout ws = make_ws_layout(N, tg, pair_capacity);
+  if (workspace_bytes < ws.total) return TRB_ERR_WORKSPACE;
+  TRB_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* wsb = (unsigned char*)workspace;
+  int* header = (int*)(wsb + ws.header);
+  int* tile_count = (int*)(wsb + ws.count);
+  int* tile_fill = (int*)(wsb + ws.fill);
+  int* tile_offset = (int*)(wsb + ws.offset);
+  int* pairs = (int*)(wsb + ws.pairs);
+  const int ntiles = N * tg.tiles_x * tg.tiles_y;
+  // header, tile_count and tile_fill are contiguous: one memset
+  TRB_CUDA_TRY(cudaMemsetAsync(wsb, 0, ws.offset, st));
+  const float sqrt_blur = sqrtf(blur_radius);
+  const bool cull = flags & TRB_CULL_BACKFACES;
+  if (max_face_count > 0) {
+    dim3 bgrid(ceil_div(max_face_count, 256), N);
+    bin_faces_kernel<false><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
+                                                   tile_count, tile_fill, tile_offset, pairs);
+    TRB_LAUNCH_CHECK();
+    alloc_tiles_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(tile_count, tile_offset, ntiles, header,
+                                                              (long long)pair_capacity);
+    TRB_LAUNCH_CHECK();
+    bin_faces_kernel<true><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
+                                                  tile_count, tile_fill, tile_offset, pairs);
+    TRB_LAUNCH_CHECK();
+  }
+  const dim3 grid(tg.tiles_x, tg.tiles_y, N);
+  const bool persp = flags & TRB_PERSPECTIVE_CORRECT, clip = flags & TRB_CLIP_BARYCENTRIC;
+  long long* p2f = (long long*)pix_to_face;
+  int rc;
+  if (K == 1) {
+    rc = launch_fine<4, 4, true>(persp, clip, grid, 0, st, verts_ndc, faces, views, H, W, K, blur_radius,
+                                 sqrt_blur, cull, tg, tile_count, tile_offset, pairs, p2f, zbuf, bary,
+                                 dists);
+  } else if (tg.ltx == 4) {
+    rc = launch_fine<4, 4, false>(persp, clip, grid, (size_t)K * 8 * 256, st, verts_ndc, faces, views, H,
+                                  W, K, blur_radius, sqrt_blur, cull, tg, tile_count, tile_offset, pairs,
+                                  p2f, zbuf, bary, dists);
+  } else {
+    rc = launch_fine<3, 3, false>(persp, clip, grid, (size_t)K * 8 * 64, st, verts_ndc, faces, views, H,
+                                  W, K, blur_radius, sqrt_blur, cull, tg, tile_count, tile_offset, pairs,
+                                  p2f, zbuf, bary, dists);
+  }
+  if (rc != TRB_OK) return rc;
+  if (stats) {
+    write_stats_kernel<<<1, 1, 0, st>>>(header, (long long)pair_capacity, stats);
+    TRB_LAUNCH_CHECK();
+  }
+  return TRB_OK;
+}
+
+extern "C" int trb_raster_backward(const float* verts_ndc, const int32_t* faces, const trb_view* views,
+                                   int N, int H, int W, int K, uint32_t flags,
+                                   const int64_t* pix_to_face, const float* grad_zbuf,
+                                   const float* grad_bary, const float* grad_dists,
+                                   float* grad_verts_ndc, int device, trb_stream_t stream) {
+  if (N < 0 || H < 1 || W < 1 || K < 1) return TRB_ERR_BAD_ARG;
+  if (K > TRB_MAX_FACES_PER_PIXEL) return TRB_ERR_K_TOO_LARGE;
+  if (N == 0) return TRB_OK;
+  if (!verts_ndc || !views || !pix_to_face || !grad_verts_ndc) return TRB_ERR_BAD_ARG;
+  TRB_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long npix = (long long)N * H * W;
+  const unsigned blocks = (unsigned)ceil_div64(npix, 256);
+  const bool persp = flags & TRB_PERSPECTIVE_CORRECT, clip = flags & TRB_CLIP_BARYCENTRIC;
+  const long long* p2f = (const long long*)pix_to_face;
+#define TRB_BWD(P, C)                                                                            \
+  raster_backward_kernel<P, C><<<blocks, 256, 0, st>>>(verts_ndc, faces, views, N, H, W, K, p2f,   \
+                                                       grad_zbuf, grad_bary, grad_dists,          \
+                                                       grad_verts_ndc)
+  if (persp && clip) TRB_BWD(true, true);
+  else if (persp) TRB_BWD(true, false);
+  else if (clip) TRB_BWD(false, true);
+  else TRB_BWD(false, false);
+#undef TRB_BWD
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}

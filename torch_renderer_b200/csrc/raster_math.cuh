@@ -1,0 +1,253 @@
+// Per-(pixel, face) arithmetic of the rasteriser, SURVEY.md Appendix A3/A4/A9.
+//
+// Everything that feeds a coverage / ordering decision is written with the round-to-nearest
+// intrinsics (__fmul_rn, __fadd_rn, __fsub_rn, __fdiv_rn): ptxas never contracts those into
+// FMAs, so the operator sequence is one IEEE fp32 operation per step -- the same sequence the
+// CPU oracle (oracle/trb_oracle.c, built with -ffp-contract=off) executes.  That is what makes
+// pix_to_face bit-exact between the two, independent of the nvcc flags of the including TU.
+#pragma once
+#include "trb_common.cuh"
+
+namespace trb {
+
+constexpr float kEps = 1e-8f;
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// A3: NDC coordinate of pixel-centre i along an axis of S1 pixels (other axis S2).
+__device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
+  float range = 2.0f;
+  if (S1 > S2) range = fdiv(fmul((float)S1, range), (float)S2);
+  const float offset = fdiv(range, 2.0f);
+  return fadd(-offset, fdiv(fadd(fmul(range, (float)i), offset), (float)S1));
+}
+
+// A4.1: edge(p; a, b) = (p.x-a.x)(b.y-a.y) - (p.y-a.y)(b.x-a.x)
+__device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
+  return fsub(fmul(fsub(px, ax), fsub(by, ay)), fmul(fsub(py, ay), fsub(bx, ax)));
+}
+
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// A4.7: squared distance from p to the segment ab.
+__device__ __forceinline__ float point_segment_d2(float px, float py, float ax, float ay, float bx,
+                                                  float by) {
+  const float bax = fsub(bx, ax), bay = fsub(by, ay);
+  const float l2 = fadd(fmul(bax, bax), fmul(bay, bay));
+  if (l2 <= kEps) {
+    const float dx = fsub(px, bx), dy = fsub(py, by);
+    return fadd(fmul(dx, dx), fmul(dy, dy));
+  }
+  float t = fdiv(fadd(fmul(bax, fsub(px, ax)), fmul(bay, fsub(py, ay))), l2);
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float qx = fadd(ax, fmul(t, bax)), qy = fadd(ay, fmul(t, bay));
+  const float dx = fsub(qx, px), dy = fsub(qy, py);
+  return fadd(fmul(dx, dx), fmul(dy, dy));
+}
+
+struct FaceXYZ {
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+};
+
+// Per-face (pixel independent) validity, A4.2 minus the bbox/pixel part.
+__device__ __forceinline__ bool face_is_drawable(const FaceXYZ& v, bool cull_backfaces) {
+  const float zmin = min3f(v.z0, v.z1, v.z2), zmax = max3f(v.z0, v.z1, v.z2);
+  const float face_area = edge_fn(v.x0, v.y0, v.x1, v.y1, v.x2, v.y2);
+  const bool back_face = face_area < 0.0f;
+  const bool zero_area = (face_area <= kEps) && (face_area >= -kEps);
+  // written so that NaN coordinates make the face undrawable
+  if (!(zmin >= kEps)) return false;
+  if (zmax < 0.0f || zero_area || (cull_backfaces && back_face)) return false;
+  return true;
+}
+
+struct Sample {
+  float z, d, c0, c1, c2;
+};
+
+// A4 steps 3-9 for a face already known to be drawable and whose inflated bbox contains p.
+// Returns false when the pixel is not a candidate of the face.
+template <bool PERSP, bool CLIP>
+__device__ __forceinline__ bool eval_pixel_face(const FaceXYZ& v, float px, float py,
+                                                float blur_radius, Sample& out) {
+  const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+  const float w0 = fdiv(edge_fn(px, py, v.x1, v.y1, v.x2, v.y2), area);
+  const float w1 = fdiv(edge_fn(px, py, v.x2, v.y2, v.x0, v.y0), area);
+  const float w2 = fdiv(edge_fn(px, py, v.x0, v.y0, v.x1, v.y1), area);
+  float b0 = w0, b1 = w1, b2 = w2;
+  if (PERSP) {
+    const float t0 = fmul(fmul(w0, v.z1), v.z2);
+    const float t1 = fmul(fmul(w1, v.z0), v.z2);
+    const float t2 = fmul(fmul(w2, v.z0), v.z1);
+    const float den = fmaxf(fadd(fadd(t0, t1), t2), kEps);
+    b0 = fdiv(t0, den); b1 = fdiv(t1, den); b2 = fdiv(t2, den);
+  }
+  float c0 = b0, c1 = b1, c2 = b2;
+  if (CLIP) {
+    c0 = fmaxf(b0, 0.0f); c1 = fmaxf(b1, 0.0f); c2 = fmaxf(b2, 0.0f);
+    const float s = fmaxf(fadd(fadd(c0, c1), c2), 1e-5f);
+    c0 = fdiv(c0, s); c1 = fdiv(c1, s); c2 = fdiv(c2, s);
+  }
+  const float pz = fadd(fadd(fmul(c0, v.z0), fmul(c1, v.z1)), fmul(c2, v.z2));
+  if (pz < 0.0f) return false;
+  const bool inside = (b0 > 0.0f) && (b1 > 0.0f) && (b2 > 0.0f);
+  const float e01 = point_segment_d2(px, py, v.x0, v.y0, v.x1, v.y1);
+  const float e02 = point_segment_d2(px, py, v.x0, v.y0, v.x2, v.y2);
+  const float e12 = point_segment_d2(px, py, v.x1, v.y1, v.x2, v.y2);
+  const float dist = min3f(e01, e02, e12);
+  if (!inside && dist >= blur_radius) return false;
+  out.z = pz; out.d = inside ? -dist : dist;
+  out.c0 = c0; out.c1 = c1; out.c2 = c2;
+  return true;
+}
+
+// (z, face) lexicographic order, A5.
+__device__ __forceinline__ bool cand_less(float za, int fa, float zb, int fb) {
+  return (za < zb) || (za == zb && fa < fb);
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of one sample (A9).  g[9] receives d loss / d (x0,y0,z0,x1,y1,z1,x2,y2,z2).
+// The forward quantities are recomputed with the exact forward sequence so that `inside`
+// and the clamps take the same branch as in the forward pass; the gradient arithmetic itself
+// is ordinary fp32 (FMAs allowed).
+__device__ __forceinline__ void edge_bwd(float px, float py, float ax, float ay, float bx, float by,
+                                         float g, float& gax, float& gay, float& gbx, float& gby) {
+  gax += g * (py - by); gay += g * (bx - px);
+  gbx += g * (ay - py); gby += g * (px - ax);
+}
+
+__device__ __forceinline__ void point_segment_bwd(float px, float py, float ax, float ay, float bx,
+                                                  float by, float g, float& gax, float& gay,
+                                                  float& gbx, float& gby) {
+  const float bax = fsub(bx, ax), bay = fsub(by, ay);
+  const float l2 = fadd(fmul(bax, bax), fmul(bay, bay));
+  if (l2 <= kEps) {
+    gbx += g * 2.0f * (bx - px); gby += g * 2.0f * (by - py);
+    return;
+  }
+  float t = fdiv(fadd(fmul(bax, fsub(px, ax)), fmul(bay, fsub(py, ay))), l2);
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float dx = (ax + t * bax) - px, dy = (ay + t * bay) - py;
+  const float ga = g * (1.0f - t) * 2.0f, gb = g * t * 2.0f;
+  gax += ga * dx; gay += ga * dy;
+  gbx += gb * dx; gby += gb * dy;
+}
+
+template <bool PERSP, bool CLIP>
+__device__ __forceinline__ void sample_backward(const FaceXYZ& v, float px, float py, float gz,
+                                                float gb0, float gb1, float gb2, float gd,
+                                                float g[9]) {
+  const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+  const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
+  const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
+  const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
+  const float w0 = fdiv(e0, area), w1 = fdiv(e1, area), w2 = fdiv(e2, area);
+  float b0 = w0, b1 = w1, b2 = w2, den = 1.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, tsum = 0.f;
+  if (PERSP) {
+    t0 = fmul(fmul(w0, v.z1), v.z2);
+    t1 = fmul(fmul(w1, v.z0), v.z2);
+    t2 = fmul(fmul(w2, v.z0), v.z1);
+    tsum = fadd(fadd(t0, t1), t2);
+    den = fmaxf(tsum, kEps);
+    b0 = fdiv(t0, den); b1 = fdiv(t1, den); b2 = fdiv(t2, den);
+  }
+  float c0 = b0, c1 = b1, c2 = b2, m0 = b0, m1 = b1, m2 = b2, s = 1.0f, ssum = 0.f;
+  if (CLIP) {
+    m0 = fmaxf(b0, 0.0f); m1 = fmaxf(b1, 0.0f); m2 = fmaxf(b2, 0.0f);
+    ssum = fadd(fadd(m0, m1), m2);
+    s = fmaxf(ssum, 1e-5f);
+    c0 = fdiv(m0, s); c1 = fdiv(m1, s); c2 = fdiv(m2, s);
+  }
+  const bool inside = (b0 > 0.0f) && (b1 > 0.0f) && (b2 > 0.0f);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+  // zbuf = c . z
+  g[2] += gz * c0; g[5] += gz * c1; g[8] += gz * c2;
+  const float gc0 = gb0 + gz * v.z0, gc1 = gb1 + gz * v.z1, gc2 = gb2 + gz * v.z2;
+  float gbb0 = gc0, gbb1 = gc1, gbb2 = gc2;
+  if (CLIP) {
+    const float inv_s = 1.0f / s;
+    float gs = -(gc0 * m0 + gc1 * m1 + gc2 * m2) * inv_s * inv_s;
+    if (!(ssum > 1e-5f)) gs = 0.0f;
+    gbb0 = b0 > 0.0f ? gc0 * inv_s + gs : 0.0f;
+    gbb1 = b1 > 0.0f ? gc1 * inv_s + gs : 0.0f;
+    gbb2 = b2 > 0.0f ? gc2 * inv_s + gs : 0.0f;
+  }
+  float gw0 = gbb0, gw1 = gbb1, gw2 = gbb2;
+  if (PERSP) {
+    const float inv_den = 1.0f / den;
+    float gden = -(gbb0 * t0 + gbb1 * t1 + gbb2 * t2) * inv_den * inv_den;
+    if (!(tsum > kEps)) gden = 0.0f;
+    const float gt0 = gbb0 * inv_den + gden, gt1 = gbb1 * inv_den + gden, gt2 = gbb2 * inv_den + gden;
+    gw0 = gt0 * v.z1 * v.z2; gw1 = gt1 * v.z0 * v.z2; gw2 = gt2 * v.z0 * v.z1;
+    g[2] += gt1 * w1 * v.z2 + gt2 * w2 * v.z1;
+    g[5] += gt0 * w0 * v.z2 + gt2 * w2 * v.z0;
+    g[8] += gt0 * w0 * v.z1 + gt1 * w1 * v.z0;
+  }
+  const float inv_area = 1.0f / area;
+  const float ge0 = gw0 * inv_area, ge1 = gw1 * inv_area, ge2 = gw2 * inv_area;
+  const float garea = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * inv_area * inv_area;
+  edge_bwd(px, py, v.x1, v.y1, v.x2, v.y2, ge0, g[3], g[4], g[6], g[7]);
+  edge_bwd(px, py, v.x2, v.y2, v.x0, v.y0, ge1, g[6], g[7], g[0], g[1]);
+  edge_bwd(px, py, v.x0, v.y0, v.x1, v.y1, ge2, g[0], g[1], g[3], g[4]);
+  g[6] += garea * (v.y1 - v.y0); g[7] += garea * (v.x0 - v.x1);
+  g[0] += garea * (v.y2 - v.y1); g[1] += garea * (v.x1 - v.x2);
+  g[3] += garea * (v.y0 - v.y2); g[4] += garea * (v.x2 - v.x0);
+  if (gd != 0.0f) {
+    const float e01 = point_segment_d2(px, py, v.x0, v.y0, v.x1, v.y1);
+    const float e02 = point_segment_d2(px, py, v.x0, v.y0, v.x2, v.y2);
+    const float e12 = point_segment_d2(px, py, v.x1, v.y1, v.x2, v.y2);
+    const float gsd = inside ? -gd : gd;
+    if (e01 <= e02 && e01 <= e12)
+      point_segment_bwd(px, py, v.x0, v.y0, v.x1, v.y1, gsd, g[0], g[1], g[3], g[4]);
+    else if (e02 <= e01 && e02 <= e12)
+      point_segment_bwd(px, py, v.x0, v.y0, v.x2, v.y2, gsd, g[0], g[1], g[6], g[7]);
+    else
+      point_segment_bwd(px, py, v.x1, v.y1, v.x2, v.y2, gsd, g[3], g[4], g[6], g[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-aggregated scatter: lanes of a warp that hold contributions for the same `key`
+// (a face or vertex id; < 0 = lane has nothing) are summed with shuffles and issued as ONE
+// atomicAdd per value.  When the warp holds many distinct keys (small-triangle regime) the
+// per-lane atomics hit distinct addresses anyway, so they are issued directly.
+template <int NV>
+__device__ __forceinline__ void warp_aggregated_add(int key, const float (&val)[NV],
+                                                    float* const (&dst)[NV]) {
+  const unsigned active = __activemask();
+  const unsigned have = __ballot_sync(active, key >= 0);
+  if (have == 0) return;
+  const unsigned peers = __match_any_sync(active, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  const unsigned leaders = __ballot_sync(active, (lane == leader) && key >= 0);
+  const int ngroups = __popc(leaders);
+  if (active == 0xffffffffu && ngroups <= 4) {
+    unsigned todo = leaders;
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int k = __shfl_sync(0xffffffffu, key, l);
+      const bool mine = (key == k);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float s = mine ? val[i] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == l && s != 0.0f) atomicAdd(dst[i], s);
+      }
+    }
+  } else if (key >= 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (val[i] != 0.0f) atomicAdd(dst[i], val[i]);
+  }
+}
+
+}  // namespace trb

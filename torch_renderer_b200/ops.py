@@ -1,0 +1,352 @@
+"""Autograd wrappers over the C ABI (``include/trb.h``).  Host plumbing only: every tensor is
+allocated here through torch's caching allocator and handed to ``libtrb.so`` as a raw pointer with
+the current stream.  Mirrors PyTorch3D's ``_RasterizeFaceVerts`` / ``_InterpFaceAttrs`` autograd
+boundary (SURVEY.md layer L3); the reference reaches it through ``MeshRasterizer`` /
+``MeshRenderer`` (torch_renderer.py:97-108, camera_pose_optimizer.py:130-158).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ShadeConfig, check
+
+_launch_count = 0  # kernels launched through libtrb.so (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launch_count
+
+
+def _bump(n: int) -> None:
+    global _launch_count
+    _launch_count += n
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: torch_renderer_b200 runs on CUDA tensors only (got device {t.device}); "
+            "there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ViewTable:
+    """Device copy of the ``trb_view[N]`` table plus the host-side sizes the launches need."""
+    views: torch.Tensor          # int32 [N, 8] on device
+    host: torch.Tensor           # same on CPU
+    N: int
+    max_face_count: int
+    max_vert_count: int
+    total_ndc_verts: int
+    total_faces_packed: int      # upper bound (exclusive) of pix_to_face values
+    shared_mesh: bool
+    pair_capacity: int = 0
+    _pending: object = None      # (pinned stats, event) of the last forward
+
+    @staticmethod
+    def build(face_start, face_count, p2f_base, world_vert_start, vert_count, device, shared_mesh):
+        n = len(face_count)
+        host = torch.zeros((n, 8), dtype=torch.int32)
+        ndc_start = 0
+        for i in range(n):
+            host[i, 0] = face_start[i]
+            host[i, 1] = face_count[i]
+            host[i, 2] = ndc_start - world_vert_start[i]
+            host[i, 3] = p2f_base[i]
+            host[i, 4] = world_vert_start[i]
+            host[i, 5] = vert_count[i]
+            host[i, 6] = ndc_start
+            ndc_start += vert_count[i]
+        total_faces = max((p2f_base[i] + face_count[i] for i in range(n)), default=0)
+        if ndc_start * 3 >= 2**31 or total_faces >= 2**31:
+            raise ValueError("batch too large for int32 indexing; render the views in chunks")
+        return ViewTable(views=host.to(device), host=host, N=n,
+                         max_face_count=max(face_count, default=0),
+                         max_vert_count=max(vert_count, default=0), total_ndc_verts=ndc_start,
+                         total_faces_packed=total_faces, shared_mesh=shared_mesh)
+
+    def default_pair_capacity(self) -> int:
+        total_fv = int(self.host[:, 1].sum())
+        return int(min(max(8 * total_fv, 1 << 16), 1 << 28))
+
+    def poll_capacity(self) -> int:
+        """Non-blocking: grows the (tile, face) pair capacity when an earlier forward reported
+        that some tiles had to fall back to a whole-mesh scan.  Never synchronises."""
+        if self.pair_capacity == 0:
+            self.pair_capacity = self.default_pair_capacity()
+        if self._pending is not None:
+            stats, event = self._pending
+            if event.query():
+                needed = int(stats[0])
+                if needed > self.pair_capacity:
+                    self.pair_capacity = int(min(needed * 5 // 4 + 1024, (1 << 31) - 1))
+                self._pending = None
+        return self.pair_capacity
+
+
+# --------------------------------------------------------------------------------------------
+class _TransformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts_world, R, T, proj, table: ViewTable, perspective: bool):
+        _require_cuda(verts_world, "transform")
+        verts_world, R, T, proj = _f32c(verts_world), _f32c(R), _f32c(T), _f32c(proj)
+        dev = verts_world.device
+        out = torch.empty((table.total_ndc_verts, 3), dtype=torch.float32, device=dev)
+        check(_lib.lib().trb_transform_forward(
+            _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
+            table.max_vert_count, int(perspective), _ptr(out), dev.index, _stream(dev)), "transform")
+        _bump(1)
+        ctx.save_for_backward(verts_world, R, T, proj)
+        ctx.table, ctx.perspective = table, perspective
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        verts_world, R, T, proj = ctx.saved_tensors
+        table = ctx.table
+        dev = verts_world.device
+        need = ctx.needs_input_grad
+        g_v = torch.zeros_like(verts_world) if need[0] else None
+        g_R = torch.zeros_like(R) if need[1] else None
+        g_T = torch.zeros_like(T) if need[2] else None
+        g_p = torch.zeros_like(proj) if need[3] else None
+        grad_out = _f32c(grad_out)
+        check(_lib.lib().trb_transform_backward(
+            _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
+            table.max_vert_count, int(ctx.perspective), _ptr(grad_out), _ptr(g_v), _ptr(g_R), _ptr(g_T),
+            _ptr(g_p), dev.index, _stream(dev)), "transform backward")
+        _bump(1)
+        return g_v, g_R, g_T, g_p, None, None
+
+
+def transform_verts(verts_world, R, T, proj, table: ViewTable, perspective: bool = True):
+    """world -> NDC for every (view, vertex); returns f32 [table.total_ndc_verts, 3]."""
+    return _TransformFn.apply(verts_world, R, T, proj, table, perspective)
+
+
+# --------------------------------------------------------------------------------------------
+class _RasterizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts_ndc, faces, table: ViewTable, H, W, K, blur_radius, flags):
+        _require_cuda(verts_ndc, "rasterize_meshes")
+        verts_ndc = _f32c(verts_ndc)
+        dev = verts_ndc.device
+        L = _lib.lib()
+        N = table.N
+        cap = table.poll_capacity()
+        nbytes = ctypes.c_size_t(0)
+        check(L.trb_raster_workspace_bytes(N, H, W, K, cap, ctypes.byref(nbytes)), "rasterize_meshes")
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+        p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        stats = torch.empty((4,), dtype=torch.int32, device=dev)
+        check(L.trb_raster_forward(
+            _ptr(verts_ndc), _ptr(faces), _ptr(table.views), N, table.max_face_count, H, W, K,
+            float(blur_radius), int(flags), cap, _ptr(ws), nbytes.value, _ptr(p2f), _ptr(zbuf),
+            _ptr(bary), _ptr(dists), _ptr(stats), dev.index, _stream(dev)), "rasterize_meshes")
+        _bump(6 if table.max_face_count > 0 else 3)
+        if table._pending is None and not torch.cuda.is_current_stream_capturing():
+            host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
+            host_stats.copy_(stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            table._pending = (host_stats, ev)
+        ctx.save_for_backward(verts_ndc, faces, p2f)
+        ctx.table, ctx.dims, ctx.flags = table, (H, W, K), flags
+        ctx.mark_non_differentiable(p2f)
+        ctx.set_materialize_grads(False)
+        return p2f, zbuf, bary, dists
+
+    @staticmethod
+    def backward(ctx, _gp2f, g_zbuf, g_bary, g_dists):
+        verts_ndc, faces, p2f = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        table = ctx.table
+        H, W, K = ctx.dims
+        dev = verts_ndc.device
+        g_verts = torch.zeros_like(verts_ndc)
+        if g_zbuf is None and g_bary is None and g_dists is None:
+            return (g_verts,) + (None,) * 7
+        g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
+        g_bary = None if g_bary is None else _f32c(g_bary)
+        g_dists = None if g_dists is None else _f32c(g_dists)
+        check(_lib.lib().trb_raster_backward(
+            _ptr(verts_ndc), _ptr(faces), _ptr(table.views), table.N, H, W, K, int(ctx.flags), _ptr(p2f),
+            _ptr(g_zbuf), _ptr(g_bary), _ptr(g_dists), _ptr(g_verts), dev.index, _stream(dev)),
+            "rasterize_meshes backward")
+        _bump(1)
+        return (g_verts,) + (None,) * 7
+
+
+def rasterize(verts_ndc, faces, table: ViewTable, image_size, blur_radius=0.0, faces_per_pixel=1,
+              perspective_correct=False, clip_barycentric_coords=False, cull_backfaces=False):
+    """Returns (pix_to_face i64 [N,H,W,K], zbuf, bary_coords [N,H,W,K,3], dists)."""
+    H, W = image_size
+    if faces_per_pixel > _lib.MAX_FACES_PER_PIXEL:
+        raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
+    flags = ((_lib.PERSPECTIVE_CORRECT if perspective_correct else 0)
+             | (_lib.CLIP_BARYCENTRIC if clip_barycentric_coords else 0)
+             | (_lib.CULL_BACKFACES if cull_backfaces else 0))
+    return _RasterizeFn.apply(verts_ndc, faces, table, int(H), int(W), int(faces_per_pixel),
+                              float(blur_radius), flags)
+
+
+# --------------------------------------------------------------------------------------------
+class _InterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pix_to_face, bary, face_attrs):
+        _require_cuda(bary, "interpolate_face_attributes")
+        bary, face_attrs = _f32c(bary), _f32c(face_attrs)
+        pix_to_face = pix_to_face.contiguous()
+        dev = bary.device
+        P, F, D = pix_to_face.numel(), face_attrs.shape[0], face_attrs.shape[2]
+        out = torch.empty(tuple(pix_to_face.shape) + (D,), dtype=torch.float32, device=dev)
+        check(_lib.lib().trb_interp_forward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs), P, F, D,
+                                            _ptr(out), dev.index, _stream(dev)),
+              "interpolate_face_attributes")
+        _bump(1)
+        ctx.save_for_backward(pix_to_face, bary, face_attrs)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pix_to_face, bary, face_attrs = ctx.saved_tensors
+        dev = bary.device
+        P, F, D = pix_to_face.numel(), face_attrs.shape[0], face_attrs.shape[2]
+        g_bary = torch.empty_like(bary)
+        g_attrs = torch.zeros_like(face_attrs)
+        grad_out = _f32c(grad_out)
+        check(_lib.lib().trb_interp_backward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs),
+                                             _ptr(grad_out), P, F, D, _ptr(g_bary), _ptr(g_attrs),
+                                             dev.index, _stream(dev)),
+              "interpolate_face_attributes backward")
+        _bump(1)
+        return None, g_bary, g_attrs
+
+
+def interpolate_face_attributes(pix_to_face, barycentric_coords, face_attributes):
+    """PyTorch3D ``pytorch3d.ops.interpolate_face_attributes`` twin: (N,H,W,K), (N,H,W,K,3),
+    (F,3,D) -> (N,H,W,K,D)."""
+    F, FV, D = face_attributes.shape
+    if FV != 3:
+        raise ValueError("Faces can only have three vertices; got %r" % FV)
+    N, H, W, K, _ = barycentric_coords.shape
+    if pix_to_face.shape != (N, H, W, K):
+        raise ValueError("pix_to_face must have shape (batch_size, H, W, K); got %r" % (pix_to_face.shape,))
+    return _InterpFn.apply(pix_to_face, barycentric_coords, face_attributes)
+
+
+# --------------------------------------------------------------------------------------------
+class _VertexNormalsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces):
+        _require_cuda(verts, "verts_normals")
+        verts = _f32c(verts)
+        dev = verts.device
+        V, F = verts.shape[0], faces.shape[0]
+        raw = torch.empty_like(verts)
+        normals = torch.empty_like(verts)
+        check(_lib.lib().trb_vertex_normals_forward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
+                                                    _ptr(normals), dev.index, _stream(dev)),
+              "verts_normals")
+        _bump(2)
+        ctx.save_for_backward(verts, faces, raw)
+        return normals
+
+    @staticmethod
+    def backward(ctx, grad_normals):
+        verts, faces, raw = ctx.saved_tensors
+        dev = verts.device
+        V, F = verts.shape[0], faces.shape[0]
+        g_raw = torch.empty_like(verts)
+        g_verts = torch.zeros_like(verts)
+        grad_normals = _f32c(grad_normals)
+        check(_lib.lib().trb_vertex_normals_backward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
+                                                     _ptr(grad_normals), _ptr(g_raw), _ptr(g_verts),
+                                                     dev.index, _stream(dev)), "verts_normals backward")
+        _bump(2)
+        return g_verts, None
+
+
+def vertex_normals(verts, faces_i32):
+    """Area-weighted unit vertex normals, differentiable w.r.t. ``verts``."""
+    return _VertexNormalsFn.apply(verts, faces_i32)
+
+
+# --------------------------------------------------------------------------------------------
+class _ShadeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face, faces,
+                table: ViewTable, cfg: ShadeConfig):
+        _require_cuda(dists, "shader")
+        dev = dists.device
+        bary, zbuf, dists = _f32c(bary), _f32c(zbuf), _f32c(dists)
+        verts = None if verts is None else _f32c(verts)
+        normals = None if normals is None else _f32c(normals)
+        colors = None if colors is None else _f32c(colors)
+        texels = None if texels is None else _f32c(texels)
+        view_params = None if view_params is None else _f32c(view_params)
+        images = torch.empty((cfg.N, cfg.H, cfg.W, 4), dtype=torch.float32, device=dev)
+        check(_lib.lib().trb_shade_forward(
+            ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
+            _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
+            _ptr(normals), _ptr(colors), _ptr(texels), _ptr(images), dev.index, _stream(dev)), "shader")
+        _bump(1)
+        ctx.save_for_backward(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face,
+                              faces)
+        ctx.table, ctx.cfg = table, cfg
+        return images
+
+    @staticmethod
+    def backward(ctx, grad_images):
+        bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face, faces = ctx.saved_tensors
+        table, cfg = ctx.table, ctx.cfg
+        dev = dists.device
+        need = ctx.needs_input_grad
+        geom = need[0] or need[1] or need[2]
+        g_bary = torch.empty_like(bary) if geom else None
+        g_zbuf = torch.empty_like(zbuf) if geom else None
+        g_dists = torch.empty_like(dists) if geom else None
+        g_verts = torch.zeros_like(verts) if (need[3] and verts is not None) else None
+        g_normals = torch.zeros_like(normals) if (need[4] and normals is not None) else None
+        g_colors = torch.zeros_like(colors) if (need[5] and colors is not None) else None
+        g_texels = torch.empty_like(texels) if (need[6] and texels is not None) else None
+        g_vp = torch.zeros_like(view_params) if (need[7] and view_params is not None) else None
+        grad_images = _f32c(grad_images)
+        check(_lib.lib().trb_shade_backward(
+            ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
+            _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
+            _ptr(normals), _ptr(colors), _ptr(texels), _ptr(grad_images), _ptr(g_bary), _ptr(g_zbuf),
+            _ptr(g_dists), _ptr(g_verts), _ptr(g_normals), _ptr(g_colors), _ptr(g_texels), _ptr(g_vp),
+            dev.index, _stream(dev)), "shader backward")
+        _bump(1)
+        return (g_bary if need[0] else None, g_zbuf if need[1] else None, g_dists if need[2] else None,
+                g_verts, g_normals, g_colors, g_texels, g_vp, None, None, None, None)
+
+
+def shade(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face, faces, table, cfg):
+    return _ShadeFn.apply(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face,
+                          faces, table, cfg)

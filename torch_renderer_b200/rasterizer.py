@@ -1,0 +1,175 @@
+"""``RasterizationSettings``, ``Fragments``, ``MeshRasterizer`` and ``rasterize_meshes`` with the
+PyTorch3D call surface.  Reference usage:
+``MeshRasterizer(cameras=..., raster_settings=...)(meshes, R=Rs, T=ts).zbuf[..., 0]``
+(torch_renderer.py:97-113, camera_pose_optimizer.py:139-142,244, batch_rendering_test.py:196-274,
+myrenderer.py:84-103).
+
+Host side only: resolves settings, turns the camera into ``(R, T, fx, fy, px, py)`` and launches the
+CUDA transform + rasteriser through ``ops``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import NamedTuple, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .structures import Meshes
+
+kMaxBinsPerDim = 22  # PyTorch3D refuses bin grids this large; kept for error parity
+
+
+class Fragments(NamedTuple):
+    """pix_to_face i64 (N,H,W,K) packed face index or -1; zbuf, dists f32 (N,H,W,K); bary_coords
+    f32 (N,H,W,K,3); background is -1 in all four."""
+    pix_to_face: torch.Tensor
+    zbuf: torch.Tensor
+    bary_coords: torch.Tensor
+    dists: Optional[torch.Tensor]
+
+    def detach(self) -> "Fragments":
+        return Fragments(self.pix_to_face, self.zbuf.detach(), self.bary_coords.detach(),
+                         None if self.dists is None else self.dists.detach())
+
+
+@dataclass
+class RasterizationSettings:
+    image_size: Union[int, Tuple[int, int]] = 256
+    blur_radius: float = 0.0
+    faces_per_pixel: int = 1
+    bin_size: Optional[int] = None
+    max_faces_per_bin: Optional[int] = None
+    perspective_correct: Optional[bool] = None
+    clip_barycentric_coords: Optional[bool] = None
+    cull_backfaces: bool = False
+    z_clip_value: Optional[float] = None
+    cull_to_frustum: bool = False
+
+
+def _parse_image_size(image_size) -> Tuple[int, int]:
+    if isinstance(image_size, int):
+        if image_size < 1:
+            raise ValueError("image size must be positive")
+        return image_size, image_size
+    if torch.is_tensor(image_size):
+        image_size = [int(v) for v in image_size.flatten().tolist()]
+    if not isinstance(image_size, (tuple, list)):
+        raise ValueError("Image size can only be a tuple/list of (H, W)")
+    if len(image_size) != 2:
+        raise ValueError("Image size can only be a tuple/list of (H, W)")
+    if not all(isinstance(i, int) for i in image_size):
+        raise ValueError("Image sizes must be integers; got %r" % (image_size,))
+    if not all(i > 0 for i in image_size):
+        raise ValueError("Image sizes must be greater than 0; got %d, %d" % tuple(image_size))
+    return int(image_size[0]), int(image_size[1])
+
+
+def _check_bin_size(bin_size, H: int, W: int) -> None:
+    """Our tiling is fixed by the kernel, but invalid requests fail exactly like upstream."""
+    if bin_size is None or bin_size == 0:
+        return
+    if bin_size < 0:
+        raise ValueError("bin_size must be >= 0")
+    bins = 1 + (max(H, W) - 1) // bin_size
+    if bins >= kMaxBinsPerDim:
+        raise ValueError("bin_size too small, number of bins per dimension must be less than %d; got %d"
+                         % (kMaxBinsPerDim, bins))
+
+
+def rasterize_meshes(meshes: Meshes, image_size=256, blur_radius: float = 0.0, faces_per_pixel: int = 8,
+                     bin_size: Optional[int] = None, max_faces_per_bin: Optional[int] = None,
+                     perspective_correct: bool = False, clip_barycentric_coords: bool = False,
+                     cull_backfaces: bool = False, z_clip_value: Optional[float] = None,
+                     cull_to_frustum: bool = False):
+    """PyTorch3D ``rasterize_meshes`` twin: ``meshes`` hold vertices already in NDC (x, y) + view z.
+    Returns (pix_to_face, zbuf, bary_coords, dists)."""
+    H, W = _parse_image_size(image_size)
+    _check_bin_size(bin_size, H, W)
+    if z_clip_value is not None or cull_to_frustum:
+        raise NotImplementedError("near-plane clipping / frustum culling (clip_faces) is not built yet "
+                                  "(SURVEY 8f rank 3); pass z_clip_value=None, cull_to_frustum=False")
+    table = meshes.view_table()
+    verts = meshes._unique_verts()
+    if table.shared_mesh:
+        # every replica has the same NDC vertices: expand (the kernels index per view)
+        verts = verts.repeat(table.N, 1)
+    return ops.rasterize(verts, meshes.faces_packed_i32(), table, (H, W), blur_radius, faces_per_pixel,
+                         perspective_correct, clip_barycentric_coords, cull_backfaces)
+
+
+def _expand_views(t: torch.Tensor, N: int, what: str) -> torch.Tensor:
+    if t.shape[0] == N:
+        return t
+    if t.shape[0] == 1:
+        return t.expand((N,) + tuple(t.shape[1:]))
+    raise ValueError(f"Wrong number of cameras: {what} has batch {t.shape[0]} but the mesh batch has {N} "
+                     "(must be 1 or equal)")
+
+
+class MeshRasterizer(nn.Module):
+    def __init__(self, cameras=None, raster_settings: Optional[RasterizationSettings] = None) -> None:
+        super().__init__()
+        if raster_settings is None:
+            raster_settings = RasterizationSettings()
+        self.cameras = cameras
+        self.raster_settings = raster_settings
+
+    def to(self, device):
+        if self.cameras is not None:
+            self.cameras = self.cameras.to(device)
+        return self
+
+    def _camera_inputs(self, meshes_world: Meshes, kwargs):
+        cameras = kwargs.get("cameras", self.cameras)
+        if cameras is None:
+            raise ValueError("Cameras must be specified either at initialization or in the forward pass "
+                             "of MeshRasterizer")
+        N = len(meshes_world)
+        dev = meshes_world.device
+        R = kwargs.get("R", None)
+        T = kwargs.get("T", None)
+        R = cameras.R if R is None else R
+        T = cameras.T if T is None else T
+        # PyTorch3D's get_world_to_view_transform stores per-call overrides on the camera object;
+        # the shaders' specular term (get_camera_center() without kwargs) relies on it.
+        cameras.R, cameras.T = R, T
+        proj_kwargs = {k: v for k, v in kwargs.items() if k not in ("R", "T", "cameras")}
+        proj, perspective = cameras.ndc_projection_params(**proj_kwargs)
+        R = _expand_views(R.to(dev), N, "R")
+        T = _expand_views(T.to(dev), N, "T")
+        proj = _expand_views(proj.to(dev), N, "projection")
+        return cameras, R, T, proj, perspective
+
+    def transform(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
+        """World -> NDC (x, y) + view z for every (view, vertex): f32 [sum_n V_n, 3], view-major."""
+        _, R, T, proj, perspective = self._camera_inputs(meshes_world, kwargs)
+        return ops.transform_verts(meshes_world._unique_verts(), R, T, proj, meshes_world.view_table(),
+                                   perspective)
+
+    def forward(self, meshes_world: Meshes, **kwargs) -> Fragments:
+        raster_settings = kwargs.get("raster_settings", self.raster_settings)
+        H, W = _parse_image_size(raster_settings.image_size)
+        _check_bin_size(raster_settings.bin_size, H, W)
+        cameras, R, T, proj, perspective = self._camera_inputs(meshes_world, kwargs)
+        table = meshes_world.view_table()
+        verts_ndc = ops.transform_verts(meshes_world._unique_verts(), R, T, proj, table, perspective)
+
+        clip_bary = raster_settings.clip_barycentric_coords
+        if clip_bary is None:
+            clip_bary = raster_settings.blur_radius > 0.0
+        persp_correct = raster_settings.perspective_correct
+        if persp_correct is None:
+            persp_correct = cameras.is_perspective()
+        if raster_settings.cull_to_frustum:
+            raise NotImplementedError("cull_to_frustum (clip_faces) is not built yet (SURVEY 8f rank 3)")
+        # z_clip_value: PyTorch3D clips faces against z = znear/2 for cameras that define znear.
+        # Faces with a vertex at or behind the camera plane are dropped by the kernel (A4.2); proper
+        # near-plane clipping of crossing faces is the `next` row 8f-3 and not built yet.
+
+        p2f, zbuf, bary, dists = ops.rasterize(
+            verts_ndc, meshes_world.faces_packed_i32(), table, (H, W), raster_settings.blur_radius,
+            raster_settings.faces_per_pixel, bool(persp_correct), bool(clip_bary),
+            bool(raster_settings.cull_backfaces))
+        return Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)

@@ -1,0 +1,187 @@
+"""``SoftPhongShader``, ``HardPhongShader``, ``SoftSilhouetteShader`` and ``MeshRenderer`` with the
+PyTorch3D call surface.  Reference usage: renderer.py:87-101,
+torch_renderer.py:102-108,144-158, camera_pose_optimizer.py:130-158, mesh_deformer.py:142-145,197,
+myrenderer.py:88,105, batch_rendering_test.py:171-200.
+
+Each shader call is ONE fused CUDA kernel (csrc/shade.cu): attribute interpolation, Phong
+lighting and blending; the backward is one kernel as well.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .blending import BlendParams
+from .lighting import AmbientLights, DirectionalLights, Materials, PointLights
+from .rasterizer import Fragments
+from .structures import Meshes
+from .textures import TexturesVertex
+
+_LIGHT_KIND = {"ambient": _lib.LIGHT_AMBIENT, "point": _lib.LIGHT_POINT, "directional": _lib.LIGHT_DIRECTIONAL}
+
+
+def _rows(t: torch.Tensor, N: int, device, what: str) -> torch.Tensor:
+    """(n, C) with n in {1, N} -> (N, C) on device."""
+    if t.device != device:
+        t = t.to(device)
+    if t.dim() == 1:
+        t = t[:, None]
+    if t.shape[0] == N:
+        return t
+    if t.shape[0] == 1:
+        return t.expand(N, t.shape[1])
+    raise ValueError(f"{what} has batch size {t.shape[0]}; expected 1 or {N}")
+
+
+def _scalar_rows(v, N: int, device) -> torch.Tensor:
+    if not torch.is_tensor(v):
+        return torch.full((N, 1), float(v), dtype=torch.float32, device=device)
+    return _rows(v.reshape(-1, 1).float(), N, device, "znear/zfar")
+
+
+def _view_params(N, device, lights, materials, cameras, znear, zfar) -> torch.Tensor:
+    """f32 [N, 20] parameter block of the shade kernel (layout: include/trb.h)."""
+    kind = getattr(lights, "kind", None)
+    if kind not in _LIGHT_KIND:
+        raise ValueError(f"unsupported lights object {type(lights).__name__}")
+    zeros3 = torch.zeros((N, 3), dtype=torch.float32, device=device)
+    amb = _rows(materials.ambient_color, N, device, "materials") * _rows(lights.ambient_color, N, device, "lights")
+    if kind == "ambient":
+        vec, dif, spec = zeros3, zeros3, zeros3
+    else:
+        vec = _rows(lights.location if kind == "point" else lights.direction, N, device, "lights")
+        dif = _rows(materials.diffuse_color, N, device, "materials") * _rows(lights.diffuse_color, N, device, "lights")
+        spec = _rows(materials.specular_color, N, device, "materials") * _rows(lights.specular_color, N, device, "lights")
+    shin = _rows(materials.shininess.reshape(-1, 1), N, device, "materials")
+    cam = _rows(cameras.get_camera_center(), N, device, "cameras") if kind != "ambient" else zeros3
+    pad = torch.zeros((N, 2), dtype=torch.float32, device=device)
+    return torch.cat([vec, amb, dif, spec, shin, cam, _scalar_rows(znear, N, device),
+                      _scalar_rows(zfar, N, device), pad], dim=1)
+
+
+def _shade_config(fragments: Fragments, shader: int, light_kind: int, texture_mode: int,
+                  blend_params: BlendParams) -> _lib.ShadeConfig:
+    N, H, W, K = fragments.pix_to_face.shape
+    bg = blend_params.background_color
+    bg = [float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg)]
+    cfg = _lib.ShadeConfig()
+    cfg.N, cfg.H, cfg.W, cfg.K = N, H, W, K
+    cfg.shader, cfg.light_kind, cfg.texture_mode = shader, light_kind, texture_mode
+    cfg.sigma, cfg.gamma = float(blend_params.sigma), float(blend_params.gamma)
+    cfg.background[0], cfg.background[1], cfg.background[2] = bg[0], bg[1], bg[2]
+    return cfg
+
+
+class _ShaderBase(nn.Module):
+    def __init__(self, device="cpu", cameras=None, lights=None, materials=None,
+                 blend_params: Optional[BlendParams] = None) -> None:
+        super().__init__()
+        self.lights = lights if lights is not None else PointLights(device=device)
+        self.materials = materials if materials is not None else Materials(device=device)
+        self.cameras = cameras
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+
+    def _get_cameras(self, **kwargs):
+        cameras = kwargs.get("cameras", self.cameras)
+        if cameras is None:
+            raise ValueError("Cameras must be specified either at initialization or in the forward pass "
+                             "of the shader.")
+        return cameras
+
+    def to(self, device):
+        if self.cameras is not None:
+            self.cameras = self.cameras.to(device)
+        self.materials = self.materials.to(device)
+        self.lights = self.lights.to(device)
+        return self
+
+    def _phong(self, shader: int, fragments: Fragments, meshes: Meshes, **kwargs) -> torch.Tensor:
+        cameras = self._get_cameras(**kwargs)
+        lights = kwargs.get("lights", self.lights)
+        materials = kwargs.get("materials", self.materials)
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        dev = fragments.pix_to_face.device
+        N = fragments.pix_to_face.shape[0]
+        table = meshes.view_table()
+        if table.N != N:
+            raise ValueError("fragments and meshes have different batch sizes")
+        textures = meshes.textures
+        if textures is None:
+            raise ValueError("Meshes does not have textures")
+        colors = texels = None
+        if isinstance(textures, TexturesVertex):
+            shared = table.shared_mesh and textures._replicas == table.N
+            if table.shared_mesh and not shared:
+                raise ValueError("textures batch does not match the extended mesh")
+            colors = textures._unique_features(shared)
+            if colors.shape[-1] != 3:
+                raise ValueError("Phong shading needs RGB (C=3) vertex features")
+            tex_mode = _lib.TEX_VERTEX
+        else:
+            texels = meshes.sample_textures(fragments)
+            tex_mode = _lib.TEX_TEXELS
+        znear = kwargs.get("znear", getattr(cameras, "znear", 1.0))
+        zfar = kwargs.get("zfar", getattr(cameras, "zfar", 100.0))
+        vp = _view_params(N, dev, lights, materials, cameras, znear, zfar)
+        cfg = _shade_config(fragments, shader, _LIGHT_KIND[lights.kind], tex_mode, blend_params)
+        return ops.shade(fragments.bary_coords, fragments.zbuf, fragments.dists, meshes._unique_verts(),
+                         meshes._unique_verts_normals(), colors, texels, vp, fragments.pix_to_face,
+                         meshes.faces_packed_i32(), table, cfg)
+
+
+class SoftPhongShader(_ShaderBase):
+    """Per-pixel Phong lighting on interpolated coordinates/normals + softmax_rgb_blend."""
+
+    def forward(self, fragments: Fragments, meshes: Meshes, **kwargs) -> torch.Tensor:
+        return self._phong(_lib.SHADER_SOFT_PHONG, fragments, meshes, **kwargs)
+
+
+class HardPhongShader(_ShaderBase):
+    """Per-pixel Phong lighting, closest face only (hard_rgb_blend)."""
+
+    def forward(self, fragments: Fragments, meshes: Meshes, **kwargs) -> torch.Tensor:
+        return self._phong(_lib.SHADER_HARD_PHONG, fragments, meshes, **kwargs)
+
+
+TexturedSoftPhongShader = SoftPhongShader  # legacy PyTorch3D alias
+
+
+class SoftSilhouetteShader(nn.Module):
+    """RGB = 1, alpha = 1 - prod_k (1 - sigmoid(-dist_k / sigma)) (sigmoid_alpha_blend)."""
+
+    def __init__(self, blend_params: Optional[BlendParams] = None) -> None:
+        super().__init__()
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+
+    def forward(self, fragments: Fragments, meshes: Meshes, **kwargs) -> torch.Tensor:
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        cfg = _shade_config(fragments, _lib.SHADER_SOFT_SILHOUETTE, 0, 0, blend_params)
+        return ops.shade(fragments.bary_coords, fragments.zbuf, fragments.dists, None, None, None, None,
+                         None, fragments.pix_to_face, None, None, cfg)
+
+
+class MeshRenderer(nn.Module):
+    """``images = shader(rasterizer(meshes_world, **kwargs), meshes_world, **kwargs)``."""
+
+    def __init__(self, rasterizer, shader) -> None:
+        super().__init__()
+        self.rasterizer = rasterizer
+        self.shader = shader
+
+    def to(self, device):
+        self.rasterizer.to(device)
+        self.shader.to(device)
+        return self
+
+    def forward(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
+        fragments = self.rasterizer(meshes_world, **kwargs)
+        return self.shader(fragments, meshes_world, **kwargs)
+
+
+class MeshRendererWithFragments(MeshRenderer):
+    def forward(self, meshes_world: Meshes, **kwargs):
+        fragments = self.rasterizer(meshes_world, **kwargs)
+        return self.shader(fragments, meshes_world, **kwargs), fragments

@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec of the mesh-rendering hot path (rasterise + SoftPhong, forward + backward).
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): the cow mesh (V=2,930, F=5,856) rendered from
+64 cameras at 512x512, faces_per_pixel=1, blur 0, FoV perspective cameras on the
+look_at_view_transform(dist=0.7, elev=linspace(0,360,64), azim=linspace(-180,180,64)) orbit,
+SoftPhongShader + PointLights; gradients flow to vertices, vertex colours and the per-view R / T.
+One "step" = one forward + backward over the 64-view batch (per GPU; weak scaling over GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the public
+API from pinned host buffers (H2D of vertices / colours / R / T and D2H of loss + gradients inside the
+timed region); `roofline` is the dominant kernel against the measured HBM peak; `cpu_baseline` is the
+CPU oracle (a port: PyTorch3D itself is not installable) timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "views/sec fwd+bwd (raster+SoftPhong) at 512^2"
+UNIT = "views/s"
+H = W = 512
+K = 1
+VIEWS_PER_GPU = 64
+WORKLOAD = ("cow.obj (V=2930,F=5856) x 64 cameras at 512x512, faces_per_pixel=1, blur 0, SoftPhong+PointLights, "
+            "fwd+bwd to verts/colours/R/T (BASELINE configs[1])")
+FALLBACK_HBM_GBS = 6650.0
+
+
+def _peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def _bytes_per_view(V, F):
+    """SURVEY 8d / BASELINE.md section 3: B_view = 56*K*H*W + 32*H*W + 96*V + 48*F."""
+    return 56 * K * H * W + 32 * H * W + 96 * V + 48 * F
+
+
+# per-kernel share of B_view (DESIGN.md "kernels and their algorithmic bytes")
+def _kernel_bytes(name, V, F):
+    hw = H * W
+    return {
+        "raster_forward": 28 * K * hw + 12 * V + 24 * F,        # Fragments written, NDC verts + faces read
+        "shade_forward": 16 * hw + 24 * V,                      # RGBA written, normals + colours read
+        "shade_backward": 28 * K * hw + 16 * hw + 36 * V + 24 * F + 12 * V,  # Fragments + grad image read
+        "raster_backward": 12 * V,                              # grad of NDC verts written
+        "transform_forward": 12 * V, "transform_backward": 12 * V,
+    }.get(name, 0)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()  # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _scene(device):
+    import torch_renderer_b200 as trb
+    from helpers import load_mesh
+    v, f = load_mesh("cow")
+    torch.manual_seed(0)
+    colors = torch.rand(v.shape[0], 3)
+    N = VIEWS_PER_GPU
+    elev = torch.linspace(0, 360, N)
+    azim = torch.linspace(-180, 180, N)
+    R, T = trb.look_at_view_transform(dist=0.7, elev=elev, azim=azim)
+    return v, f, colors, R, T
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import torch_renderer_b200 as trb
+    from torch_renderer_b200 import ops
+    from torch_renderer_b200.parallel import allreduce_shared_grads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: torch_renderer_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    v, f, colors, R, T = _scene(dev)
+    V, F, N = v.shape[0], f.shape[0], VIEWS_PER_GPU
+    # weak scaling: every rank renders its own 64 views of the orbit (rotated per rank), mesh replicated
+    if world > 1:
+        elev = torch.linspace(0, 360, N) + 360.0 * rank / world / N
+        azim = torch.linspace(-180, 180, N) + 360.0 * rank / world / N
+        R, T = trb.look_at_view_transform(dist=0.7, elev=elev, azim=azim)
+
+    verts = v.to(dev).requires_grad_(True)
+    cols = colors.to(dev).requires_grad_(True)
+    Rd = R.to(dev).requires_grad_(True)
+    Td = T.to(dev).requires_grad_(True)
+    faces = f.to(dev)
+    mesh = trb.Meshes(verts=[verts], faces=[faces], textures=trb.TexturesVertex(cols[None]))
+    meshes = mesh.extend(N)
+    cameras = trb.FoVPerspectiveCameras(device=dev)
+    lights = trb.PointLights(device=dev, location=[[0.0, 0.0, -3.0]])
+    settings = trb.RasterizationSettings(image_size=H, blur_radius=0.0, faces_per_pixel=K)
+    renderer = trb.MeshRenderer(rasterizer=trb.MeshRasterizer(cameras=cameras, raster_settings=settings),
+                                shader=trb.SoftPhongShader(device=dev, cameras=cameras, lights=lights))
+    grad_img = torch.randn(N, H, W, 4, device=dev) / (N * H * W)
+    params = [verts, cols, Rd, Td]
+
+    def step_device():
+        for p in params:
+            p.grad = None
+        images = renderer(meshes, R=Rd, T=Td)
+        images.backward(grad_img)
+        allreduce_shared_grads([verts.grad, cols.grad])
+        return images
+
+    # pinned host copies for the end-to-end leg
+    host = [t.detach().cpu().pin_memory() for t in params]
+    host_out = [torch.empty_like(h).pin_memory() for h in host]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for p, h in zip(params, host):
+            p.grad = None
+            p.data.copy_(h, non_blocking=True)
+        images = renderer(meshes, R=Rd, T=Td)
+        loss = (images * grad_img).sum()
+        loss.backward()
+        allreduce_shared_grads([verts.grad, cols.grad])
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        for p, o in zip(params, host_out):
+            o.copy_(p.grad, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms_total = timed(step_device, args.steps)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * N / (ms_step / 1e3)
+
+    # per-kernel durations, same steps again with CUDA events around every libtrb call
+    barrier()
+    ops.start_event_log()
+    for _ in range(args.steps):
+        step_device()
+    kern = ops.stop_event_log()
+    per_launch_ms = {k: ms / n for k, (n, ms) in kern.items()}
+    dominant = max(per_launch_ms, key=per_launch_ms.get)
+    peak, peak_src = _peak()
+    dom_bytes = _kernel_bytes(dominant, V, F) * N
+    achieved = dom_bytes / (per_launch_ms[dominant] * 1e-3) / 1e9
+    step_bytes = _bytes_per_view(V, F) * N
+    step_achieved = step_bytes / (ms_step * 1e-3) / 1e9
+    traffic = TRAFFIC_BYTES_PER_LAUNCH.get(dominant)
+
+    # end-to-end through the public API with host buffers
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * N / (ms_e2e / 1e3)
+    h2d = sum(h.numel() * 4 for h in host)
+    d2h = 4 + sum(h.numel() * 4 for h in host_out)
+
+    cpu = cpu_baseline(sample_views=args.cpu_views) if (rank == 0 and world == 1 and not args.no_cpu) else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic cameras on the reference cow mesh geometry "
+            "(tests/golden/meshes.npz), random vertex colours, seed 0",
+            "config": {"workload": WORKLOAD, "views_per_gpu": N, "image": [H, W], "faces_per_pixel": K,
+                       "parallelism": f"view-sharded x{world}, mesh replicated, 1 fused allreduce of shared grads",
+                       "l2_policy": "inputs larger than L2: Fragments + images + their grads = 1.2 GB per step vs 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e, 4)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": round(per_launch_ms[dominant], 4),
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "step_achieved": round(step_achieved, 1), "step_frac": round(step_achieved / peak, 4),
+                         "kernels_ms_per_launch": {k: round(x, 4) for k, x in sorted(per_launch_ms.items())}},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
+# filled in after each profiling pass, None until a capture of that kernel exists.
+TRAFFIC_BYTES_PER_LAUNCH = {}
+
+
+def cpu_baseline(sample_views=2, threads=0):
+    """The oracle (kind 'port': C restatement of PyTorch3D's naive CPU rasteriser + torch-CPU shading)
+    on this box's host cores, forward + backward, on `sample_views` views of the bench workload."""
+    import oracle
+    from helpers import fov_proj, load_mesh
+    from oracle import shading_ref as sref
+    import torch_renderer_b200 as trb
+    v, f = load_mesh("cow")
+    torch.manual_seed(0)
+    colors = torch.rand(v.shape[0], 3)
+    n = sample_views
+    elev = torch.linspace(0, 360, VIEWS_PER_GPU)[:n]
+    azim = torch.linspace(-180, 180, VIEWS_PER_GPU)[:n]
+    R, T = trb.look_at_view_transform(dist=0.7, elev=elev, azim=azim)
+    cores = oracle.num_threads() if threads <= 0 else threads
+    torch.set_num_threads(cores)
+    proj = fov_proj(n)
+    ones = lambda *x: torch.tensor([list(x)], dtype=torch.float32).repeat(n, 1)
+    grad_img = torch.randn(n, H, W, 4) / (n * H * W)
+    t0 = time.perf_counter()
+    vr, cr, Rr, Tr = (t.clone().requires_grad_(True) for t in (v, colors, R, T))
+    ndc = sref.world_to_ndc(vr, Rr, Tr, proj[:, 0], proj[:, 1], proj[:, 2], proj[:, 3], True)
+    fv = ndc[:, f].reshape(-1, 3, 3)
+    first = np.arange(n, dtype=np.int64) * f.shape[0]
+    count = np.full((n,), f.shape[0], dtype=np.int64)
+    p2f, zbuf, bary, dists = oracle.rasterize_forward(fv.detach().numpy(), first, count, (H, W), 0.0, K, True,
+                                                      False, False, cores)
+    p2f_t = torch.from_numpy(p2f)
+    zb, ba, di = (torch.from_numpy(a).requires_grad_(True) for a in (zbuf, bary, dists))
+    cam = -torch.matmul(Tr[:, None, :], torch.linalg.inv(Rr))[:, 0, :]
+    img = sref.shade(p2f_t, ba, zb, di, f.repeat(n, 1), vr, sref.vertex_normals(vr, f), cr, shader="soft_phong",
+                     light_kind="point", light_vec=ones(0, 0, -3.0), light_ambient=ones(.5, .5, .5),
+                     light_diffuse=ones(.3, .3, .3), light_specular=ones(.2, .2, .2), mat_ambient=ones(1, 1, 1),
+                     mat_diffuse=ones(1, 1, 1), mat_specular=ones(1, 1, 1), shininess=torch.full((n,), 64.0),
+                     camera_center=cam)
+    img.backward(grad_img)
+    g_fv = oracle.rasterize_backward(fv.detach().numpy(), p2f, zb.grad.numpy(), ba.grad.numpy(), di.grad.numpy(),
+                                     True, False)
+    fv.backward(torch.from_numpy(g_fv))
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the 64 views of the same workload, forward+backward, {dt:.1f} s wall",
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  PyTorch3D (which holds it) is
+    not installable, so this is the oracle port with all host threads; each step = 1 view fwd+bwd."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(sample_views=1)
+    times = []
+    for _ in range(max(1, min(args.steps, 5))):
+        r = cpu_baseline(sample_views=1)
+        times.append(r["seconds"])
+    sec = statistics.mean(times)
+    value = 1.0 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic cameras on the reference cow mesh geometry, seed 0",
+            "config": {"workload": WORKLOAD, "sample": "each step = 1 view of the 64-view batch, forward+backward"},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": "1 view per step, forward+backward, all host threads"},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-views", type=int, default=2, help="views in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""Multi-rank host logic on CPU with the gloo backend, world_size 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from torch_renderer_b200.parallel import allreduce_shared_grads, chunk_views, max_views_for_memory, shard_views
+
+
+def test_shard_and_chunk_views():
+    for n in (1, 7, 64, 1024):
+        for w in (1, 2, 3, 8):
+            spans = [shard_views(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_views(4, 2, 2)
+    assert chunk_views(10, 4) == [(0, 4), (4, 8), (8, 10)]
+    assert chunk_views(0, 4) == []
+    # C5: 1024^2, K=8: 235 MB of Fragments per view -> a 30 GB budget holds ~70 views with grads
+    n = max_views_for_memory(1024, 1024, 8, 30 * 10**9)
+    assert 50 < n < 128
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        n_views, V = 6, 11
+        per_view = torch.randn(n_views, V, 3)          # every rank knows the full problem
+        s, e = shard_views(n_views, rank, world)
+        g_verts = per_view[s:e].sum(0)                 # partial gradient from this rank's views
+        g_cols = (per_view[s:e] ** 2).sum(0)
+        allreduce_shared_grads([g_verts, None, g_cols])
+        ok = torch.allclose(g_verts, per_view.sum(0), atol=1e-5) and torch.allclose(g_cols, (per_view ** 2).sum(0), atol=1e-5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_shared_grads_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True), (1, True)]
+
+
+def test_allreduce_is_noop_without_process_group():
+    g = torch.ones(3)
+    assert allreduce_shared_grads([g]) is None and torch.equal(g, torch.ones(3))

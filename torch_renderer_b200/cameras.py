@@ -121,7 +121,7 @@ class CamerasBase(TensorProperties):
     def get_camera_center(self, **kwargs) -> torch.Tensor:
         """Camera centre in world coordinates: ``-T @ inv(R)``."""
         R, T = self._rt(kwargs)
-        return -torch.matmul(T[:, None, :], torch.linalg.inv(R))[:, 0, :]
+        return -torch.matmul(T[:, None, :], torch.linalg.inv_ex(R)[0])[:, 0, :]  # inv_ex: no host sync
 
     def get_full_projection_transform(self, **kwargs) -> Transform3d:
         w2v = self.get_world_to_view_transform(**kwargs)

@@ -27,6 +27,47 @@ def _bump(n: int) -> None:
     _launch_count += n
 
 
+# Optional per-call CUDA-event timing (bench.py's roofline leg).  None = off (the default).
+_event_log = None
+
+
+def start_event_log() -> None:
+    global _event_log
+    _event_log = []
+
+
+def stop_event_log():
+    """Returns {call name: (launches, total milliseconds)}; synchronises the device."""
+    global _event_log
+    log, _event_log = _event_log or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in log:
+        n, ms = out.get(name, (0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1))
+    return out
+
+
+class _timed:
+    """Brackets one C-ABI call with CUDA events on the launching stream when the log is on."""
+
+    def __init__(self, name: str, device: torch.device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if _event_log is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _event_log is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.device))
+            _event_log.append((self.name, self.e0, e1))
+        return False
+
+
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -112,9 +153,10 @@ class _TransformFn(torch.autograd.Function):
         verts_world, R, T, proj = _f32c(verts_world), _f32c(R), _f32c(T), _f32c(proj)
         dev = verts_world.device
         out = torch.empty((table.total_ndc_verts, 3), dtype=torch.float32, device=dev)
-        check(_lib.lib().trb_transform_forward(
-            _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
-            table.max_vert_count, int(perspective), _ptr(out), dev.index, _stream(dev)), "transform")
+        with _timed("transform_forward", dev):
+            check(_lib.lib().trb_transform_forward(
+                _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
+                table.max_vert_count, int(perspective), _ptr(out), dev.index, _stream(dev)), "transform")
         _bump(1)
         ctx.save_for_backward(verts_world, R, T, proj)
         ctx.table, ctx.perspective = table, perspective
@@ -131,10 +173,11 @@ class _TransformFn(torch.autograd.Function):
         g_T = torch.zeros_like(T) if need[2] else None
         g_p = torch.zeros_like(proj) if need[3] else None
         grad_out = _f32c(grad_out)
-        check(_lib.lib().trb_transform_backward(
-            _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
-            table.max_vert_count, int(ctx.perspective), _ptr(grad_out), _ptr(g_v), _ptr(g_R), _ptr(g_T),
-            _ptr(g_p), dev.index, _stream(dev)), "transform backward")
+        with _timed("transform_backward", dev):
+            check(_lib.lib().trb_transform_backward(
+                _ptr(verts_world), _ptr(R), _ptr(T), _ptr(proj), _ptr(table.views), table.N,
+                table.max_vert_count, int(ctx.perspective), _ptr(grad_out), _ptr(g_v), _ptr(g_R), _ptr(g_T),
+                _ptr(g_p), dev.index, _stream(dev)), "transform backward")
         _bump(1)
         return g_v, g_R, g_T, g_p, None, None
 
@@ -162,10 +205,11 @@ class _RasterizeFn(torch.autograd.Function):
         bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         stats = torch.empty((4,), dtype=torch.int32, device=dev)
-        check(L.trb_raster_forward(
-            _ptr(verts_ndc), _ptr(faces), _ptr(table.views), N, table.max_face_count, H, W, K,
-            float(blur_radius), int(flags), cap, _ptr(ws), nbytes.value, _ptr(p2f), _ptr(zbuf),
-            _ptr(bary), _ptr(dists), _ptr(stats), dev.index, _stream(dev)), "rasterize_meshes")
+        with _timed("raster_forward", dev):
+            check(L.trb_raster_forward(
+                _ptr(verts_ndc), _ptr(faces), _ptr(table.views), N, table.max_face_count, H, W, K,
+                float(blur_radius), int(flags), cap, _ptr(ws), nbytes.value, _ptr(p2f), _ptr(zbuf),
+                _ptr(bary), _ptr(dists), _ptr(stats), dev.index, _stream(dev)), "rasterize_meshes")
         _bump(6 if table.max_face_count > 0 else 3)
         if table._pending is None and not torch.cuda.is_current_stream_capturing():
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
@@ -193,10 +237,11 @@ class _RasterizeFn(torch.autograd.Function):
         g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
         g_bary = None if g_bary is None else _f32c(g_bary)
         g_dists = None if g_dists is None else _f32c(g_dists)
-        check(_lib.lib().trb_raster_backward(
-            _ptr(verts_ndc), _ptr(faces), _ptr(table.views), table.N, H, W, K, int(ctx.flags), _ptr(p2f),
-            _ptr(g_zbuf), _ptr(g_bary), _ptr(g_dists), _ptr(g_verts), dev.index, _stream(dev)),
-            "rasterize_meshes backward")
+        with _timed("raster_backward", dev):
+            check(_lib.lib().trb_raster_backward(
+                _ptr(verts_ndc), _ptr(faces), _ptr(table.views), table.N, H, W, K, int(ctx.flags), _ptr(p2f),
+                _ptr(g_zbuf), _ptr(g_bary), _ptr(g_dists), _ptr(g_verts), dev.index, _stream(dev)),
+                "rasterize_meshes backward")
         _bump(1)
         return (g_verts,) + (None,) * 7
 
@@ -224,9 +269,10 @@ class _InterpFn(torch.autograd.Function):
         dev = bary.device
         P, F, D = pix_to_face.numel(), face_attrs.shape[0], face_attrs.shape[2]
         out = torch.empty(tuple(pix_to_face.shape) + (D,), dtype=torch.float32, device=dev)
-        check(_lib.lib().trb_interp_forward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs), P, F, D,
-                                            _ptr(out), dev.index, _stream(dev)),
-              "interpolate_face_attributes")
+        with _timed("interp_forward", dev):
+            check(_lib.lib().trb_interp_forward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs), P, F, D,
+                                                _ptr(out), dev.index, _stream(dev)),
+                  "interpolate_face_attributes")
         _bump(1)
         ctx.save_for_backward(pix_to_face, bary, face_attrs)
         return out
@@ -239,10 +285,11 @@ class _InterpFn(torch.autograd.Function):
         g_bary = torch.empty_like(bary)
         g_attrs = torch.zeros_like(face_attrs)
         grad_out = _f32c(grad_out)
-        check(_lib.lib().trb_interp_backward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs),
-                                             _ptr(grad_out), P, F, D, _ptr(g_bary), _ptr(g_attrs),
-                                             dev.index, _stream(dev)),
-              "interpolate_face_attributes backward")
+        with _timed("interp_backward", dev):
+            check(_lib.lib().trb_interp_backward(_ptr(pix_to_face), _ptr(bary), _ptr(face_attrs),
+                                                 _ptr(grad_out), P, F, D, _ptr(g_bary), _ptr(g_attrs),
+                                                 dev.index, _stream(dev)),
+                  "interpolate_face_attributes backward")
         _bump(1)
         return None, g_bary, g_attrs
 
@@ -269,9 +316,10 @@ class _VertexNormalsFn(torch.autograd.Function):
         V, F = verts.shape[0], faces.shape[0]
         raw = torch.empty_like(verts)
         normals = torch.empty_like(verts)
-        check(_lib.lib().trb_vertex_normals_forward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
-                                                    _ptr(normals), dev.index, _stream(dev)),
-              "verts_normals")
+        with _timed("vertex_normals_forward", dev):
+            check(_lib.lib().trb_vertex_normals_forward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
+                                                        _ptr(normals), dev.index, _stream(dev)),
+                  "verts_normals")
         _bump(2)
         ctx.save_for_backward(verts, faces, raw)
         return normals
@@ -284,9 +332,10 @@ class _VertexNormalsFn(torch.autograd.Function):
         g_raw = torch.empty_like(verts)
         g_verts = torch.zeros_like(verts)
         grad_normals = _f32c(grad_normals)
-        check(_lib.lib().trb_vertex_normals_backward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
-                                                     _ptr(grad_normals), _ptr(g_raw), _ptr(g_verts),
-                                                     dev.index, _stream(dev)), "verts_normals backward")
+        with _timed("vertex_normals_backward", dev):
+            check(_lib.lib().trb_vertex_normals_backward(_ptr(verts), _ptr(faces), V, F, _ptr(raw),
+                                                         _ptr(grad_normals), _ptr(g_raw), _ptr(g_verts),
+                                                         dev.index, _stream(dev)), "verts_normals backward")
         _bump(2)
         return g_verts, None
 
@@ -310,10 +359,11 @@ class _ShadeFn(torch.autograd.Function):
         texels = None if texels is None else _f32c(texels)
         view_params = None if view_params is None else _f32c(view_params)
         images = torch.empty((cfg.N, cfg.H, cfg.W, 4), dtype=torch.float32, device=dev)
-        check(_lib.lib().trb_shade_forward(
-            ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
-            _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
-            _ptr(normals), _ptr(colors), _ptr(texels), _ptr(images), dev.index, _stream(dev)), "shader")
+        with _timed("shade_forward", dev):
+            check(_lib.lib().trb_shade_forward(
+                ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
+                _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
+                _ptr(normals), _ptr(colors), _ptr(texels), _ptr(images), dev.index, _stream(dev)), "shader")
         _bump(1)
         ctx.save_for_backward(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face,
                               faces)
@@ -336,12 +386,13 @@ class _ShadeFn(torch.autograd.Function):
         g_texels = torch.empty_like(texels) if (need[6] and texels is not None) else None
         g_vp = torch.zeros_like(view_params) if (need[7] and view_params is not None) else None
         grad_images = _f32c(grad_images)
-        check(_lib.lib().trb_shade_backward(
-            ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
-            _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
-            _ptr(normals), _ptr(colors), _ptr(texels), _ptr(grad_images), _ptr(g_bary), _ptr(g_zbuf),
-            _ptr(g_dists), _ptr(g_verts), _ptr(g_normals), _ptr(g_colors), _ptr(g_texels), _ptr(g_vp),
-            dev.index, _stream(dev)), "shader backward")
+        with _timed("shade_backward", dev):
+            check(_lib.lib().trb_shade_backward(
+                ctypes.byref(cfg), _ptr(None if table is None else table.views), _ptr(view_params),
+                _ptr(pix_to_face), _ptr(bary), _ptr(zbuf), _ptr(dists), _ptr(faces), _ptr(verts),
+                _ptr(normals), _ptr(colors), _ptr(texels), _ptr(grad_images), _ptr(g_bary), _ptr(g_zbuf),
+                _ptr(g_dists), _ptr(g_verts), _ptr(g_normals), _ptr(g_colors), _ptr(g_texels), _ptr(g_vp),
+                dev.index, _stream(dev)), "shader backward")
         _bump(1)
         return (g_bary if need[0] else None, g_zbuf if need[1] else None, g_dists if need[2] else None,
                 g_verts, g_normals, g_colors, g_texels, g_vp, None, None, None, None)

@@ -82,6 +82,7 @@ class Meshes:
         self._faces_packed = None
         self._faces_i32 = None
         self._verts_normals_packed = None
+        self._verts_normals_key = None
         self._view_table = None
         self._num_verts = None
         self._num_faces = None
@@ -207,12 +208,17 @@ class Meshes:
         return self._verts_list[0] if self._replicas > 1 else self.verts_packed()
 
     def _unique_verts_normals(self) -> torch.Tensor:
-        if self._verts_normals_packed is None:
-            verts = self._unique_verts()
-            if not verts.is_cuda:
-                raise RuntimeError("vertex normals are computed by the CUDA extension; move the mesh "
-                                   "to a CUDA device (no CPU fallback)")
+        verts = self._unique_verts()
+        if not verts.is_cuda:
+            raise RuntimeError("vertex normals are computed by the CUDA extension; move the mesh "
+                               "to a CUDA device (no CPU fallback)")
+        if verts.requires_grad:
+            # a cached result would carry an autograd graph that the previous backward() freed
+            return ops.vertex_normals(verts, self.faces_packed_i32())
+        key = (verts.data_ptr(), verts._version)
+        if self._verts_normals_packed is None or self._verts_normals_key != key:
             self._verts_normals_packed = ops.vertex_normals(verts, self.faces_packed_i32())
+            self._verts_normals_key = key
         return self._verts_normals_packed
 
     def verts_normals_packed(self) -> torch.Tensor:

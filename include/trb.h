@@ -17,7 +17,7 @@
  *   MeshRasterizer.transform (Transform3d bmm + divide)
  *                                  -> trb_transform_forward / trb_transform_backward
  *   Meshes.verts_normals_packed    -> trb_vertex_normals_forward / _backward
- *   MeshRenderer.forward + loss.backward() end to end (fragments never re-read in between)
+ *   MeshRenderer.forward + loss.backward() end to end (Fragments written once, read once)
  *                                  -> trb_render_forward / trb_render_backward
  *
  * Contract:
@@ -190,6 +190,60 @@ int trb_shade_backward(const trb_shade_config* host_cfg, const trb_view* views,
                        float* grad_verts_world, float* grad_vert_normals, float* grad_vert_colors,
                        float* grad_texels, float* grad_view_params, int device,
                        trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused render pipeline: everything MeshRenderer.forward / loss.backward() does for one batch of
+ * views, in one call each way (vertex normals, camera transform, tile binning, fine rasterisation
+ * with the shading + blending epilogue; and the reverse).  Fragments are written once in the
+ * forward and read once in the backward; nothing else of size N*H*W*K touches HBM.
+ *
+ * shade.shader may be TRB_SHADER_NONE: rasterise only (MeshRasterizer.forward).  Textures are
+ * per-vertex colours (TexturesVertex); other textures go through trb_shade_forward with texels.
+ */
+#define TRB_SHADER_NONE (-1)
+
+typedef struct trb_render_config {
+  trb_shade_config shade;
+  float blur_radius;
+  uint32_t raster_flags;         /* TRB_PERSPECTIVE_CORRECT | TRB_CLIP_BARYCENTRIC | TRB_CULL_BACKFACES */
+  int32_t perspective;           /* camera model: 1 = divide by view z, 0 = orthographic */
+  int32_t max_face_count;
+  int32_t max_vert_count;
+  int32_t camera_center_from_rt; /* 1: view_params[n][13:16] := -T[n] * inv(R[n]) (and its gradient
+                                    flows back into grad_R / grad_T) */
+  int64_t num_world_verts;       /* rows of verts_world / vert_colors */
+  int64_t num_faces;             /* rows of faces */
+  int64_t num_ndc_verts;         /* rows of verts_ndc = sum_n vert_count */
+  int64_t pair_capacity;
+} trb_render_config;
+
+/* workspace_bytes: scratch for the forward; num_tiles: length of tile_hit (int32);
+ * backward_scratch_floats: length of the f32 scratch the backward needs. */
+int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* num_tiles,
+                     int64_t* backward_scratch_floats);
+/* view_params f32[N,20] is in/out (camera centre filled in when camera_center_from_rt).
+ * Outputs: verts_ndc f32[num_ndc_verts,3]; normals_raw, normals f32[num_world_verts,3] (Phong only);
+ * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); tile_hit i32[num_tiles]. */
+int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
+                       const float* verts_world, const int32_t* faces, const float* vert_colors,
+                       const float* R, const float* T, const float* proj, float* view_params,
+                       float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
+                       float* zbuf, float* bary, float* dists, float* images, int32_t* tile_hit,
+                       void* workspace, size_t workspace_bytes, int32_t* stats, int device,
+                       trb_stream_t stream);
+/* grad_images may be NULL (shader NONE); grad_zbuf / grad_bary / grad_dists are optional extra
+ * upstream gradients on the Fragments.  Every grad_* output is ACCUMULATED into (caller zeroes;
+ * any may be NULL); `scratch` is zeroed by the call. */
+int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views,
+                        const float* verts_world, const int32_t* faces, const float* vert_colors,
+                        const float* R, const float* T, const float* proj, const float* view_params,
+                        const float* verts_ndc, const float* normals_raw, const float* normals,
+                        const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                        const float* dists, const int32_t* tile_hit, const float* grad_images,
+                        const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                        float* grad_verts_world, float* grad_vert_colors, float* grad_R, float* grad_T,
+                        float* grad_proj, float* grad_view_params, float* scratch, int device,
+                        trb_stream_t stream);
 
 #ifdef __cplusplus
 }

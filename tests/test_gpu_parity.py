@@ -238,7 +238,7 @@ def _render_setup(name, N, image_size, K, blur, shader, lights_kind, seed=0, bac
                 lights_kind=lights_kind, background=background, persp=persp)
 
 
-def _cuda_render(s, requires_grad=False):
+def _cuda_render(s, requires_grad=False, fused=False):
     trb = _trb()
     v = s["v"].to(DEV).requires_grad_(requires_grad)
     c = s["colors"].to(DEV).requires_grad_(requires_grad)
@@ -263,9 +263,12 @@ def _cuda_render(s, requires_grad=False):
         shader = trb.HardPhongShader(device=DEV, cameras=cameras, lights=lights, blend_params=blend)
     else:
         shader = trb.SoftSilhouetteShader(blend_params=blend)
-    fragments = rasterizer(meshes)
     verts_ndc = rasterizer.transform(meshes)
-    images = shader(fragments, meshes)
+    if fused:   # ONE C-ABI call each way (trb_render_forward / trb_render_backward)
+        images, fragments = trb.MeshRendererWithFragments(rasterizer, shader)(meshes)
+    else:       # rasteriser and shader composed as separate modules
+        fragments = rasterizer(meshes)
+        images = shader(fragments, meshes)
     return dict(images=images, fragments=fragments, verts_ndc=verts_ndc, v=v, c=c, R=R, T=T)
 
 
@@ -305,15 +308,17 @@ RENDER_CASES = [
     ("teapot", 2, (64, 64), 2, 0.0, "hard_phong", "point"),
     ("teapot", 2, (64, 64), 10, 9.21024e-4, "soft_silhouette", "point"),
     ("sphere", 1, (48, 48), 50, 9.21024e-4, "soft_silhouette", "point"),
+    ("sphere", 1, (40, 40), 30, 2e-3, "soft_phong", "point"),
 ]
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name,N,image_size,K,blur,shader,lights", RENDER_CASES)
-def test_render_end_to_end_forward(name, N, image_size, K, blur, shader, lights):
+def test_render_end_to_end_forward(name, N, image_size, K, blur, shader, lights, fused):
     """Public API (Meshes + cameras + lights + settings -> images / Fragments) vs the oracle pipeline
     fed with the NDC vertices the CUDA transform emitted (the bit-exact contract starts there)."""
     s = _render_setup(name, N, image_size, K, blur, shader, lights, seed=3, background=(0.1, 0.2, 0.3))
-    out = _cuda_render(s)
+    out = _cuda_render(s, fused=fused)
     ndc = out["verts_ndc"].detach().cpu().reshape(N, -1, 3)
     # the CUDA transform itself against the torch restatement
     assert torch.allclose(ndc, _ndc(s["v"], s["R"], s["T"], fov_proj(N)), atol=2e-6, rtol=2e-6)
@@ -334,15 +339,18 @@ GRAD_CASES = [
     ("teapot", 1, (48, 48), 1, 0.0, "soft_phong", "ambient"),
     ("teapot", 2, (48, 48), 1, 0.0, "hard_phong", "point"),
     ("sphere", 2, (40, 40), 12, 2e-3, "soft_silhouette", "point"),
+    ("sphere", 1, (32, 32), 30, 2e-3, "soft_phong", "point"),
+    ("sphere", 2, (40, 40), 3, 1e-3, "hard_phong", "directional"),
 ]
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name,N,image_size,K,blur,shader,lights", GRAD_CASES)
-def test_render_end_to_end_gradients(name, N, image_size, K, blur, shader, lights):
+def test_render_end_to_end_gradients(name, N, image_size, K, blur, shader, lights, fused):
     """loss.backward() through the public API: gradients w.r.t. vertices, vertex colours and camera
     R / T against fp64 autograd of the oracle model (pix_to_face held fixed)."""
     s = _render_setup(name, N, image_size, K, blur, shader, lights, seed=5, background=(0.0, 0.0, 0.0))
-    out = _cuda_render(s, requires_grad=True)
+    out = _cuda_render(s, requires_grad=True, fused=fused)
     torch.manual_seed(7)
     target = torch.rand(N, image_size[0], image_size[1], 4)
     w = torch.rand(N, image_size[0], image_size[1])
@@ -472,3 +480,69 @@ def test_full_size_properties():
     assert torch.equal(img[..., 3] > 0, covered)
     sil = trb.SoftSilhouetteShader()(a, meshes)
     assert torch.equal(sil[..., 3] >= 0.5, covered)
+
+
+def test_fused_renderer_kwargs_cameras_and_separate_shader_camera():
+    """camera_pose_optimizer.py pattern: one camera object shared by rasteriser and shader, pose passed
+    as R=, T= kwargs with requires_grad; and the mesh_deformer.py pattern: cameras= / lights= kwargs.
+    Fused and modular paths must agree on images and gradients."""
+    trb = _trb()
+    torch.manual_seed(0)
+    v, f = _scene("teapot")
+    colors = torch.rand(v.shape[0], 3)
+    R0, T0 = _views(2, seed=12)
+    res = {}
+    for fused in (False, True):
+        R = R0.to(DEV).requires_grad_(True)
+        T = T0.to(DEV).requires_grad_(True)
+        vd = v.to(DEV).requires_grad_(True)
+        cams = trb.FoVPerspectiveCameras(device=DEV)
+        lights = trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]])
+        mesh = trb.Meshes(verts=[vd], faces=[f.to(DEV)], textures=trb.TexturesVertex(colors.to(DEV)[None])).extend(2)
+        rast = trb.MeshRasterizer(cameras=cams, raster_settings=trb.RasterizationSettings(image_size=64))
+        shader = trb.SoftPhongShader(device=DEV, cameras=cams, lights=lights,
+                                     blend_params=trb.BlendParams(1e-4, 1e-4, (0, 0, 0)))
+        if fused:
+            img = trb.MeshRenderer(rast, shader)(mesh, R=R, T=T)
+        else:
+            frag = rast(mesh, R=R, T=T)
+            img = shader(frag, mesh, R=R, T=T)
+        (img[..., :3] ** 2).sum().backward()
+        res[fused] = (img.detach(), R.grad.clone(), T.grad.clone(), vd.grad.clone())
+    assert torch.allclose(res[False][0], res[True][0], atol=1e-6)
+    for a, b in zip(res[False][1:], res[True][1:]):
+        assert rel_l2(a, b) < 1e-4
+    # cameras= and lights= kwargs with a different camera object in the shader
+    cams_a = trb.PerspectiveCameras(device=DEV, R=R0.to(DEV), T=T0.to(DEV))
+    cams_b = trb.PerspectiveCameras(device=DEV, R=R0[:1].to(DEV), T=T0[:1].to(DEV))
+    mesh = trb.Meshes(verts=[v.to(DEV)], faces=[f.to(DEV)], textures=trb.TexturesVertex(colors.to(DEV)[None])).extend(2)
+    rast = trb.MeshRasterizer(cameras=cams_b, raster_settings=trb.RasterizationSettings(image_size=48, perspective_correct=False))
+    shader = trb.SoftPhongShader(device=DEV, cameras=cams_b, lights=trb.AmbientLights(device=DEV))
+    lights = trb.PointLights(device=DEV, location=[[2.0, 2.0, -2.0]])
+    img_f = trb.MeshRenderer(rast, shader)(mesh, cameras=cams_a, lights=lights)
+    frag = rast(mesh, cameras=cams_a, lights=lights)
+    img_m = shader(frag, mesh, cameras=cams_a, lights=lights)
+    assert torch.allclose(img_f, img_m, atol=1e-6)
+    assert (frag.pix_to_face >= 0).sum() > 100
+
+
+def test_fused_rasterizer_depth_gradient_and_fragment_grads():
+    """torch_renderer.DepthRender pattern: loss on relu(zbuf[...,0]) from the bare rasteriser, plus a
+    renderer-with-fragments loss that mixes image and fragment gradients."""
+    trb = _trb()
+    s = _render_setup("teapot", 2, (48, 48), 2, 1e-3, "soft_phong", "point", seed=8, background=(0, 0, 0))
+    out = _cuda_render(s, requires_grad=True, fused=True)
+    fr = out["fragments"]
+    torch.manual_seed(3)
+    wz, wb, wd = torch.rand(2, 48, 48, 2), torch.rand(2, 48, 48, 2, 3), torch.rand(2, 48, 48, 2)
+    m = (fr.pix_to_face >= 0).cpu()
+    loss = (out["images"] ** 2).sum() + (fr.zbuf * (wz * m).to(DEV)).sum() + \
+        (fr.bary_coords * (wb * m[..., None]).to(DEV)).sum() + (fr.dists * (wd * m).to(DEV)).sum() * 100
+    loss.backward()
+    ref = _oracle_render(s, fr.pix_to_face.cpu(), torch.float64)
+    loss_ref = (ref["images"] ** 2).sum() + (ref["zbuf"] * wz * m).sum() + (ref["bary"] * wb * m[..., None]).sum() + \
+        (ref["dists"] * wd * m).sum() * 100
+    loss_ref.backward()
+    for k in ("v", "R", "T", "c"):
+        e = rel_l2(out[k].grad.cpu(), ref[k].grad)
+        assert e < 1e-3, f"grad {k}: rel L2 err {e}"

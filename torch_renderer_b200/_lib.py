@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libtrb.so")
 TRB_OK, TRB_ERR_BAD_ARG, TRB_ERR_K_TOO_LARGE, TRB_ERR_WORKSPACE, TRB_ERR_CUDA = range(5)
 
 PERSPECTIVE_CORRECT, CLIP_BARYCENTRIC, CULL_BACKFACES = 1, 2, 4
-SHADER_SOFT_PHONG, SHADER_HARD_PHONG, SHADER_SOFT_SILHOUETTE = 0, 1, 2
+SHADER_NONE, SHADER_SOFT_PHONG, SHADER_HARD_PHONG, SHADER_SOFT_SILHOUETTE = -1, 0, 1, 2
 LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
 TEX_VERTEX, TEX_TEXELS = 0, 1
 VIEW_PARAM_STRIDE = 20
@@ -33,9 +33,11 @@ class ShadeConfig(ctypes.Structure):
 
 
 class RenderConfig(ctypes.Structure):
-    _fields_ = [("shade", ShadeConfig), ("blur_radius", _f), ("flags", _u32),
+    _fields_ = [("shade", ShadeConfig), ("blur_radius", _f), ("raster_flags", _u32),
                 ("perspective", _c.c_int32), ("max_face_count", _c.c_int32),
-                ("max_vert_count", _c.c_int32), ("reserved", _c.c_int32)]
+                ("max_vert_count", _c.c_int32), ("camera_center_from_rt", _c.c_int32),
+                ("num_world_verts", _c.c_int64), ("num_faces", _c.c_int64),
+                ("num_ndc_verts", _c.c_int64), ("pair_capacity", _c.c_int64)]
 
 
 # name -> argtypes; every function returns int (trb_status) unless noted
@@ -54,6 +56,9 @@ _SIGNATURES = {
     "trb_vertex_normals_backward": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _vp],
     "trb_shade_forward": [_c.POINTER(ShadeConfig)] + [_vp] * 12 + [_i, _vp],
     "trb_shade_backward": [_c.POINTER(ShadeConfig)] + [_vp] * 20 + [_i, _vp],
+    "trb_render_sizes": [_c.POINTER(RenderConfig), _c.POINTER(_sz), _c.POINTER(_i64), _c.POINTER(_i64)],
+    "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _i, _vp],
+    "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_i, _vp],
 }
 
 _lib = None

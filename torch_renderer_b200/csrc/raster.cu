@@ -11,60 +11,9 @@
 //  * the per-pixel queue keeps only (z, face) -- 8 B per entry, in registers for K=1 and in
 //    shared memory otherwise -- and barycentrics/distances are recomputed for the K survivors;
 //  * ties are broken by (z, face index), so the result does not depend on list order.
-#include "raster_math.cuh"
+#include "raster_internal.cuh"
 
 namespace trb {
-
-struct TileGrid {
-  int tiles_x, tiles_y, ltx, lty;
-};
-
-__host__ inline TileGrid make_tile_grid(int H, int W, int K) {
-  TileGrid g;
-  if (K <= 24) { g.ltx = 4; g.lty = 4; } else { g.ltx = 3; g.lty = 3; }
-  g.tiles_x = (W + (1 << g.ltx) - 1) >> g.ltx;
-  g.tiles_y = (H + (1 << g.lty) - 1) >> g.lty;
-  return g;
-}
-
-struct WsLayout {
-  size_t header, count, offset, fill, pairs, total;
-};
-
-__host__ inline WsLayout make_ws_layout(int N, const TileGrid& g, int64_t pair_capacity) {
-  WsLayout w;
-  const size_t ntiles = (size_t)N * g.tiles_x * g.tiles_y;
-  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  w.header = 0;
-  w.count = align(64);
-  w.fill = w.count + align(ntiles * 4);
-  w.offset = w.fill + align(ntiles * 4);
-  w.pairs = w.offset + align(ntiles * 4);
-  w.total = w.pairs + align((size_t)pair_capacity * 4);
-  return w;
-}
-
-__device__ __forceinline__ FaceXYZ load_face(const float* __restrict__ verts,
-                                             const int* __restrict__ faces, const trb_view& vd,
-                                             int local_face) {
-  const int r = vd.face_start + local_face;
-  int i0, i1, i2;
-  if (faces != nullptr) {
-    i0 = __ldg(faces + 3 * (size_t)r) + vd.vert_delta;
-    i1 = __ldg(faces + 3 * (size_t)r + 1) + vd.vert_delta;
-    i2 = __ldg(faces + 3 * (size_t)r + 2) + vd.vert_delta;
-  } else {
-    i0 = 3 * r; i1 = i0 + 1; i2 = i0 + 2;
-  }
-  FaceXYZ v;
-  const float* p0 = verts + 3 * (size_t)i0;
-  const float* p1 = verts + 3 * (size_t)i1;
-  const float* p2 = verts + 3 * (size_t)i2;
-  v.x0 = __ldg(p0); v.y0 = __ldg(p0 + 1); v.z0 = __ldg(p0 + 2);
-  v.x1 = __ldg(p1); v.y1 = __ldg(p1 + 1); v.z1 = __ldg(p1 + 2);
-  v.x2 = __ldg(p2); v.y2 = __ldg(p2 + 1); v.z2 = __ldg(p2 + 2);
-  return v;
-}
 
 // Conservative range of pixel indices (in output order) whose centre can lie in [lo, hi].
 // Pixel-centre i' = S-1-i has NDC coordinate -off + (range*i' + off)/S  (A3).
@@ -334,6 +283,33 @@ raster_backward_kernel(const float* __restrict__ verts, const int* __restrict__ 
   }
 }
 
+int run_binning(const float* verts_ndc, const int* faces, const trb_view* views, int N, int max_face_count,
+                int H, int W, const TileGrid& tg, const WsLayout& ws, void* workspace, float sqrt_blur, bool cull,
+                long long pair_capacity, cudaStream_t st) {
+  unsigned char* wsb = (unsigned char*)workspace;
+  int* header = (int*)(wsb + ws.header);
+  int* tile_count = (int*)(wsb + ws.count);
+  int* tile_fill = (int*)(wsb + ws.fill);
+  int* tile_offset = (int*)(wsb + ws.offset);
+  int* pairs = (int*)(wsb + ws.pairs);
+  const int ntiles = N * tg.tiles_x * tg.tiles_y;
+  // header, tile_count and tile_fill are contiguous: one memset
+  TRB_CUDA_TRY(cudaMemsetAsync(wsb, 0, ws.offset, st));
+  if (max_face_count > 0) {
+    dim3 bgrid(ceil_div(max_face_count, 256), N);
+    bin_faces_kernel<false><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
+                                                   tile_count, tile_fill, tile_offset, pairs);
+    TRB_LAUNCH_CHECK();
+    alloc_tiles_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(tile_count, tile_offset, ntiles, header,
+                                                              pair_capacity);
+    TRB_LAUNCH_CHECK();
+    bin_faces_kernel<true><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
+                                                  tile_count, tile_fill, tile_offset, pairs);
+    TRB_LAUNCH_CHECK();
+  }
+  return TRB_OK;
+}
+
 template <int LTX, int LTY, bool K1>
 static int launch_fine(bool persp, bool clip, dim3 grid, size_t dyn_smem, cudaStream_t st,
                        const float* verts, const int* faces, const trb_view* views, int H, int W,
@@ -395,25 +371,14 @@ extern "C" int trb_raster_forward(const float* verts_ndc, const int32_t* faces, 
   unsigned char* wsb = (unsigned char*)workspace;
   int* header = (int*)(wsb + ws.header);
   int* tile_count = (int*)(wsb + ws.count);
-  int* tile_fill = (int*)(wsb + ws.fill);
   int* tile_offset = (int*)(wsb + ws.offset);
   int* pairs = (int*)(wsb + ws.pairs);
-  const int ntiles = N * tg.tiles_x * tg.tiles_y;
-  // header, tile_count and tile_fill are contiguous: one memset
-  TRB_CUDA_TRY(cudaMemsetAsync(wsb, 0, ws.offset, st));
   const float sqrt_blur = sqrtf(blur_radius);
   const bool cull = flags & TRB_CULL_BACKFACES;
-  if (max_face_count > 0) {
-    dim3 bgrid(ceil_div(max_face_count, 256), N);
-    bin_faces_kernel<false><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
-                                                   tile_count, tile_fill, tile_offset, pairs);
-    TRB_LAUNCH_CHECK();
-    alloc_tiles_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(tile_count, tile_offset, ntiles, header,
-                                                              (long long)pair_capacity);
-    TRB_LAUNCH_CHECK();
-    bin_faces_kernel<true><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
-                                                  tile_count, tile_fill, tile_offset, pairs);
-    TRB_LAUNCH_CHECK();
+  {
+    const int brc = run_binning(verts_ndc, faces, views, N, max_face_count, H, W, tg, ws, workspace, sqrt_blur,
+                                cull, (long long)pair_capacity, st);
+    if (brc != TRB_OK) return brc;
   }
   const dim3 grid(tg.tiles_x, tg.tiles_y, N);
   const bool persp = flags & TRB_PERSPECTIVE_CORRECT, clip = flags & TRB_CLIP_BARYCENTRIC;

@@ -105,6 +105,55 @@ __device__ __forceinline__ bool eval_pixel_face(const FaceXYZ& v, float px, floa
   return true;
 }
 
+// Same arithmetic as eval_pixel_face, split so that the fused kernel can (a) reuse the three edge
+// functions it already evaluated for its early reject and (b) postpone the distance when the
+// blur radius is zero (then only strictly-inside samples survive and the distance of the
+// winner is all that is ever needed).  `area` = edge(v2; v0, v1) + kEps, exactly as above.
+__device__ __forceinline__ bool eval_from_edges(const FaceXYZ& v, float area, float e0, float e1, float e2,
+                                                bool persp, bool clip, float& pz, float& c0, float& c1,
+                                                float& c2, bool& inside) {
+  const float w0 = fdiv(e0, area), w1 = fdiv(e1, area), w2 = fdiv(e2, area);
+  float b0 = w0, b1 = w1, b2 = w2;
+  if (persp) {
+    const float t0 = fmul(fmul(w0, v.z1), v.z2);
+    const float t1 = fmul(fmul(w1, v.z0), v.z2);
+    const float t2 = fmul(fmul(w2, v.z0), v.z1);
+    const float den = fmaxf(fadd(fadd(t0, t1), t2), kEps);
+    b0 = fdiv(t0, den); b1 = fdiv(t1, den); b2 = fdiv(t2, den);
+  }
+  c0 = b0; c1 = b1; c2 = b2;
+  if (clip) {
+    c0 = fmaxf(b0, 0.0f); c1 = fmaxf(b1, 0.0f); c2 = fmaxf(b2, 0.0f);
+    const float s = fmaxf(fadd(fadd(c0, c1), c2), 1e-5f);
+    c0 = fdiv(c0, s); c1 = fdiv(c1, s); c2 = fdiv(c2, s);
+  }
+  pz = fadd(fadd(fmul(c0, v.z0), fmul(c1, v.z1)), fmul(c2, v.z2));
+  inside = (b0 > 0.0f) && (b1 > 0.0f) && (b2 > 0.0f);
+  return !(pz < 0.0f);
+}
+
+__device__ __forceinline__ float triangle_d2(const FaceXYZ& v, float px, float py) {
+  const float e01 = point_segment_d2(px, py, v.x0, v.y0, v.x1, v.y1);
+  const float e02 = point_segment_d2(px, py, v.x0, v.y0, v.x2, v.y2);
+  const float e12 = point_segment_d2(px, py, v.x1, v.y1, v.x2, v.y2);
+  return min3f(e01, e02, e12);
+}
+
+// Runtime-flag variant of eval_pixel_face (identical operator sequence).
+__device__ __forceinline__ bool eval_pixel_face_rt(const FaceXYZ& v, float px, float py, bool persp,
+                                                   bool clip, float blur_radius, Sample& out) {
+  const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+  const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
+  const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
+  const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
+  bool inside;
+  if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, out.z, out.c0, out.c1, out.c2, inside)) return false;
+  const float dist = triangle_d2(v, px, py);
+  if (!inside && dist >= blur_radius) return false;
+  out.d = inside ? -dist : dist;
+  return true;
+}
+
 // (z, face) lexicographic order, A5.
 __device__ __forceinline__ bool cand_less(float za, int fa, float zb, int fb) {
   return (za < zb) || (za == zb && fa < fb);
@@ -138,10 +187,9 @@ __device__ __forceinline__ void point_segment_bwd(float px, float py, float ax, 
   gbx += gb * dx; gby += gb * dy;
 }
 
-template <bool PERSP, bool CLIP>
-__device__ __forceinline__ void sample_backward(const FaceXYZ& v, float px, float py, float gz,
-                                                float gb0, float gb1, float gb2, float gd,
-                                                float g[9]) {
+__device__ __forceinline__ void sample_backward_rt(const FaceXYZ& v, float px, float py, bool PERSP,
+                                                   bool CLIP, float gz, float gb0, float gb1, float gb2,
+                                                   float gd, float g[9]) {
   const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
   const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
   const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
@@ -210,6 +258,13 @@ __device__ __forceinline__ void sample_backward(const FaceXYZ& v, float px, floa
     else
       point_segment_bwd(px, py, v.x1, v.y1, v.x2, v.y2, gsd, g[3], g[4], g[6], g[7]);
   }
+}
+
+template <bool PERSP, bool CLIP>
+__device__ __forceinline__ void sample_backward(const FaceXYZ& v, float px, float py, float gz,
+                                                float gb0, float gb1, float gb2, float gd,
+                                                float g[9]) {
+  sample_backward_rt(v, px, py, PERSP, CLIP, gz, gb0, gb1, gb2, gd, g);
 }
 
 // ------------------------------------------------------------------------------------------

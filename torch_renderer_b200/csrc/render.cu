@@ -1,0 +1,749 @@
+// Fused render pipeline for sm_100a: everything `MeshRenderer.forward` and `loss.backward()` do for
+// one batch of views, in one C-ABI call each way (reference call sites: renderer.py:100-101,
+// torch_renderer.py:113-120,158, camera_pose_optimizer.py:244-250,303, mesh_deformer.py:197,221).
+//
+// Forward launches: vertex normals (2, Phong only) -> camera centres (1) -> world->NDC (1) -> tile
+// binning (memset + 3) -> ONE fine kernel that rasterises a 16x16 (or 8x8) tile per CTA and, in its
+// epilogue, interpolates attributes, lights and blends.  HBM traffic of the big kernel is exactly the
+// compulsory 28*K + 16 bytes per pixel of output (Fragments + RGBA) plus L2-resident mesh reads.
+//
+// Backward launches: one memset -> ONE kernel that re-reads Fragments + the image gradient, runs the
+// lighting model and the blend backward once per sample and chains straight into the rasteriser
+// backward (no grad_bary / grad_zbuf / grad_dists tensors exist), scattering with warp-aggregated
+// atomics -> camera-centre backward -> NDC->world backward -> vertex-normal backward (2).  Tiles the
+// forward found empty are skipped wholesale (`tile_hit`), so the backward touches only covered tiles.
+#include "raster_internal.cuh"
+#include "shade_math.cuh"
+
+namespace trb {
+
+// ---- 3x3 inverse (adjugate) ------------------------------------------------------------------
+__device__ __forceinline__ void inv3(const float* r, float a[9]) {
+  const float c00 = r[4] * r[8] - r[5] * r[7], c01 = r[5] * r[6] - r[3] * r[8], c02 = r[3] * r[7] - r[4] * r[6];
+  const float det = r[0] * c00 + r[1] * c01 + r[2] * c02;
+  const float id = 1.0f / det;
+  a[0] = c00 * id; a[1] = (r[2] * r[7] - r[1] * r[8]) * id; a[2] = (r[1] * r[5] - r[2] * r[4]) * id;
+  a[3] = c01 * id; a[4] = (r[0] * r[8] - r[2] * r[6]) * id; a[5] = (r[2] * r[3] - r[0] * r[5]) * id;
+  a[6] = c02 * id; a[7] = (r[1] * r[6] - r[0] * r[7]) * id; a[8] = (r[0] * r[4] - r[1] * r[3]) * id;
+}
+
+// camera centre C = -T * inv(R)  (row vectors)
+__global__ void camera_center_kernel(const float* __restrict__ R, const float* __restrict__ T,
+                                     float* __restrict__ vp, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float a[9];
+  inv3(R + 9 * (size_t)n, a);
+  const float* t = T + 3 * (size_t)n;
+  float* o = vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
+  o[0] = -(t[0] * a[0] + t[1] * a[3] + t[2] * a[6]);
+  o[1] = -(t[0] * a[1] + t[1] * a[4] + t[2] * a[7]);
+  o[2] = -(t[0] * a[2] + t[1] * a[5] + t[2] * a[8]);
+}
+
+// dC = -dT A - C dR A   =>   gT_i = -sum_k gC_k A_ik ;  gR_ij = -C_i * sum_k A_jk gC_k
+__global__ void camera_center_backward_kernel(const float* __restrict__ R, const float* __restrict__ vp,
+                                              const float* __restrict__ g_vp, float* __restrict__ gR,
+                                              float* __restrict__ gT, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float a[9];
+  inv3(R + 9 * (size_t)n, a);
+  const float* c = vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
+  const float* g = g_vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
+  float ag[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) ag[j] = a[3 * j] * g[0] + a[3 * j + 1] * g[1] + a[3 * j + 2] * g[2];
+  if (gT) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gT[3 * (size_t)n + i] -= ag[i];
+  }
+  if (gR) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gR[9 * (size_t)n + 3 * i + j] -= c[i] * ag[j];
+  }
+}
+
+// ---- fused fine pass ---------------------------------------------------------------------------
+struct FineArgs {
+  const float* verts_ndc; const int* faces; const trb_view* views;
+  int H, W, K; float blur_radius, sqrt_blur; unsigned flags; TileGrid tg;
+  const int* tile_count; const int* tile_offset; const int* pairs;
+  long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* tile_hit;
+  const float* view_params; const float* verts_world; const float* normals; const float* colors;
+  float sigma, gamma, bg0, bg1, bg2;
+};
+
+struct ShadeIn {
+  const float* verts_world; const float* normals; const float* colors; const int* faces;
+};
+
+template <int LIGHT>
+__device__ __forceinline__ F3 shade_sample(const ShadeIn& in, const trb_view& vd, const ViewParams& vp,
+                                           int local_face, float b0, float b1, float b2) {
+  const size_t r = (size_t)(vd.face_start + local_face);
+  const int i0 = __ldg(in.faces + 3 * r), i1 = __ldg(in.faces + 3 * r + 1), i2 = __ldg(in.faces + 3 * r + 2);
+  const F3 tex = interp3(b0, b1, b2, ld3(in.colors, i0), ld3(in.colors, i1), ld3(in.colors, i2));
+  if (LIGHT == TRB_LIGHT_AMBIENT) return {vp.amb[0] * tex.x, vp.amb[1] * tex.y, vp.amb[2] * tex.z};
+  const F3 P = interp3(b0, b1, b2, ld3(in.verts_world, i0), ld3(in.verts_world, i1), ld3(in.verts_world, i2));
+  const F3 nr = interp3(b0, b1, b2, ld3(in.normals, i0), ld3(in.normals, i1), ld3(in.normals, i2));
+  Lit lit;
+  return phong_color<LIGHT>(vp, P, nr, tex, lit);
+}
+
+template <int LTX, int LTY, bool K1, int SHADER, int LIGHT>
+__global__ void __launch_bounds__((1 << LTX) * (1 << LTY))
+render_fine_kernel(const FineArgs a) {
+  constexpr int TX = 1 << LTX, TY = 1 << LTY, NT = TX * TY;
+  __shared__ float4 s_bb[NT];   // xmin, xmax, ymin, ymax (blur inflated; empty when undrawable)
+  __shared__ float4 s_va[NT];   // x0 y0 z0 x1
+  __shared__ float4 s_vb[NT];   // y1 z1 x2 y2
+  __shared__ float2 s_vc[NT];   // z2, area (= edge(v2;v0,v1) + kEps)
+  __shared__ int s_id[NT];
+  extern __shared__ unsigned char s_dyn[];  // K>1: float kz[K][NT]; int kf[K][NT]
+  const int K = a.K;
+  float* kz = reinterpret_cast<float*>(s_dyn);
+  int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)(K1 ? 0 : K) * NT;
+
+  const int n = blockIdx.z;
+  const trb_view vd = a.views[n];
+  const int tid = threadIdx.x;
+  const int H = a.H, W = a.W;
+  const int xi = blockIdx.x * TX + (tid & (TX - 1));
+  const int yi = blockIdx.y * TY + (tid >> LTX);
+  const bool live = (xi < W) && (yi < H);
+  const float px = pix_to_ndc(W - 1 - xi, W, H);
+  const float py = pix_to_ndc(H - 1 - yi, H, W);
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+  const bool cull = a.flags & TRB_CULL_BACKFACES;
+  const bool hard_edges = a.blur_radius == 0.0f;
+  const float blur = a.blur_radius;
+
+  const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
+  int nlist = a.tile_count[t];
+  const int off = a.tile_offset[t];
+  const bool overflow = (nlist > 0) && (off < 0);
+  if (overflow) nlist = vd.face_count;
+
+  int cnt = 0;
+  float best_z = 0.0f; int best_f = -1;
+  Sample best_s = {0, 0, 0, 0, 0};
+  FaceXYZ best_v = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+  for (int base = 0; base < nlist; base += NT) {
+    const int j = base + tid;
+    float4 bb = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
+    if (j < nlist) {
+      const int lf = overflow ? j : a.pairs[off + j];
+      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
+      const bool ok = overflow ? face_is_drawable(v, cull) : true;
+      if (ok) {
+        bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
+        bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
+      }
+      s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
+      s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
+      s_vc[tid] = make_float2(v.z2, fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps));
+      s_id[tid] = lf;
+    }
+    s_bb[tid] = bb;
+    __syncthreads();
+    const int m = min(NT, nlist - base);
+    if (live) {
+      for (int q = 0; q < m; ++q) {
+        const float4 b = s_bb[q];
+        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
+        const float4 va = s_va[q], vb = s_vb[q];
+        const float2 vc = s_vc[q];
+        FaceXYZ v;
+        v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
+        v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
+        const float area = vc.y;
+        const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
+        const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
+        const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
+        if (hard_edges) {
+          // blur 0: only strictly-inside samples survive, and w_i = e_i / area keeps the sign of
+          // e_i * area exactly, so a non-positive edge is an exact (not approximate) reject.
+          if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                          : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+            continue;
+        }
+        Sample s;
+        bool inside;
+        if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, s.z, s.c0, s.c1, s.c2, inside)) continue;
+        if (hard_edges) {
+          if (!inside) continue;
+          s.d = 0.0f;  // filled in for the winner(s) only
+        } else {
+          const float dist = triangle_d2(v, px, py);
+          if (!inside && dist >= blur) continue;
+          s.d = inside ? -dist : dist;
+        }
+        const int f = s_id[q];
+        if (K1) {
+          if (best_f < 0 || cand_less(s.z, f, best_z, best_f)) { best_z = s.z; best_f = f; best_s = s; best_v = v; }
+        } else {
+          if (cnt == K && !cand_less(s.z, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
+          int pos = cnt < K ? cnt : K - 1;
+          while (pos > 0 && cand_less(s.z, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
+            kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
+            kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
+            --pos;
+          }
+          kz[pos * NT + tid] = s.z; kf[pos * NT + tid] = f;
+          if (cnt < K) ++cnt;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const bool hit = live && (K1 ? best_f >= 0 : cnt > 0);
+  const int any_hit = __syncthreads_or(hit ? 1 : 0);
+  if (tid == 0) a.tile_hit[t] = any_hit;
+  if (!live) return;
+
+  const size_t pix = ((size_t)n * H + yi) * W + xi;
+  ViewParams vp;
+  ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
+  if (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG) vp = load_view_params(a.view_params, n);
+  const float eps = 1e-10f;
+
+  if (K1) {
+    if (hit && hard_edges) best_s.d = -triangle_d2(best_v, px, py);
+    st_cs(a.p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
+    st_cs(a.zbuf + pix, hit ? best_s.z : -1.0f);
+    st_cs(a.dists + pix, hit ? best_s.d : -1.0f);
+    st_cs(a.bary + pix * 3 + 0, hit ? best_s.c0 : -1.0f);
+    st_cs(a.bary + pix * 3 + 1, hit ? best_s.c1 : -1.0f);
+    st_cs(a.bary + pix * 3 + 2, hit ? best_s.c2 : -1.0f);
+    if (SHADER == TRB_SHADER_NONE) return;
+    float4 out;
+    if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+      // 1 - (1 - p) is not bit-identical to p; keep the product form of sigmoid_alpha_blend
+      out = make_float4(1.0f, 1.0f, 1.0f, hit ? 1.0f - (1.0f - sigmoidf(-best_s.d / a.sigma)) : 0.0f);
+    } else if (!hit) {
+      out = make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+    } else {
+      const F3 c = shade_sample<LIGHT>(sin, vd, vp, best_f, best_s.c0, best_s.c1, best_s.c2);
+      if (SHADER == TRB_SHADER_HARD_PHONG) {
+        out = make_float4(c.x, c.y, c.z, 1.0f);
+      } else {
+        const float zrange = vp.zfar - vp.znear;
+        const float zinv = (vp.zfar - best_s.z) / zrange;
+        const float zmax = fmaxf(zinv, eps);
+        const float prob = sigmoidf(-best_s.d / a.sigma);
+        const float w = prob * expf((zinv - zmax) / a.gamma);
+        const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+        const float inv = 1.0f / (w + delta);
+        out = make_float4((w * c.x + delta * a.bg0) * inv, (w * c.y + delta * a.bg1) * inv,
+                          (w * c.z + delta * a.bg2) * inv, 1.0f - (1.0f - prob));
+      }
+    }
+    st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+    return;
+  }
+
+  // K > 1: layers are sorted front to back, so the softmax's max z_inv belongs to layer 0
+  const size_t o = pix * K;
+  float alpha = 1.0f, wsum = 0.0f, zmax = eps, zrange = 1.0f;
+  F3 acc = {0, 0, 0};
+  F3 hard_c = {a.bg0, a.bg1, a.bg2};
+  if (SHADER == TRB_SHADER_SOFT_PHONG) {
+    zrange = vp.zfar - vp.znear;
+    if (cnt > 0) zmax = fmaxf(eps, (vp.zfar - kz[tid]) / zrange);
+  }
+  for (int k = 0; k < K; ++k) {
+    Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+    long long pf = -1;
+    if (k < cnt) {
+      const int f = kf[k * NT + tid];
+      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
+      eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
+      pf = (long long)vd.p2f_base + f;
+      if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+        alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
+      } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+        if (k == 0) hard_c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+      } else if (SHADER == TRB_SHADER_SOFT_PHONG) {
+        const float prob = sigmoidf(-s.d / a.sigma);
+        alpha *= 1.0f - prob;
+        const float zinv = (vp.zfar - s.z) / zrange;
+        const float w = prob * expf((zinv - zmax) / a.gamma);
+        const F3 c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+        wsum += w;
+        acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
+      }
+    }
+    st_cs(a.p2f + o + k, pf);
+    st_cs(a.zbuf + o + k, s.z);
+    st_cs(a.dists + o + k, s.d);
+    st_cs(a.bary + (o + k) * 3 + 0, s.c0);
+    st_cs(a.bary + (o + k) * 3 + 1, s.c1);
+    st_cs(a.bary + (o + k) * 3 + 2, s.c2);
+  }
+  if (SHADER == TRB_SHADER_NONE) return;
+  float4 out;
+  if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+    out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
+  } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt > 0 ? 1.0f : 0.0f);
+  } else {
+    const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+    const float inv = 1.0f / (wsum + delta);
+    out = make_float4((acc.x + delta * a.bg0) * inv, (acc.y + delta * a.bg1) * inv,
+                      (acc.z + delta * a.bg2) * inv, 1.0f - alpha);
+  }
+  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+}
+
+// ---- fused backward ----------------------------------------------------------------------------
+struct BwdArgs {
+  const float* verts_ndc; const int* faces; const trb_view* views;
+  int H, W, K; unsigned flags; TileGrid tg; const int* tile_hit;
+  const long long* p2f; const float* zbuf; const float* bary; const float* dists;
+  const float* view_params; const float* verts_world; const float* normals; const float* colors;
+  const float* g_images; const float* g_zbuf; const float* g_bary; const float* g_dists;
+  float* g_verts_ndc; float* g_verts_world; float* g_normals; float* g_colors; float* g_view_params;
+  float sigma, gamma, bg0, bg1, bg2;
+};
+
+__device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, F3 g, float* base, int i0,
+                                         int i1, int i2) {
+  const float v[9] = {b0 * g.x, b0 * g.y, b0 * g.z, b1 * g.x, b1 * g.y, b1 * g.z, b2 * g.x, b2 * g.y, b2 * g.z};
+  float* const d[9] = {base + 3 * (size_t)i0, base + 3 * (size_t)i0 + 1, base + 3 * (size_t)i0 + 2,
+                       base + 3 * (size_t)i1, base + 3 * (size_t)i1 + 1, base + 3 * (size_t)i1 + 2,
+                       base + 3 * (size_t)i2, base + 3 * (size_t)i2 + 1, base + 3 * (size_t)i2 + 2};
+  warp_aggregated_add<9>(key, v, d);
+}
+
+template <bool K1, int SHADER, int LIGHT>
+__global__ void __launch_bounds__(256)
+render_backward_kernel(const BwdArgs a) {
+  const int t = (blockIdx.z * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
+  if (a.tile_hit[t] == 0) return;  // uniform for the CTA: the forward found no face in this tile
+  extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
+  const int NT = blockDim.x;
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int H = a.H, W = a.W, K = a.K;
+  const int xi = (blockIdx.x << a.tg.ltx) + (tid & ((1 << a.tg.ltx) - 1));
+  const int yi = (blockIdx.y << a.tg.lty) + (tid >> a.tg.ltx);
+  const bool live = (xi < W) && (yi < H);
+  const trb_view vd = a.views[n];
+  const float px = pix_to_ndc(W - 1 - xi, W, H);
+  const float py = pix_to_ndc(H - 1 - yi, H, W);
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+  const size_t pix = live ? ((size_t)n * H + yi) * W + xi : 0;
+  const size_t s0 = pix * K;
+  constexpr bool PHONG = (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG);
+  constexpr bool SOFT = (SHADER == TRB_SHADER_SOFT_PHONG);
+  constexpr bool SIL = (SHADER == TRB_SHADER_SOFT_SILHOUETTE);
+
+  int nk = 0;
+  if (live) {
+    while (nk < K && a.p2f[s0 + nk] >= 0) ++nk;
+  }
+  float4 g = make_float4(0, 0, 0, 0);
+  if (SHADER != TRB_SHADER_NONE && nk > 0) g = __ldg(reinterpret_cast<const float4*>(a.g_images) + pix);
+
+  ViewParams vp;
+  if (PHONG) vp = load_view_params(a.view_params, n);
+  const float eps = 1e-10f;
+  const float zrange = PHONG ? vp.zfar - vp.znear : 1.0f;
+
+  // ---- pass A: blend bookkeeping (no colours yet)
+  float zmax = eps; int kmax = -1;
+  float prod_nz = 1.0f; int zeros = 0;
+  float wsum = 0.0f, delta = 0.0f, den = 1.0f;
+  if (SOFT || SIL) {
+    for (int k = 0; k < nk; ++k) {
+      const float q = 1.0f - sigmoidf(-a.dists[s0 + k] / a.sigma);
+      if (q == 0.0f) ++zeros; else prod_nz *= q;
+      if (SOFT) {
+        const float zinv = (vp.zfar - a.zbuf[s0 + k]) / zrange;
+        if (zinv > zmax) { zmax = zinv; kmax = k; }
+      }
+    }
+  }
+  if (SOFT) {
+    for (int k = 0; k < nk; ++k) {
+      const float zinv = (vp.zfar - a.zbuf[s0 + k]) / zrange;
+      wsum += sigmoidf(-a.dists[s0 + k] / a.sigma) * expf((zinv - zmax) / a.gamma);
+    }
+    delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+    den = wsum + delta;
+  }
+  const float inv_den = 1.0f / den;
+
+  // ---- pass B: lighting model forward + backward, vertex-attribute scatters
+  const int nshade = (SHADER == TRB_SHADER_HARD_PHONG) ? min(nk, 1) : (PHONG ? nk : 0);
+  F3 acc = {0, 0, 0};
+  F3 g_lv_acc = {0, 0, 0}, g_cam_acc = {0, 0, 0};
+  float4 park1 = make_float4(0, 0, 0, 0);
+  if (PHONG) {
+    const int nloop = __reduce_max_sync(0xffffffffu, nshade);
+    for (int k = 0; k < nloop; ++k) {
+      const bool on = k < nshade;
+      int key = -1, i0 = 0, i1 = 0, i2 = 0;
+      float b0 = 0, b1 = 0, b2 = 0;
+      F3 gP = {0, 0, 0}, gN = {0, 0, 0}, gT = {0, 0, 0};
+      if (on) {
+        const size_t s = s0 + k;
+        const long long f = a.p2f[s];
+        key = (int)f;
+        const size_t r = (size_t)(vd.face_start + (int)(f - vd.p2f_base));
+        i0 = __ldg(a.faces + 3 * r); i1 = __ldg(a.faces + 3 * r + 1); i2 = __ldg(a.faces + 3 * r + 2);
+        b0 = a.bary[s * 3]; b1 = a.bary[s * 3 + 1]; b2 = a.bary[s * 3 + 2];
+        const F3 C0 = ld3(a.colors, i0), C1 = ld3(a.colors, i1), C2 = ld3(a.colors, i2);
+        const F3 tex = interp3(b0, b1, b2, C0, C1, C2);
+        F3 X0 = {0, 0, 0}, X1 = X0, X2 = X0, N0 = X0, N1 = X0, N2 = X0, P = X0, nr = X0;
+        if (LIGHT != TRB_LIGHT_AMBIENT) {
+          X0 = ld3(a.verts_world, i0); X1 = ld3(a.verts_world, i1); X2 = ld3(a.verts_world, i2);
+          N0 = ld3(a.normals, i0); N1 = ld3(a.normals, i1); N2 = ld3(a.normals, i2);
+          P = interp3(b0, b1, b2, X0, X1, X2);
+          nr = interp3(b0, b1, b2, N0, N1, N2);
+        }
+        Lit lit;
+        const F3 c = phong_color<LIGHT>(vp, P, nr, tex, lit);
+        float wn = 1.0f;
+        float gdotc = 0.0f;
+        if (SOFT) {
+          const float zinv = (vp.zfar - a.zbuf[s]) / zrange;
+          const float w = sigmoidf(-a.dists[s] / a.sigma) * expf((zinv - zmax) / a.gamma);
+          acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
+          gdotc = g.x * c.x + g.y * c.y + g.z * c.z;
+          wn = w * inv_den;
+        }
+        const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
+        F3 g_lv, g_cam;
+        phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
+        g_lv_acc.x += g_lv.x; g_lv_acc.y += g_lv.y; g_lv_acc.z += g_lv.z;
+        g_cam_acc.x += g_cam.x; g_cam_acc.y += g_cam.y; g_cam_acc.z += g_cam.z;
+        float gb0 = dot3(gT, C0), gb1 = dot3(gT, C1), gb2 = dot3(gT, C2);
+        if (LIGHT != TRB_LIGHT_AMBIENT) {
+          gb0 += dot3(gP, X0) + dot3(gN, N0); gb1 += dot3(gP, X1) + dot3(gN, N1); gb2 += dot3(gP, X2) + dot3(gN, N2);
+        }
+        const float4 pk = make_float4(gb0, gb1, gb2, gdotc);
+        if (K1) park1 = pk; else s_park[k * NT + tid] = pk;
+      }
+      if (a.g_colors) scatter9(key, b0, b1, b2, gT, a.g_colors, i0, i1, i2);
+      if (LIGHT != TRB_LIGHT_AMBIENT) {
+        if (a.g_verts_world) scatter9(key, b0, b1, b2, gP, a.g_verts_world, i0, i1, i2);
+        if (a.g_normals) scatter9(key, b0, b1, b2, gN, a.g_normals, i0, i1, i2);
+      }
+    }
+    if (LIGHT != TRB_LIGHT_AMBIENT && a.g_view_params) {
+      // a CTA never straddles two views: one atomic per warp and component
+      float vals[6] = {g_lv_acc.x, g_lv_acc.y, g_lv_acc.z, g_cam_acc.x, g_cam_acc.y, g_cam_acc.z};
+      float* gp = a.g_view_params + (size_t)n * TRB_VIEW_PARAM_STRIDE;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float sum = warp_sum(vals[i]);
+        if ((tid & 31) == 0 && sum != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), sum);
+      }
+    }
+  }
+
+  // ---- pass C: blend backward -> (g_z, g_bary, g_dist) per sample -> rasteriser backward
+  if (!a.g_verts_ndc) return;
+  float g_rgb = 0.0f, g_zmax = 0.0f;
+  if (SOFT) {
+    const F3 rgb = {(acc.x + delta * a.bg0) * inv_den, (acc.y + delta * a.bg1) * inv_den,
+                    (acc.z + delta * a.bg2) * inv_den};
+    g_rgb = g.x * rgb.x + g.y * rgb.y + g.z * rgb.z;
+    const float g_delta = ((g.x * a.bg0 + g.y * a.bg1 + g.z * a.bg2) - g_rgb) * inv_den;
+    const bool delta_clamped = !(expf((eps - zmax) / a.gamma) > eps);
+    g_zmax = delta_clamped ? 0.0f : -g_delta * delta / a.gamma;
+  }
+  const int nloop = __reduce_max_sync(0xffffffffu, nk);
+  for (int k = 0; k <= nloop; ++k) {
+    // iteration k == nloop routes the softmax-max gradient to its arg-max layer (soft Phong only)
+    const bool tail = (k == nloop);
+    if (tail && !SOFT) break;
+    const int kk = tail ? kmax : k;
+    const bool on = tail ? (kmax >= 0 && g_zmax != 0.0f) : (k < nk);
+    int key = -1, i0 = 0, i1 = 0, i2 = 0;
+    float gv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) gv[i] = 0.0f;
+    if (on) {
+      const size_t s = s0 + kk;
+      const long long f = a.p2f[s];
+      float gz = 0.0f, gd = 0.0f, gb0 = 0.0f, gb1 = 0.0f, gb2 = 0.0f;
+      if (tail) {
+        gz = -g_zmax / zrange;
+      } else {
+        if (SOFT || SIL) {
+          const float p = sigmoidf(-a.dists[s] / a.sigma);
+          const float q = 1.0f - p;
+          const float others = zeros == 0 ? prod_nz / q : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
+          float g_p = g.w * others;
+          if (SOFT) {
+            const float zinv = (vp.zfar - a.zbuf[s]) / zrange;
+            const float E = expf((zinv - zmax) / a.gamma);
+            const float4 pk = K1 ? park1 : s_park[k * NT + tid];
+            const float g_w = (pk.w - g_rgb) * inv_den;
+            g_p += g_w * E;
+            const float g_zinv = g_w * (p * E) / a.gamma;
+            g_zmax -= g_zinv;
+            gz = -g_zinv / zrange;
+          }
+          gd = g_p * p * q * (-1.0f / a.sigma);
+        }
+        if (PHONG && k < nshade) {
+          const float4 pk = K1 ? park1 : s_park[k * NT + tid];
+          gb0 = pk.x; gb1 = pk.y; gb2 = pk.z;
+        }
+        if (a.g_zbuf) gz += a.g_zbuf[s];
+        if (a.g_dists) gd += a.g_dists[s];
+        if (a.g_bary) { gb0 += a.g_bary[s * 3]; gb1 += a.g_bary[s * 3 + 1]; gb2 += a.g_bary[s * 3 + 2]; }
+      }
+      const int lf = (int)(f - vd.p2f_base);
+      const size_t r = (size_t)(vd.face_start + lf);
+      if (a.faces != nullptr) {
+        i0 = __ldg(a.faces + 3 * r) + vd.vert_delta;
+        i1 = __ldg(a.faces + 3 * r + 1) + vd.vert_delta;
+        i2 = __ldg(a.faces + 3 * r + 2) + vd.vert_delta;
+      } else {
+        i0 = 3 * (int)r; i1 = i0 + 1; i2 = i0 + 2;
+      }
+      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
+      sample_backward_rt(v, px, py, persp, clip, gz, gb0, gb1, gb2, gd, gv);
+      key = (int)f;
+    }
+    float* const dst[9] = {a.g_verts_ndc + 3 * (size_t)i0, a.g_verts_ndc + 3 * (size_t)i0 + 1,
+                           a.g_verts_ndc + 3 * (size_t)i0 + 2, a.g_verts_ndc + 3 * (size_t)i1,
+                           a.g_verts_ndc + 3 * (size_t)i1 + 1, a.g_verts_ndc + 3 * (size_t)i1 + 2,
+                           a.g_verts_ndc + 3 * (size_t)i2, a.g_verts_ndc + 3 * (size_t)i2 + 1,
+                           a.g_verts_ndc + 3 * (size_t)i2 + 2};
+    warp_aggregated_add<9>(key, gv, dst);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int check_render_cfg(const trb_render_config* c) {
+  if (!c) return TRB_ERR_BAD_ARG;
+  const trb_shade_config& s = c->shade;
+  if (s.N < 0 || s.H < 1 || s.W < 1 || s.K < 1) return TRB_ERR_BAD_ARG;
+  if (s.K > TRB_MAX_FACES_PER_PIXEL) return TRB_ERR_K_TOO_LARGE;
+  if (s.N > 65535) return TRB_ERR_BAD_ARG;
+  if (s.shader < -1 || s.shader > 2 || s.light_kind < 0 || s.light_kind > 2) return TRB_ERR_BAD_ARG;
+  if (s.shader != TRB_SHADER_NONE && (!(s.sigma > 0.0f) || !(s.gamma > 0.0f))) return TRB_ERR_BAD_ARG;
+  if (s.shader >= 0 && s.shader != TRB_SHADER_SOFT_SILHOUETTE && s.texture_mode != TRB_TEX_VERTEX)
+    return TRB_ERR_BAD_ARG;
+  if (!(c->blur_radius >= 0.0f) || c->max_face_count < 0 || c->max_vert_count < 0 || c->pair_capacity < 0 ||
+      c->num_world_verts < 0 || c->num_faces < 0 || c->num_ndc_verts < 0)
+    return TRB_ERR_BAD_ARG;
+  return TRB_OK;
+}
+
+static inline bool is_phong(int shader) {
+  return shader == TRB_SHADER_SOFT_PHONG || shader == TRB_SHADER_HARD_PHONG;
+}
+
+template <int LTX, int LTY, bool K1>
+static int launch_render_fine(int shader, int light, dim3 grid, size_t dyn, cudaStream_t st, const FineArgs& a) {
+  constexpr int NT = (1 << LTX) * (1 << LTY);
+#define TRB_RF(SH, L)                                                                             \
+  do {                                                                                            \
+    auto kern = render_fine_kernel<LTX, LTY, K1, SH, L>;                                          \
+    if (dyn > 0)                                                                                  \
+      TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    kern<<<grid, NT, dyn, st>>>(a);                                                               \
+  } while (0)
+  if (shader == TRB_SHADER_NONE) TRB_RF(TRB_SHADER_NONE, 0);
+  else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RF(TRB_SHADER_SOFT_SILHOUETTE, 0);
+  else if (shader == TRB_SHADER_SOFT_PHONG) {
+    if (light == 0) TRB_RF(TRB_SHADER_SOFT_PHONG, 0); else if (light == 1) TRB_RF(TRB_SHADER_SOFT_PHONG, 1);
+    else TRB_RF(TRB_SHADER_SOFT_PHONG, 2);
+  } else {
+    if (light == 0) TRB_RF(TRB_SHADER_HARD_PHONG, 0); else if (light == 1) TRB_RF(TRB_SHADER_HARD_PHONG, 1);
+    else TRB_RF(TRB_SHADER_HARD_PHONG, 2);
+  }
+#undef TRB_RF
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
+template <bool K1>
+static int launch_render_backward(int shader, int light, dim3 grid, int nt, size_t dyn, cudaStream_t st,
+                                  const BwdArgs& a) {
+#define TRB_RB(SH, L)                                                                             \
+  do {                                                                                            \
+    auto kern = render_backward_kernel<K1, SH, L>;                                                \
+    if (dyn > 0)                                                                                  \
+      TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    kern<<<grid, nt, dyn, st>>>(a);                                                               \
+  } while (0)
+  if (shader == TRB_SHADER_NONE) TRB_RB(TRB_SHADER_NONE, 0);
+  else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RB(TRB_SHADER_SOFT_SILHOUETTE, 0);
+  else if (shader == TRB_SHADER_SOFT_PHONG) {
+    if (light == 0) TRB_RB(TRB_SHADER_SOFT_PHONG, 0); else if (light == 1) TRB_RB(TRB_SHADER_SOFT_PHONG, 1);
+    else TRB_RB(TRB_SHADER_SOFT_PHONG, 2);
+  } else {
+    if (light == 0) TRB_RB(TRB_SHADER_HARD_PHONG, 0); else if (light == 1) TRB_RB(TRB_SHADER_HARD_PHONG, 1);
+    else TRB_RB(TRB_SHADER_HARD_PHONG, 2);
+  }
+#undef TRB_RB
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_bytes, int64_t* num_tiles,
+                                int64_t* backward_scratch_floats) {
+  const int rc = check_render_cfg(cfg);
+  if (rc != TRB_OK) return rc;
+  const trb_shade_config& s = cfg->shade;
+  const TileGrid tg = make_tile_grid(s.H, s.W, s.K);
+  if (workspace_bytes) *workspace_bytes = make_ws_layout(s.N, tg, cfg->pair_capacity).total;
+  if (num_tiles) *num_tiles = (int64_t)s.N * tg.tiles_x * tg.tiles_y;
+  // backward scratch: grad of NDC verts [num_ndc_verts,3] + grad normals [V,3] + grad raw normals [V,3]
+  if (backward_scratch_floats) *backward_scratch_floats = 3 * cfg->num_ndc_verts + 6 * cfg->num_world_verts;
+  return TRB_OK;
+}
+
+extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* views,
+                                  const float* verts_world, const int32_t* faces, const float* vert_colors,
+                                  const float* R, const float* T, const float* proj, float* view_params,
+                                  float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
+                                  float* zbuf, float* bary, float* dists, float* images, int32_t* tile_hit,
+                                  void* workspace, size_t workspace_bytes, int32_t* stats, int device,
+                                  trb_stream_t stream) {
+  int rc = check_render_cfg(cfg);
+  if (rc != TRB_OK) return rc;
+  const trb_shade_config& sc = cfg->shade;
+  const int N = sc.N, H = sc.H, W = sc.W, K = sc.K;
+  if (N == 0) return TRB_OK;
+  if (!views || !R || !T || !proj || !verts_ndc || !pix_to_face || !zbuf || !bary || !dists || !tile_hit ||
+      !workspace)
+    return TRB_ERR_BAD_ARG;
+  if (cfg->max_face_count > 0 && (!verts_world || !faces)) return TRB_ERR_BAD_ARG;
+  if (sc.shader != TRB_SHADER_NONE && !images) return TRB_ERR_BAD_ARG;
+  if (is_phong(sc.shader) && (!view_params || !vert_colors || !normals_raw || !normals)) return TRB_ERR_BAD_ARG;
+  const TileGrid tg = make_tile_grid(H, W, K);
+  const WsLayout ws = make_ws_layout(N, tg, cfg->pair_capacity);
+  if (workspace_bytes < ws.total) return TRB_ERR_WORKSPACE;
+  TRB_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (is_phong(sc.shader) && sc.light_kind != TRB_LIGHT_AMBIENT) {
+    rc = trb_vertex_normals_forward(verts_world, faces, cfg->num_world_verts, cfg->num_faces, normals_raw,
+                                    normals, device, stream);
+    if (rc != TRB_OK) return rc;
+    if (cfg->camera_center_from_rt) {
+      camera_center_kernel<<<ceil_div(N, 128), 128, 0, st>>>(R, T, view_params, N);
+      TRB_LAUNCH_CHECK();
+    }
+  }
+  rc = trb_transform_forward(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective,
+                             verts_ndc, device, stream);
+  if (rc != TRB_OK) return rc;
+  const float sqrt_blur = sqrtf(cfg->blur_radius);
+  rc = run_binning(verts_ndc, faces, views, N, cfg->max_face_count, H, W, tg, ws, workspace, sqrt_blur,
+                   cfg->raster_flags & TRB_CULL_BACKFACES, (long long)cfg->pair_capacity, st);
+  if (rc != TRB_OK) return rc;
+
+  unsigned char* wsb = (unsigned char*)workspace;
+  FineArgs a;
+  a.verts_ndc = verts_ndc; a.faces = faces; a.views = views;
+  a.H = H; a.W = W; a.K = K; a.blur_radius = cfg->blur_radius; a.sqrt_blur = sqrt_blur;
+  a.flags = cfg->raster_flags; a.tg = tg;
+  a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
+  a.pairs = (const int*)(wsb + ws.pairs);
+  a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
+  a.tile_hit = tile_hit;
+  a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
+  a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
+  a.bg2 = sc.background[2];
+  const dim3 grid(tg.tiles_x, tg.tiles_y, N);
+  if (K == 1) rc = launch_render_fine<4, 4, true>(sc.shader, sc.light_kind, grid, 0, st, a);
+  else if (tg.ltx == 4) rc = launch_render_fine<4, 4, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 256, st, a);
+  else rc = launch_render_fine<3, 3, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 64, st, a);
+  if (rc != TRB_OK) return rc;
+  if (stats) {
+    write_stats_kernel<<<1, 1, 0, st>>>((const int*)(wsb + ws.header), (long long)cfg->pair_capacity, stats);
+    TRB_LAUNCH_CHECK();
+  }
+  return TRB_OK;
+}
+
+extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view* views,
+                                   const float* verts_world, const int32_t* faces, const float* vert_colors,
+                                   const float* R, const float* T, const float* proj, const float* view_params,
+                                   const float* verts_ndc, const float* normals_raw, const float* normals,
+                                   const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                                   const float* dists, const int32_t* tile_hit, const float* grad_images,
+                                   const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                   float* grad_verts_world, float* grad_vert_colors, float* grad_R,
+                                   float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
+                                   int device, trb_stream_t stream) {
+  int rc = check_render_cfg(cfg);
+  if (rc != TRB_OK) return rc;
+  const trb_shade_config& sc = cfg->shade;
+  const int N = sc.N, H = sc.H, W = sc.W, K = sc.K;
+  if (N == 0 || cfg->max_face_count == 0) return TRB_OK;
+  if (!views || !verts_world || !faces || !R || !T || !proj || !verts_ndc || !pix_to_face || !zbuf || !bary ||
+      !dists || !tile_hit || !scratch)
+    return TRB_ERR_BAD_ARG;
+  if (sc.shader != TRB_SHADER_NONE && !grad_images) return TRB_ERR_BAD_ARG;
+  const bool phong = is_phong(sc.shader);
+  const bool lit = phong && sc.light_kind != TRB_LIGHT_AMBIENT;
+  if (phong && (!view_params || !vert_colors)) return TRB_ERR_BAD_ARG;
+  if (lit && (!normals_raw || !normals)) return TRB_ERR_BAD_ARG;
+  TRB_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const TileGrid tg = make_tile_grid(H, W, K);
+  const size_t n_ndc = (size_t)cfg->num_ndc_verts, V = (size_t)cfg->num_world_verts;
+  TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (3 * n_ndc + 6 * V) * sizeof(float), st));
+  float* g_ndc = scratch;
+  float* g_normals = scratch + 3 * n_ndc;
+  float* g_raw = g_normals + 3 * V;
+  const bool geom = grad_verts_world || grad_R || grad_T || grad_proj;
+  // the camera centre (when derived from R, T) feeds grad_R / grad_T through grad_view_params
+  float* g_vp = grad_view_params;
+  const bool cam_chain = lit && cfg->camera_center_from_rt && (grad_R || grad_T);
+  if (cam_chain && !g_vp) return TRB_ERR_BAD_ARG;  // caller provides the f32[N,20] buffer
+
+  BwdArgs a;
+  a.verts_ndc = verts_ndc; a.faces = faces; a.views = views; a.H = H; a.W = W; a.K = K;
+  a.flags = cfg->raster_flags; a.tg = tg; a.tile_hit = tile_hit;
+  a.p2f = (const long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
+  a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
+  a.g_images = grad_images; a.g_zbuf = grad_zbuf; a.g_bary = grad_bary; a.g_dists = grad_dists;
+  a.g_verts_ndc = geom ? g_ndc : nullptr;
+  a.g_verts_world = (lit && grad_verts_world) ? grad_verts_world : nullptr;
+  a.g_normals = (lit && grad_verts_world) ? g_normals : nullptr;
+  a.g_colors = phong ? grad_vert_colors : nullptr;
+  a.g_view_params = lit ? g_vp : nullptr;
+  a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
+  a.bg2 = sc.background[2];
+  const dim3 grid(tg.tiles_x, tg.tiles_y, N);
+  const int nt = (1 << tg.ltx) * (1 << tg.lty);
+  if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
+  else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, phong ? (size_t)K * nt * 16 : 0, st, a);
+  if (rc != TRB_OK) return rc;
+
+  if (cam_chain) {
+    camera_center_backward_kernel<<<ceil_div(N, 128), 128, 0, st>>>(R, view_params, g_vp, grad_R, grad_T, N);
+    TRB_LAUNCH_CHECK();
+  }
+  if (geom) {
+    rc = trb_transform_backward(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective, g_ndc,
+                                grad_verts_world, grad_R, grad_T, grad_proj, device, stream);
+    if (rc != TRB_OK) return rc;
+  }
+  if (lit && grad_verts_world) {
+    rc = trb_vertex_normals_backward(verts_world, faces, cfg->num_world_verts, cfg->num_faces, normals_raw,
+                                     g_normals, g_raw, grad_verts_world, device, stream);
+    if (rc != TRB_OK) return rc;
+  }
+  return TRB_OK;
+}

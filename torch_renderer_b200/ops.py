@@ -401,3 +401,112 @@ class _ShadeFn(torch.autograd.Function):
 def shade(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face, faces, table, cfg):
     return _ShadeFn.apply(bary, zbuf, dists, verts, normals, colors, texels, view_params, pix_to_face,
                           faces, table, cfg)
+
+
+# --------------------------------------------------------------------------------------------
+class _RenderFn(torch.autograd.Function):
+    """The fused pipeline: one C-ABI call forward (normals, camera centres, world->NDC, binning, fine
+    rasterisation + shading epilogue) and one backward.  ``spec`` carries the static configuration."""
+
+    @staticmethod
+    def forward(ctx, verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
+        _require_cuda(verts, "render")
+        dev = verts.device
+        L = _lib.lib()
+        verts, R, T, proj = _f32c(verts), _f32c(R), _f32c(T), _f32c(proj)
+        colors = None if colors is None else _f32c(colors)
+        # the kernel may write the camera centres into the block: never alias a cached tensor
+        vp = None if view_params is None else _f32c(view_params).clone()
+        N, (H, W), K = table.N, spec["image_size"], spec["K"]
+        shader = spec["shader"]
+        cfg = _lib.RenderConfig()
+        sc = cfg.shade
+        sc.N, sc.H, sc.W, sc.K = N, H, W, K
+        sc.shader, sc.light_kind, sc.texture_mode = shader, spec["light_kind"], _lib.TEX_VERTEX
+        sc.sigma, sc.gamma = spec["sigma"], spec["gamma"]
+        sc.background[0], sc.background[1], sc.background[2] = spec["background"]
+        cfg.blur_radius, cfg.raster_flags = spec["blur_radius"], spec["flags"]
+        cfg.perspective = int(spec["perspective"])
+        cfg.max_face_count, cfg.max_vert_count = table.max_face_count, table.max_vert_count
+        cfg.camera_center_from_rt = int(spec["camera_center_from_rt"])
+        cfg.num_world_verts, cfg.num_faces = verts.shape[0], (0 if faces is None else faces.shape[0])
+        cfg.num_ndc_verts = table.total_ndc_verts
+        cfg.pair_capacity = table.poll_capacity()
+        ws_bytes, n_tiles, n_scratch = ctypes.c_size_t(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        check(L.trb_render_sizes(ctypes.byref(cfg), ctypes.byref(ws_bytes), ctypes.byref(n_tiles),
+                                 ctypes.byref(n_scratch)), "render")
+        phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
+        ws = torch.empty((ws_bytes.value,), dtype=torch.uint8, device=dev)
+        verts_ndc = torch.empty((table.total_ndc_verts, 3), dtype=torch.float32, device=dev)
+        normals_raw = torch.empty_like(verts) if phong else None
+        normals = torch.empty_like(verts) if phong else None
+        p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        images = (torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if shader != _lib.SHADER_NONE
+                  else torch.empty((0,), dtype=torch.float32, device=dev))
+        tile_hit = torch.empty((max(n_tiles.value, 1),), dtype=torch.int32, device=dev)
+        stats = torch.empty((4,), dtype=torch.int32, device=dev)
+        with _timed("render_forward", dev):
+            check(L.trb_render_forward(
+                ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
+                _ptr(proj), _ptr(vp), _ptr(verts_ndc), _ptr(normals_raw), _ptr(normals), _ptr(p2f), _ptr(zbuf),
+                _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), _ptr(tile_hit),
+                _ptr(ws), ws_bytes.value, _ptr(stats), dev.index, _stream(dev)), "render")
+        lit = phong and spec["light_kind"] != _lib.LIGHT_AMBIENT
+        _bump(7 + (3 if lit else 0))
+        if table._pending is None and not torch.cuda.is_current_stream_capturing():
+            host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
+            host_stats.copy_(stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            table._pending = (host_stats, ev)
+        ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, verts_ndc, normals_raw, normals, p2f, zbuf,
+                              bary, dists, tile_hit)
+        ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch.value
+        ctx.mark_non_differentiable(p2f, verts_ndc)
+        ctx.set_materialize_grads(False)
+        return images, p2f, zbuf, bary, dists, verts_ndc
+
+    @staticmethod
+    def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists, g_ndc_ext):
+        (verts, colors, R, T, proj, vp, faces, verts_ndc, normals_raw, normals, p2f, zbuf, bary, dists,
+         tile_hit) = ctx.saved_tensors
+        table, cfg = ctx.table, ctx.cfg
+        dev = verts.device
+        need = ctx.needs_input_grad  # verts, colors, R, T, proj, view_params
+        N, V = table.N, verts.shape[0]
+        shader = cfg.shade.shader
+        if shader != _lib.SHADER_NONE and g_images is None:
+            g_images = torch.zeros((N, cfg.shade.H, cfg.shade.W, 4), dtype=torch.float32, device=dev)
+        # one zero-filled buffer for every accumulated gradient
+        sizes = [V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE]
+        flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
+        parts = list(flat.split(sizes))
+        g_verts, g_cols, g_R, g_T, g_proj, g_vp = parts
+        scratch = torch.empty((max(ctx.n_scratch, 1),), dtype=torch.float32, device=dev)
+        f32 = lambda t: None if t is None else _f32c(t)
+        want_vp = vp is not None
+        with _timed("render_backward", dev):
+            check(_lib.lib().trb_render_backward(
+                ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
+                _ptr(proj), _ptr(vp), _ptr(verts_ndc), _ptr(normals_raw), _ptr(normals), _ptr(p2f), _ptr(zbuf),
+                _ptr(bary), _ptr(dists), _ptr(tile_hit), _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
+                _ptr(f32(g_zbuf)), _ptr(f32(g_bary)), _ptr(f32(g_dists)),
+                _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
+                _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),
+                _ptr(g_vp if want_vp else None), _ptr(scratch), dev.index, _stream(dev)), "render backward")
+        _bump(7)
+        return (g_verts.view(V, 3) if need[0] else None,
+                g_cols.view(V, 3) if (need[1] and colors is not None) else None,
+                g_R.view(N, 3, 3) if need[2] else None, g_T.view(N, 3) if need[3] else None,
+                g_proj.view(N, 4) if need[4] else None,
+                g_vp.view(N, _lib.VIEW_PARAM_STRIDE) if (need[5] and want_vp) else None, None, None, None)
+
+
+def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
+    """Returns (images [N,H,W,4] or empty, pix_to_face, zbuf, bary, dists, verts_ndc)."""
+    if spec["K"] > _lib.MAX_FACES_PER_PIXEL:
+        raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
+    return _RenderFn.apply(verts, colors, R, T, proj, view_params, faces, table, spec)

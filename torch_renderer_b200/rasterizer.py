@@ -15,7 +15,7 @@ from typing import NamedTuple, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .structures import Meshes
 
 kMaxBinsPerDim = 22  # PyTorch3D refuses bin grids this large; kept for error parity
@@ -99,6 +99,22 @@ def rasterize_meshes(meshes: Meshes, image_size=256, blur_radius: float = 0.0, f
                          perspective_correct, clip_barycentric_coords, cull_backfaces)
 
 
+def _cached_projection(cameras, proj_kwargs):
+    """``cameras.ndc_projection_params`` memoised on the camera object while its intrinsics are
+    untouched constants (keyed on tensor identity + version) -- a handful of tiny launches saved per call."""
+    if proj_kwargs:
+        return cameras.ndc_projection_params(**proj_kwargs)
+    tensors = [(k, v) for k, v in cameras.__dict__.items() if torch.is_tensor(v) and k not in ("R", "T")]
+    if any(v.requires_grad for _, v in tensors):
+        return cameras.ndc_projection_params()
+    key = tuple((k, id(v), v._version) for k, v in tensors)
+    cache = cameras.__dict__.get("_trb_proj_cache")
+    if cache is None or cache[0] != key:
+        cache = (key, cameras.ndc_projection_params())
+        cameras.__dict__["_trb_proj_cache"] = cache
+    return cache[1]
+
+
 def _expand_views(t: torch.Tensor, N: int, what: str) -> torch.Tensor:
     if t.shape[0] == N:
         return t
@@ -135,27 +151,20 @@ class MeshRasterizer(nn.Module):
         # PyTorch3D's get_world_to_view_transform stores per-call overrides on the camera object;
         # the shaders' specular term (get_camera_center() without kwargs) relies on it.
         cameras.R, cameras.T = R, T
-        proj_kwargs = {k: v for k, v in kwargs.items() if k not in ("R", "T", "cameras")}
-        proj, perspective = cameras.ndc_projection_params(**proj_kwargs)
+        proj_kwargs = {k: v for k, v in kwargs.items()
+                       if k not in ("R", "T", "cameras", "lights", "materials", "blend_params", "raster_settings")}
+        proj, perspective = _cached_projection(cameras, proj_kwargs)
         R = _expand_views(R.to(dev), N, "R")
         T = _expand_views(T.to(dev), N, "T")
         proj = _expand_views(proj.to(dev), N, "projection")
         return cameras, R, T, proj, perspective
 
-    def transform(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
-        """World -> NDC (x, y) + view z for every (view, vertex): f32 [sum_n V_n, 3], view-major."""
-        _, R, T, proj, perspective = self._camera_inputs(meshes_world, kwargs)
-        return ops.transform_verts(meshes_world._unique_verts(), R, T, proj, meshes_world.view_table(),
-                                   perspective)
-
-    def forward(self, meshes_world: Meshes, **kwargs) -> Fragments:
+    def _resolve(self, meshes_world: Meshes, kwargs):
+        """Everything the kernels need for this call: camera tensors + the static raster spec."""
         raster_settings = kwargs.get("raster_settings", self.raster_settings)
         H, W = _parse_image_size(raster_settings.image_size)
         _check_bin_size(raster_settings.bin_size, H, W)
         cameras, R, T, proj, perspective = self._camera_inputs(meshes_world, kwargs)
-        table = meshes_world.view_table()
-        verts_ndc = ops.transform_verts(meshes_world._unique_verts(), R, T, proj, table, perspective)
-
         clip_bary = raster_settings.clip_barycentric_coords
         if clip_bary is None:
             clip_bary = raster_settings.blur_radius > 0.0
@@ -167,9 +176,24 @@ class MeshRasterizer(nn.Module):
         # z_clip_value: PyTorch3D clips faces against z = znear/2 for cameras that define znear.
         # Faces with a vertex at or behind the camera plane are dropped by the kernel (A4.2); proper
         # near-plane clipping of crossing faces is the `next` row 8f-3 and not built yet.
+        K = int(raster_settings.faces_per_pixel)
+        if K > _lib.MAX_FACES_PER_PIXEL:
+            raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
+        flags = ((_lib.PERSPECTIVE_CORRECT if persp_correct else 0) | (_lib.CLIP_BARYCENTRIC if clip_bary else 0)
+                 | (_lib.CULL_BACKFACES if raster_settings.cull_backfaces else 0))
+        spec = dict(image_size=(H, W), K=K, blur_radius=float(raster_settings.blur_radius), flags=flags,
+                    perspective=bool(perspective), shader=_lib.SHADER_NONE, light_kind=0, sigma=1.0, gamma=1.0,
+                    background=(0.0, 0.0, 0.0), camera_center_from_rt=False)
+        return cameras, R, T, proj, spec
 
-        p2f, zbuf, bary, dists = ops.rasterize(
-            verts_ndc, meshes_world.faces_packed_i32(), table, (H, W), raster_settings.blur_radius,
-            raster_settings.faces_per_pixel, bool(persp_correct), bool(clip_bary),
-            bool(raster_settings.cull_backfaces))
+    def transform(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
+        """World -> NDC (x, y) + view z for every (view, vertex): f32 [sum_n V_n, 3], view-major."""
+        _, R, T, proj, perspective = self._camera_inputs(meshes_world, kwargs)
+        return ops.transform_verts(meshes_world._unique_verts(), R, T, proj, meshes_world.view_table(),
+                                   perspective)
+
+    def forward(self, meshes_world: Meshes, **kwargs) -> Fragments:
+        _, R, T, proj, spec = self._resolve(meshes_world, kwargs)
+        _, p2f, zbuf, bary, dists, _ = ops.render(meshes_world._unique_verts(), None, R, T, proj, None,
+                                                  meshes_world.faces_packed_i32(), meshes_world.view_table(), spec)
         return Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)

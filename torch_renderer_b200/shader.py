@@ -42,8 +42,9 @@ def _scalar_rows(v, N: int, device) -> torch.Tensor:
     return _rows(v.reshape(-1, 1).float(), N, device, "znear/zfar")
 
 
-def _view_params(N, device, lights, materials, cameras, znear, zfar) -> torch.Tensor:
-    """f32 [N, 20] parameter block of the shade kernel (layout: include/trb.h)."""
+def _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera_center=True) -> torch.Tensor:
+    """f32 [N, 20] parameter block of the shade kernel (layout: include/trb.h).  With
+    ``with_camera_center=False`` the camera-centre slots are left zero (the fused kernel fills them)."""
     kind = getattr(lights, "kind", None)
     if kind not in _LIGHT_KIND:
         raise ValueError(f"unsupported lights object {type(lights).__name__}")
@@ -56,10 +57,31 @@ def _view_params(N, device, lights, materials, cameras, znear, zfar) -> torch.Te
         dif = _rows(materials.diffuse_color, N, device, "materials") * _rows(lights.diffuse_color, N, device, "lights")
         spec = _rows(materials.specular_color, N, device, "materials") * _rows(lights.specular_color, N, device, "lights")
     shin = _rows(materials.shininess.reshape(-1, 1), N, device, "materials")
-    cam = _rows(cameras.get_camera_center(), N, device, "cameras") if kind != "ambient" else zeros3
+    if kind != "ambient" and with_camera_center:
+        cam = _rows(cameras.get_camera_center(), N, device, "cameras")
+    else:
+        cam = zeros3
     pad = torch.zeros((N, 2), dtype=torch.float32, device=device)
     return torch.cat([vec, amb, dif, spec, shin, cam, _scalar_rows(znear, N, device),
                       _scalar_rows(zfar, N, device), pad], dim=1)
+
+
+def _cached_view_params(owner, N, device, lights, materials, cameras, znear, zfar, with_camera_center):
+    """Memoises the parameter block on the shader while every input is an unmodified constant."""
+    tensors = [v for obj in (lights, materials) for v in obj.__dict__.values() if torch.is_tensor(v)]
+    tensors += [v for v in (znear, zfar) if torch.is_tensor(v)]
+    if with_camera_center:
+        tensors += [cameras.R, cameras.T]
+    if any(t.requires_grad for t in tensors):
+        return _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera_center)
+    key = (N, str(device), with_camera_center, id(lights), id(materials),
+           tuple((id(t), t._version) for t in tensors),
+           tuple(float(v) for v in (znear, zfar) if not torch.is_tensor(v)))
+    cache = owner.__dict__.get("_trb_vp_cache")
+    if cache is None or cache[0] != key:
+        cache = (key, _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera_center))
+        owner.__dict__["_trb_vp_cache"] = cache
+    return cache[1]
 
 
 def _shade_config(fragments: Fragments, shader: int, light_kind: int, texture_mode: int,
@@ -125,7 +147,7 @@ class _ShaderBase(nn.Module):
             tex_mode = _lib.TEX_TEXELS
         znear = kwargs.get("znear", getattr(cameras, "znear", 1.0))
         zfar = kwargs.get("zfar", getattr(cameras, "zfar", 100.0))
-        vp = _view_params(N, dev, lights, materials, cameras, znear, zfar)
+        vp = _cached_view_params(self, N, dev, lights, materials, cameras, znear, zfar, True)
         cfg = _shade_config(fragments, shader, _LIGHT_KIND[lights.kind], tex_mode, blend_params)
         return ops.shade(fragments.bary_coords, fragments.zbuf, fragments.dists, meshes._unique_verts(),
                          meshes._unique_verts_normals(), colors, texels, vp, fragments.pix_to_face,
@@ -164,7 +186,11 @@ class SoftSilhouetteShader(nn.Module):
 
 
 class MeshRenderer(nn.Module):
-    """``images = shader(rasterizer(meshes_world, **kwargs), meshes_world, **kwargs)``."""
+    """``images = shader(rasterizer(meshes_world, **kwargs), meshes_world, **kwargs)``.
+
+    When the rasteriser is a ``MeshRasterizer`` and the shader one of this package's shaders on
+    per-vertex colours, the whole call is ONE fused C-ABI call (``trb_render_forward``) and its
+    backward another; otherwise the two modules are composed as written above."""
 
     def __init__(self, rasterizer, shader) -> None:
         super().__init__()
@@ -176,12 +202,72 @@ class MeshRenderer(nn.Module):
         self.shader.to(device)
         return self
 
+    def _render_fused(self, meshes_world: Meshes, kwargs):
+        """Returns (images, Fragments) through the fused pipeline, or None when it does not apply."""
+        from .rasterizer import MeshRasterizer
+        rast, shader = self.rasterizer, self.shader
+        if type(rast) is not MeshRasterizer:
+            return None
+        if type(shader) is SoftSilhouetteShader:
+            kind = _lib.SHADER_SOFT_SILHOUETTE
+        elif type(shader) is SoftPhongShader:
+            kind = _lib.SHADER_SOFT_PHONG
+        elif type(shader) is HardPhongShader:
+            kind = _lib.SHADER_HARD_PHONG
+        else:
+            return None
+        table = meshes_world.view_table()
+        N, dev = table.N, meshes_world.device
+        colors = vp = None
+        light_kind = 0
+        blend_params = kwargs.get("blend_params", shader.blend_params)
+        from_rt = False
+        phong = kind != _lib.SHADER_SOFT_SILHOUETTE
+        if phong:
+            textures = meshes_world.textures
+            if not isinstance(textures, TexturesVertex):
+                return None
+            shared = table.shared_mesh and textures._replicas == table.N
+            if table.shared_mesh and not shared:
+                return None
+            colors = textures._unique_features(shared)
+            if colors.shape[-1] != 3 or colors.shape[0] != meshes_world._unique_verts().shape[0]:
+                return None
+        cameras, R, T, proj, spec = rast._resolve(meshes_world, kwargs)   # also stores R, T on `cameras`
+        if phong:
+            shader_cameras = shader._get_cameras(**kwargs)
+            lights = kwargs.get("lights", shader.lights)
+            materials = kwargs.get("materials", shader.materials)
+            light_kind = _LIGHT_KIND.get(getattr(lights, "kind", None))
+            if light_kind is None:
+                return None
+            # the shader asks its camera object for the centre; when that is the object the rasteriser
+            # just used, the centre belongs to this call's R, T and the kernel derives it (and its
+            # gradient) itself
+            from_rt = shader_cameras is cameras
+            znear = kwargs.get("znear", getattr(shader_cameras, "znear", 1.0))
+            zfar = kwargs.get("zfar", getattr(shader_cameras, "zfar", 100.0))
+            vp = _cached_view_params(shader, N, dev, lights, materials, shader_cameras, znear, zfar, not from_rt)
+        bg = blend_params.background_color
+        bg = tuple(float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg))
+        spec.update(shader=kind, light_kind=light_kind, sigma=float(blend_params.sigma),
+                    gamma=float(blend_params.gamma), background=bg, camera_center_from_rt=from_rt)
+        images, p2f, zbuf, bary, dists, _ = ops.render(
+            meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec)
+        return images, Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+
     def forward(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
+        fused = self._render_fused(meshes_world, kwargs)
+        if fused is not None:
+            return fused[0]
         fragments = self.rasterizer(meshes_world, **kwargs)
         return self.shader(fragments, meshes_world, **kwargs)
 
 
 class MeshRendererWithFragments(MeshRenderer):
     def forward(self, meshes_world: Meshes, **kwargs):
+        fused = self._render_fused(meshes_world, kwargs)
+        if fused is not None:
+            return fused
         fragments = self.rasterizer(meshes_world, **kwargs)
         return self.shader(fragments, meshes_world, **kwargs), fragments

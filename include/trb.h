@@ -245,6 +245,12 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         float* grad_proj, float* grad_view_params, float* scratch, int device,
                         trb_stream_t stream);
 
+/* Measurement hook (bench.py's roofline leg): when non-NULL, the four cudaEvent_t handles are
+ * recorded on the call's stream immediately before / after the dominant kernel of
+ * trb_render_forward (the fused fine pass) and of trb_render_backward (the fused backward).
+ * Process-global and off by default; pass NULLs to switch it off again. */
+int trb_debug_set_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* bwd_stop);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "trb_render_sizes": [_c.POINTER(RenderConfig), _c.POINTER(_sz), _c.POINTER(_i64), _c.POINTER(_i64)],
     "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _i, _vp],
     "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_i, _vp],
+    "trb_debug_set_events": [_vp, _vp, _vp, _vp],
 }
 
 _lib = None

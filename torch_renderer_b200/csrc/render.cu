@@ -593,9 +593,17 @@ static int launch_render_backward(int shader, int light, dim3 grid, int nt, size
   return TRB_OK;
 }
 
+static cudaEvent_t g_dbg_events[4] = {nullptr, nullptr, nullptr, nullptr};
+
 }  // namespace trb
 
 using namespace trb;
+
+extern "C" int trb_debug_set_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* bwd_stop) {
+  g_dbg_events[0] = (cudaEvent_t)fwd_start; g_dbg_events[1] = (cudaEvent_t)fwd_stop;
+  g_dbg_events[2] = (cudaEvent_t)bwd_start; g_dbg_events[3] = (cudaEvent_t)bwd_stop;
+  return TRB_OK;
+}
 
 extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_bytes, int64_t* num_tiles,
                                 int64_t* backward_scratch_floats) {
@@ -664,10 +672,12 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
   const dim3 grid(tg.tiles_x, tg.tiles_y, N);
+  if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
   if (K == 1) rc = launch_render_fine<4, 4, true>(sc.shader, sc.light_kind, grid, 0, st, a);
   else if (tg.ltx == 4) rc = launch_render_fine<4, 4, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 256, st, a);
   else rc = launch_render_fine<3, 3, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 64, st, a);
   if (rc != TRB_OK) return rc;
+  if (g_dbg_events[1]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[1], st));
   if (stats) {
     write_stats_kernel<<<1, 1, 0, st>>>((const int*)(wsb + ws.header), (long long)cfg->pair_capacity, stats);
     TRB_LAUNCH_CHECK();
@@ -727,9 +737,11 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   a.bg2 = sc.background[2];
   const dim3 grid(tg.tiles_x, tg.tiles_y, N);
   const int nt = (1 << tg.ltx) * (1 << tg.lty);
+  if (g_dbg_events[2]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[2], st));
   if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
   else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, phong ? (size_t)K * nt * 16 : 0, st, a);
   if (rc != TRB_OK) return rc;
+  if (g_dbg_events[3]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[3], st));
 
   if (cam_chain) {
     camera_center_backward_kernel<<<ceil_div(N, 128), 128, 0, st>>>(R, view_params, g_vp, grad_R, grad_T, N);

@@ -15,22 +15,6 @@
 
 namespace trb {
 
-// Conservative range of pixel indices (in output order) whose centre can lie in [lo, hi].
-// Pixel-centre i' = S-1-i has NDC coordinate -off + (range*i' + off)/S  (A3).
-__device__ __forceinline__ void pixel_range(float lo, float hi, int S1, int S2, int& p_lo, int& p_hi) {
-  float range = 2.0f;
-  if (S1 > S2) range = (float)S1 * 2.0f / (float)S2;
-  const float off = 0.5f * range;
-  const float scale = (float)S1 / range;
-  float a = (lo + off) * scale - 0.5f;  // fractional flipped index of lo
-  float b = (hi + off) * scale - 0.5f;
-  a = fminf(fmaxf(a, -2.0f), (float)S1 + 1.0f);
-  b = fminf(fmaxf(b, -2.0f), (float)S1 + 1.0f);
-  int i_lo = (int)floorf(a) - 1, i_hi = (int)ceilf(b) + 1;  // +-1 px of slack (>> fp error)
-  i_lo = max(i_lo, 0); i_hi = min(i_hi, S1 - 1);
-  p_lo = S1 - 1 - i_hi; p_hi = S1 - 1 - i_lo;
-}
-
 // ------------------------------------------------------------------------------------------
 // Binning.  One thread per (view, face): count (FILL=false) or write (FILL=true) the face into
 // every tile its blur-inflated bounding box can touch.

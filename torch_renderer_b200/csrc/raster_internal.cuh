@@ -56,6 +56,24 @@ __device__ __forceinline__ FaceXYZ load_face(const float* __restrict__ verts,
   return v;
 }
 
+// Conservative range of pixel indices (in output order) whose centre can lie in [lo, hi].
+// Pixel-centre i' = S-1-i has NDC coordinate -off + (range*i' + off)/S  (A3), i.e. fractional index
+// (x + off) * S / range - 0.5.  The 0.02 px of slack is ~10x the fp32 error of that expression for
+// images up to 4096 px; the exact per-pixel bbox test of A4.2 is still applied afterwards.
+__device__ __forceinline__ void pixel_range(float lo, float hi, int S1, int S2, int& p_lo, int& p_hi) {
+  float range = 2.0f;
+  if (S1 > S2) range = (float)S1 * 2.0f / (float)S2;
+  const float off = 0.5f * range;
+  const float scale = (float)S1 / range;
+  float a = (lo + off) * scale - 0.5f;
+  float b = (hi + off) * scale - 0.5f;
+  a = fminf(fmaxf(a, -2.0f), (float)S1 + 1.0f);
+  b = fminf(fmaxf(b, -2.0f), (float)S1 + 1.0f);
+  int i_lo = (int)ceilf(a - 0.02f), i_hi = (int)floorf(b + 0.02f);
+  i_lo = max(i_lo, 0); i_hi = min(i_hi, S1 - 1);
+  p_lo = S1 - 1 - i_hi; p_hi = S1 - 1 - i_lo;
+}
+
 // Runs count -> allocate -> fill on `stream`; the workspace must have been laid out with
 // make_ws_layout and is zeroed here.  Defined in raster.cu.
 int run_binning(const float* verts_ndc, const int* faces, const trb_view* views, int N, int max_face_count,

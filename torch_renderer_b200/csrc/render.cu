@@ -300,6 +300,222 @@ render_fine_kernel(const FineArgs a) {
   st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
 }
 
+// ---- fused fine pass, faces_per_pixel == 1 ---------------------------------------------------------
+// The meshes this path sees most (cow at 512^2: ~3.5 px per face, ~200 faces per 16x16 tile) make a
+// per-pixel walk over the tile's face list 95% wasted bbox rejects.  Here the walk is FACE-parallel:
+// each thread takes one face of the list and visits only the pixels of that face's (tile-clipped)
+// bounding box, publishing candidates with a shared-memory atomicMin on a 64-bit key
+// (z bits << 32 | face) -- which is exactly the (z, face index) order of A5 because z >= 0.
+// Faces whose clipped bbox is large go to a second, pixel-parallel pass (one thread per pixel walking
+// the few big faces), so neither regime degenerates.  Tiles with an empty list only stream out the
+// background.
+constexpr int kSmallFaceMaxPixels = 64;
+
+__device__ __forceinline__ unsigned long long pack_key(float z, int f) {
+  const unsigned zb = (z == 0.0f) ? 0u : __float_as_uint(z);  // -0.0f must not sort last
+  return ((unsigned long long)zb << 32) | (unsigned)f;
+}
+
+template <int SHADER, int LIGHT>
+__global__ void __launch_bounds__(256)
+render_fine_k1_kernel(const FineArgs a) {
+  constexpr int TX = 16, TY = 16, NT = 256;
+  const int n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int H = a.H, W = a.W;
+  const int lx = tid & (TX - 1), ly = tid >> 4;
+  const int tile_x0 = blockIdx.x * TX, tile_y0 = blockIdx.y * TY;
+  const int xi = tile_x0 + lx, yi = tile_y0 + ly;
+  const bool live = (xi < W) && (yi < H);
+  const size_t pix = ((size_t)n * H + yi) * W + xi;
+  const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
+  int nlist = a.tile_count[t];
+
+  if (nlist == 0) {  // uniform: nothing can cover this tile
+    if (tid == 0) a.tile_hit[t] = 0;
+    if (!live) return;
+    st_cs(a.p2f + pix, -1ll);
+    st_cs(a.zbuf + pix, -1.0f);
+    st_cs(a.dists + pix, -1.0f);
+    st_cs(a.bary + pix * 3 + 0, -1.0f);
+    st_cs(a.bary + pix * 3 + 1, -1.0f);
+    st_cs(a.bary + pix * 3 + 2, -1.0f);
+    if (SHADER == TRB_SHADER_NONE) return;
+    const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                              : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+    st_cs(reinterpret_cast<float4*>(a.images) + pix, bgv);
+    return;
+  }
+
+  __shared__ unsigned long long s_key[NT];
+  __shared__ float s_px[TX], s_py[TY];
+  __shared__ float4 s_bb[NT];
+  __shared__ float4 s_va[NT];
+  __shared__ float4 s_vb[NT];
+  __shared__ float2 s_vc[NT];
+  __shared__ int s_id[NT];
+  __shared__ int s_big[NT];
+  __shared__ int s_nbig;
+
+  const trb_view vd = a.views[n];
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+  const bool cull = a.flags & TRB_CULL_BACKFACES;
+  const bool hard_edges = a.blur_radius == 0.0f;
+  const float blur = a.blur_radius;
+  const int off = a.tile_offset[t];
+  const bool overflow = off < 0;
+  if (overflow) nlist = vd.face_count;
+
+  s_key[tid] = ~0ull;
+  if (tid < TX) s_px[tid] = pix_to_ndc(W - 1 - (tile_x0 + tid), W, H);
+  else if (tid < TX + TY) s_py[tid - TX] = pix_to_ndc(H - 1 - (tile_y0 + tid - TX), H, W);
+  if (tid == 0) s_nbig = 0;
+  __syncthreads();
+  const float px = s_px[lx], py = s_py[ly];
+  unsigned long long best_key = ~0ull;
+  // last pixel column / row of the tile that exists in the image
+  const int x_hi = min(tile_x0 + TX, W) - 1, y_hi = min(tile_y0 + TY, H) - 1;
+
+  for (int base = 0; base < nlist; base += NT) {
+    const int j = base + tid;
+    if (j < nlist) {
+      const int lf = overflow ? j : a.pairs[off + j];
+      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
+      const bool ok = overflow ? face_is_drawable(v, cull) : true;
+      if (ok) {
+        float4 bb;
+        bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
+        bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
+        const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+        int c0, c1, r0, r1;
+        pixel_range(bb.x, bb.y, W, H, c0, c1);
+        pixel_range(bb.z, bb.w, H, W, r0, r1);
+        c0 = max(c0, tile_x0); c1 = min(c1, x_hi); r0 = max(r0, tile_y0); r1 = min(r1, y_hi);
+        const int npx = (c1 >= c0 && r1 >= r0) ? (c1 - c0 + 1) * (r1 - r0 + 1) : 0;
+        if (npx > kSmallFaceMaxPixels) {
+          // big face: stage it for the pixel-parallel pass
+          const int slot = atomicAdd(&s_nbig, 1);
+          s_big[slot] = tid;
+          s_bb[tid] = bb;
+          s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
+          s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
+          s_vc[tid] = make_float2(v.z2, area);
+          s_id[tid] = lf;
+        } else if (npx > 0) {
+          for (int r = r0; r <= r1; ++r) {
+            const float qy = s_py[r - tile_y0];
+            if ((qy > bb.w) || (qy < bb.z)) continue;
+            for (int c = c0; c <= c1; ++c) {
+              const float qx = s_px[c - tile_x0];
+              if ((qx > bb.y) || (qx < bb.x)) continue;
+              const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
+              const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
+              const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
+              if (hard_edges) {
+                // blur 0: w_i = e_i / area keeps the sign of e_i * area exactly => exact reject
+                if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                                : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+                  continue;
+              }
+              float pz, b0, b1, b2;
+              bool inside;
+              if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
+              if (!inside) {
+                if (hard_edges) continue;
+                if (triangle_d2(v, qx, qy) >= blur) continue;
+              }
+              atomicMin(&s_key[(r - tile_y0) * TX + (c - tile_x0)], pack_key(pz, lf));
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int nbig = s_nbig;
+    if (live) {
+      for (int i = 0; i < nbig; ++i) {
+        const int q = s_big[i];
+        const float4 b = s_bb[q];
+        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
+        const float4 va = s_va[q], vb = s_vb[q];
+        const float2 vc = s_vc[q];
+        FaceXYZ v;
+        v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
+        v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
+        const float area = vc.y;
+        const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
+        const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
+        const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
+        if (hard_edges) {
+          if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                          : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+            continue;
+        }
+        float pz, b0, b1, b2;
+        bool inside;
+        if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
+        if (!inside) {
+          if (hard_edges) continue;
+          if (triangle_d2(v, px, py) >= blur) continue;
+        }
+        const unsigned long long key = pack_key(pz, s_id[q]);
+        if (key < best_key) best_key = key;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nbig = 0;
+    // (the next iteration's first barrier orders this reset before any atomicAdd consumer reads it)
+    __syncthreads();
+  }
+
+  const unsigned long long key = min(best_key, s_key[tid]);
+  const bool hit = live && (key != ~0ull);
+  const int any_hit = __syncthreads_or(hit ? 1 : 0);
+  if (tid == 0) a.tile_hit[t] = any_hit;
+  if (!live) return;
+
+  Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+  int best_f = -1;
+  if (hit) {
+    best_f = (int)(unsigned)(key & 0xffffffffull);
+    const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, best_f);
+    eval_pixel_face_rt(v, px, py, persp, clip, blur, s);  // same operator sequence => same z as the key
+  }
+  st_cs(a.p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
+  st_cs(a.zbuf + pix, s.z);
+  st_cs(a.dists + pix, s.d);
+  st_cs(a.bary + pix * 3 + 0, s.c0);
+  st_cs(a.bary + pix * 3 + 1, s.c1);
+  st_cs(a.bary + pix * 3 + 2, s.c2);
+  if (SHADER == TRB_SHADER_NONE) return;
+  float4 out;
+  if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+    // 1 - (1 - p) is not bit-identical to p; keep the product form of sigmoid_alpha_blend
+    out = make_float4(1.0f, 1.0f, 1.0f, hit ? 1.0f - (1.0f - sigmoidf(-s.d / a.sigma)) : 0.0f);
+  } else if (!hit) {
+    out = make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+  } else {
+    const ViewParams vp = load_view_params(a.view_params, n);
+    const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
+    const F3 c = shade_sample<LIGHT>(sin, vd, vp, best_f, s.c0, s.c1, s.c2);
+    if (SHADER == TRB_SHADER_HARD_PHONG) {
+      out = make_float4(c.x, c.y, c.z, 1.0f);
+    } else {
+      const float eps = 1e-10f;
+      const float zrange = vp.zfar - vp.znear;
+      const float zinv = (vp.zfar - s.z) / zrange;
+      const float zmax = fmaxf(zinv, eps);
+      const float prob = sigmoidf(-s.d / a.sigma);
+      const float w = prob * expf((zinv - zmax) / a.gamma);
+      const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+      const float inv = 1.0f / (w + delta);
+      out = make_float4((w * c.x + delta * a.bg0) * inv, (w * c.y + delta * a.bg1) * inv,
+                        (w * c.z + delta * a.bg2) * inv, 1.0f - (1.0f - prob));
+    }
+  }
+  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+}
+
 // ---- fused backward ----------------------------------------------------------------------------
 struct BwdArgs {
   const float* verts_ndc; const int* faces; const trb_view* views;
@@ -569,6 +785,22 @@ static int launch_render_fine(int shader, int light, dim3 grid, size_t dyn, cuda
   return TRB_OK;
 }
 
+static int launch_render_fine_k1(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
+#define TRB_RF1(SH, L) render_fine_k1_kernel<SH, L><<<grid, 256, 0, st>>>(a)
+  if (shader == TRB_SHADER_NONE) TRB_RF1(TRB_SHADER_NONE, 0);
+  else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RF1(TRB_SHADER_SOFT_SILHOUETTE, 0);
+  else if (shader == TRB_SHADER_SOFT_PHONG) {
+    if (light == 0) TRB_RF1(TRB_SHADER_SOFT_PHONG, 0); else if (light == 1) TRB_RF1(TRB_SHADER_SOFT_PHONG, 1);
+    else TRB_RF1(TRB_SHADER_SOFT_PHONG, 2);
+  } else {
+    if (light == 0) TRB_RF1(TRB_SHADER_HARD_PHONG, 0); else if (light == 1) TRB_RF1(TRB_SHADER_HARD_PHONG, 1);
+    else TRB_RF1(TRB_SHADER_HARD_PHONG, 2);
+  }
+#undef TRB_RF1
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
 template <bool K1>
 static int launch_render_backward(int shader, int light, dim3 grid, int nt, size_t dyn, cudaStream_t st,
                                   const BwdArgs& a) {
@@ -673,7 +905,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.bg2 = sc.background[2];
   const dim3 grid(tg.tiles_x, tg.tiles_y, N);
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
-  if (K == 1) rc = launch_render_fine<4, 4, true>(sc.shader, sc.light_kind, grid, 0, st, a);
+  if (K == 1) rc = launch_render_fine_k1(sc.shader, sc.light_kind, grid, st, a);
   else if (tg.ltx == 4) rc = launch_render_fine<4, 4, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 256, st, a);
   else rc = launch_render_fine<3, 3, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 64, st, a);
   if (rc != TRB_OK) return rc;

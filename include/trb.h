@@ -217,7 +217,8 @@ typedef struct trb_render_config {
   int64_t pair_capacity;
 } trb_render_config;
 
-/* workspace_bytes: scratch for the forward; num_tiles: length of tile_hit (int32);
+/* workspace_bytes: scratch for the forward; num_tiles: length of tile_hit (int32: a count followed by
+ * the ids of the tiles in which the forward found a face -- the backward only visits those);
  * backward_scratch_floats: length of the f32 scratch the backward needs. */
 int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* num_tiles,
                      int64_t* backward_scratch_floats);

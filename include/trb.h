@@ -217,19 +217,19 @@ typedef struct trb_render_config {
   int64_t pair_capacity;
 } trb_render_config;
 
-/* workspace_bytes: scratch for the forward; num_tiles: length of tile_hit (int32: a count followed by
- * the ids of the tiles in which the forward found a face -- the backward only visits those);
- * backward_scratch_floats: length of the f32 scratch the backward needs. */
-int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* num_tiles,
+/* workspace_bytes: scratch for the forward; hit_pixels_len: length of hit_pixels (int32: a count
+ * followed by the linear ids of the pixels that got at least one face -- the backward visits only
+ * those); backward_scratch_floats: length of the f32 scratch the backward needs. */
+int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* hit_pixels_len,
                      int64_t* backward_scratch_floats);
 /* view_params f32[N,20] is in/out (camera centre filled in when camera_center_from_rt).
  * Outputs: verts_ndc f32[num_ndc_verts,3]; normals_raw, normals f32[num_world_verts,3] (Phong only);
- * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); tile_hit i32[num_tiles]. */
+ * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); hit_pixels i32[hit_pixels_len]. */
 int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        const float* verts_world, const int32_t* faces, const float* vert_colors,
                        const float* R, const float* T, const float* proj, float* view_params,
                        float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
-                       float* zbuf, float* bary, float* dists, float* images, int32_t* tile_hit,
+                       float* zbuf, float* bary, float* dists, float* images, int32_t* hit_pixels,
                        void* workspace, size_t workspace_bytes, int32_t* stats, int device,
                        trb_stream_t stream);
 /* grad_images may be NULL (shader NONE); grad_zbuf / grad_bary / grad_dists are optional extra
@@ -240,7 +240,7 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         const float* R, const float* T, const float* proj, const float* view_params,
                         const float* verts_ndc, const float* normals_raw, const float* normals,
                         const int64_t* pix_to_face, const float* zbuf, const float* bary,
-                        const float* dists, const int32_t* tile_hit, const float* grad_images,
+                        const float* dists, const int32_t* hit_pixels, const float* grad_images,
                         const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
                         float* grad_verts_world, float* grad_vert_colors, float* grad_R, float* grad_T,
                         float* grad_proj, float* grad_view_params, float* scratch, int device,

@@ -11,7 +11,7 @@
 // lighting model and the blend backward once per sample and chains straight into the rasteriser
 // backward (no grad_bary / grad_zbuf / grad_dists tensors exist), scattering with warp-aggregated
 // atomics -> camera-centre backward -> NDC->world backward -> vertex-normal backward (2).  Tiles the
-// forward found empty are skipped wholesale (`tile_hit`), so the backward touches only covered tiles.
+// forward leaves a compact list of covered pixels (`hit_pixels`); the backward visits only those.
 #include "raster_internal.cuh"
 #include "shade_math.cuh"
 
@@ -71,10 +71,32 @@ struct FineArgs {
   const float* verts_ndc; const int* faces; const trb_view* views;
   int H, W, K; float blur_radius, sqrt_blur; unsigned flags; TileGrid tg;
   const int* tile_count; const int* tile_offset; const int* pairs;
-  long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* tile_hit;
+  long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   float sigma, gamma, bg0, bg1, bg2;
 };
+
+// Appends the linear indices of the pixels of this CTA that got at least one face to the global
+// list the backward pass walks (hit_pixels[0] = count, [1..] = pixel ids, row-major inside a tile so
+// that neighbouring lanes of the backward still see neighbouring pixels).  Must be reached by every
+// thread of the CTA.
+template <int NT>
+__device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int pix) {
+  __shared__ int s_wcnt[NT / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ball = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) s_wcnt[warp] = __popc(ball);
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+    s_base = tot > 0 ? atomicAdd(hit_pixels, tot) : 0;
+  }
+  __syncthreads();
+  if (hit) hit_pixels[1 + s_base + s_wcnt[warp] + __popc(ball & ((1u << lane) - 1u))] = pix;
+}
 
 struct ShadeIn {
   const float* verts_world; const float* normals; const float* colors; const int* faces;
@@ -202,11 +224,10 @@ render_fine_kernel(const FineArgs a) {
   }
 
   const bool hit = live && (K1 ? best_f >= 0 : cnt > 0);
-  const int any_hit = __syncthreads_or(hit ? 1 : 0);
-  if (tid == 0 && any_hit) a.tile_hit[1 + atomicAdd(a.tile_hit, 1)] = t;  // compact list for the backward
+  const size_t pix = ((size_t)n * H + yi) * W + xi;
+  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
   if (!live) return;
 
-  const size_t pix = ((size_t)n * H + yi) * W + xi;
   ViewParams vp;
   ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
   if (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG) vp = load_view_params(a.view_params, n);
@@ -469,8 +490,7 @@ render_fine_k1_kernel(const FineArgs a) {
 
   const unsigned long long key = min(best_key, s_key[tid]);
   const bool hit = live && (key != ~0ull);
-  const int any_hit = __syncthreads_or(hit ? 1 : 0);
-  if (tid == 0 && any_hit) a.tile_hit[1 + atomicAdd(a.tile_hit, 1)] = t;  // compact list for the backward
+  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
   if (!live) return;
 
   Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
@@ -518,7 +538,7 @@ render_fine_k1_kernel(const FineArgs a) {
 // ---- fused backward ----------------------------------------------------------------------------
 struct BwdArgs {
   const float* verts_ndc; const int* faces; const trb_view* views;
-  int H, W, K; unsigned flags; TileGrid tg; const int* tile_hit;
+  int H, W, K; unsigned flags; const int* hit_pixels;
   const long long* p2f; const float* zbuf; const float* bary; const float* dists;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   const float* g_images; const float* g_zbuf; const float* g_bary; const float* g_dists;
@@ -536,38 +556,39 @@ __device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, 
 }
 
 template <bool K1, int SHADER, int LIGHT>
-__device__ __forceinline__ void render_backward_tile(const BwdArgs& a, int t, float4* s_park);
+__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
 
-// Persistent CTAs walk the compact list of tiles in which the forward pass found at least one face
-// (tile_hit[0] = count, tile_hit[1..] = tile ids).  Launching one CTA per tile instead costs more than
-// the useful work when 94% of the tiles are empty (ncu: half of all stall samples sat on the
-// early-exit load).
+// Persistent CTAs walk the compact list of covered pixels the forward pass left behind
+// (hit_pixels[0] = count, [1..] = linear pixel ids): every lane that enters the body has a pixel with
+// at least one face, however sparse the image is (cow at 512^2: 1.5% of the pixels).  Whole warps
+// enter together so the warp-level reductions inside stay legal.
 template <bool K1, int SHADER, int LIGHT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 render_backward_kernel(const BwdArgs a) {
   extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
-  const int count = a.tile_hit[0];
-  for (int i = blockIdx.x; i < count; i += gridDim.x)
-    render_backward_tile<K1, SHADER, LIGHT>(a, a.tile_hit[1 + i], s_park);
+  const int count = a.hit_pixels[0];
+  const int count_up = (count + 31) & ~31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count_up; i += stride) {
+    const bool live = i < count;
+    render_backward_pixel<K1, SHADER, LIGHT>(a, live, live ? a.hit_pixels[1 + i] : 0, s_park);
+  }
 }
 
 template <bool K1, int SHADER, int LIGHT>
-__device__ __forceinline__ void render_backward_tile(const BwdArgs& a, int t, float4* s_park) {
+__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park) {
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
-  const int tiles_per_view = a.tg.tiles_x * a.tg.tiles_y;
-  const int n = t / tiles_per_view;
-  const int trem = t - n * tiles_per_view;
-  const int tby = trem / a.tg.tiles_x, tbx = trem - tby * a.tg.tiles_x;
-  const int H = a.H, W = a.W, K = a.K;
-  const int xi = (tbx << a.tg.ltx) + (tid & ((1 << a.tg.ltx) - 1));
-  const int yi = (tby << a.tg.lty) + (tid >> a.tg.ltx);
-  const bool live = (xi < W) && (yi < H);
+  const int H = a.H, W = a.W;
+  const int K = K1 ? 1 : a.K;
+  const int n = pixi / (H * W);
+  const int prem = pixi - n * (H * W);
+  const int yi = prem / W, xi = prem - yi * W;
   const trb_view vd = a.views[n];
   const float px = pix_to_ndc(W - 1 - xi, W, H);
   const float py = pix_to_ndc(H - 1 - yi, H, W);
   const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
-  const size_t pix = live ? ((size_t)n * H + yi) * W + xi : 0;
+  const size_t pix = (size_t)pixi;
   const size_t s0 = pix * K;
   constexpr bool PHONG = (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG);
   constexpr bool SOFT = (SHADER == TRB_SHADER_SOFT_PHONG);
@@ -667,13 +688,21 @@ __device__ __forceinline__ void render_backward_tile(const BwdArgs& a, int t, fl
       }
     }
     if (LIGHT != TRB_LIGHT_AMBIENT && a.g_view_params) {
-      // a CTA never straddles two views: one atomic per warp and component
+      // one atomic per warp and component while the warp stays inside one view
       float vals[6] = {g_lv_acc.x, g_lv_acc.y, g_lv_acc.z, g_cam_acc.x, g_cam_acc.y, g_cam_acc.z};
       float* gp = a.g_view_params + (size_t)n * TRB_VIEW_PARAM_STRIDE;
+      const int n0 = __shfl_sync(0xffffffffu, n, 0);
+      if (__all_sync(0xffffffffu, !live || n == n0)) {
+        float* gp0 = a.g_view_params + (size_t)n0 * TRB_VIEW_PARAM_STRIDE;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float sum = warp_sum(vals[i]);
-        if ((tid & 31) == 0 && sum != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), sum);
+        for (int i = 0; i < 6; ++i) {
+          const float sum = warp_sum(live ? vals[i] : 0.0f);
+          if ((tid & 31) == 0 && sum != 0.0f) atomicAdd(gp0 + (i < 3 ? i : 10 + i), sum);
+        }
+      } else if (live) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          if (vals[i] != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), vals[i]);
       }
     }
   }
@@ -760,7 +789,7 @@ static int check_render_cfg(const trb_render_config* c) {
   const trb_shade_config& s = c->shade;
   if (s.N < 0 || s.H < 1 || s.W < 1 || s.K < 1) return TRB_ERR_BAD_ARG;
   if (s.K > TRB_MAX_FACES_PER_PIXEL) return TRB_ERR_K_TOO_LARGE;
-  if (s.N > 65535) return TRB_ERR_BAD_ARG;
+  if (s.N > 65535 || (int64_t)s.N * s.H * s.W >= 2147483647ll) return TRB_ERR_BAD_ARG;
   if (s.shader < -1 || s.shader > 2 || s.light_kind < 0 || s.light_kind > 2) return TRB_ERR_BAD_ARG;
   if (s.shader != TRB_SHADER_NONE && (!(s.sigma > 0.0f) || !(s.gamma > 0.0f))) return TRB_ERR_BAD_ARG;
   if (s.shader >= 0 && s.shader != TRB_SHADER_SOFT_SILHOUETTE && s.texture_mode != TRB_TEX_VERTEX)
@@ -858,8 +887,8 @@ extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_
   const trb_shade_config& s = cfg->shade;
   const TileGrid tg = make_tile_grid(s.H, s.W, s.K);
   if (workspace_bytes) *workspace_bytes = make_ws_layout(s.N, tg, cfg->pair_capacity).total;
-  // tile_hit = [count, tile ids...]
-  if (num_tiles) *num_tiles = (int64_t)s.N * tg.tiles_x * tg.tiles_y + 1;
+  // hit_pixels = [count, pixel ids...]
+  if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W + 1;
   // backward scratch: grad of NDC verts [num_ndc_verts,3] + grad normals [V,3] + grad raw normals [V,3]
   if (backward_scratch_floats) *backward_scratch_floats = 3 * cfg->num_ndc_verts + 6 * cfg->num_world_verts;
   return TRB_OK;
@@ -914,7 +943,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
   a.pairs = (const int*)(wsb + ws.pairs);
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
-  a.tile_hit = tile_hit;
+  a.hit_pixels = tile_hit;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
@@ -958,7 +987,6 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   if (lit && (!normals_raw || !normals)) return TRB_ERR_BAD_ARG;
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
-  const TileGrid tg = make_tile_grid(H, W, K);
   const size_t n_ndc = (size_t)cfg->num_ndc_verts, V = (size_t)cfg->num_world_verts;
   TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (3 * n_ndc + 6 * V) * sizeof(float), st));
   float* g_ndc = scratch;
@@ -972,7 +1000,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
 
   BwdArgs a;
   a.verts_ndc = verts_ndc; a.faces = faces; a.views = views; a.H = H; a.W = W; a.K = K;
-  a.flags = cfg->raster_flags; a.tg = tg; a.tile_hit = tile_hit;
+  a.flags = cfg->raster_flags; a.hit_pixels = tile_hit;
   a.p2f = (const long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.g_images = grad_images; a.g_zbuf = grad_zbuf; a.g_bary = grad_bary; a.g_dists = grad_dists;
@@ -983,12 +1011,13 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   a.g_view_params = lit ? g_vp : nullptr;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
-  const int nt = (1 << tg.ltx) * (1 << tg.lty);
-  const int ntiles = N * tg.tiles_x * tg.tiles_y;
-  const dim3 grid(min(ntiles, kNumSMs * (nt == 256 ? 4 : 16)));
+  // block size: the K>1 Phong path parks 16 B per (layer, thread) in shared memory
+  const int nt = (K == 1 || !phong) ? 128 : (K <= 24 ? 128 : (K <= 100 ? 64 : 32));
+  const size_t dyn = (K > 1 && phong) ? (size_t)K * nt * 16 : 0;
+  const dim3 grid(kNumSMs * (512 / nt));
   if (g_dbg_events[2]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[2], st));
   if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
-  else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, phong ? (size_t)K * nt * 16 : 0, st, a);
+  else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, dyn, st, a);
   if (rc != TRB_OK) return rc;
   if (g_dbg_events[3]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[3], st));
 

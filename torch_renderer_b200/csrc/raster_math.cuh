@@ -269,22 +269,38 @@ __device__ __forceinline__ void sample_backward(const FaceXYZ& v, float px, floa
 
 // ------------------------------------------------------------------------------------------
 // Warp-aggregated scatter: lanes of a warp that hold contributions for the same `key`
-// (a face or vertex id; < 0 = lane has nothing) are summed with shuffles and issued as ONE
-// atomicAdd per value.  When the warp holds many distinct keys (small-triangle regime) the
-// per-lane atomics hit distinct addresses anyway, so they are issued directly.
-template <int NV>
-__device__ __forceinline__ void warp_aggregated_add(int key, const float (&val)[NV],
-                                                    float* const (&dst)[NV]) {
+// (a face id; < 0 = lane has nothing) are summed with shuffles and issued as ONE atomicAdd per value.
+// When the warp holds many distinct keys (small-triangle regime) the per-lane atomics hit distinct
+// addresses anyway, so they are issued directly.  The grouping (one match.any) can be shared by
+// several scatters that use the same key.
+struct WarpGroups {
+  unsigned leaders;   // ballot of group leaders that hold a valid key
+  bool any;           // some lane has a key
+  bool aggregate;     // full warp and few groups: reduce with shuffles
+};
+
+__device__ __forceinline__ WarpGroups warp_groups(int key) {
+  WarpGroups wg;
   const unsigned active = __activemask();
   const unsigned have = __ballot_sync(active, key >= 0);
-  if (have == 0) return;
+  wg.any = have != 0;
+  wg.leaders = 0; wg.aggregate = false;
+  if (!wg.any) return wg;
   const unsigned peers = __match_any_sync(active, key);
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
-  const unsigned leaders = __ballot_sync(active, (lane == leader) && key >= 0);
-  const int ngroups = __popc(leaders);
-  if (active == 0xffffffffu && ngroups <= 4) {
-    unsigned todo = leaders;
+  wg.leaders = __ballot_sync(active, (lane == leader) && key >= 0);
+  wg.aggregate = (active == 0xffffffffu) && (__popc(wg.leaders) <= 4);
+  return wg;
+}
+
+template <int NV>
+__device__ __forceinline__ void warp_groups_add(const WarpGroups& wg, int key, const float (&val)[NV],
+                                                float* const (&dst)[NV]) {
+  if (!wg.any) return;
+  if (wg.aggregate) {
+    const int lane = threadIdx.x & 31;
+    unsigned todo = wg.leaders;
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
@@ -302,6 +318,114 @@ __device__ __forceinline__ void warp_aggregated_add(int key, const float (&val)[
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (val[i] != 0.0f) atomicAdd(dst[i], val[i]);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void warp_aggregated_add(int key, const float (&val)[NV],
+                                                    float* const (&dst)[NV]) {
+  const WarpGroups wg = warp_groups(key);
+  warp_groups_add<NV>(wg, key, val, dst);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast-math variants for backward passes.  Gradients are compared with fp64 autograd at 1e-3
+// relative L2, so nothing here has to reproduce the forward's IEEE sequence; the one decision
+// that matters -- whether the sample is inside its face -- is read off the sign of the saved
+// signed distance instead of being recomputed.
+__device__ __forceinline__ float pix_to_ndc_fast(int i, int S1, int S2) {
+  const float range = (S1 > S2) ? 2.0f * (float)S1 / (float)S2 : 2.0f;
+  return -0.5f * range + (range * (float)i + 0.5f * range) / (float)S1;
+}
+
+__device__ __forceinline__ float seg_d2_fast(float px, float py, float ax, float ay, float bx, float by,
+                                             float& t_out, bool& degenerate) {
+  const float bax = bx - ax, bay = by - ay;
+  const float l2 = bax * bax + bay * bay;
+  degenerate = l2 <= kEps;
+  if (degenerate) {
+    t_out = 1.0f;
+    const float dx = px - bx, dy = py - by;
+    return dx * dx + dy * dy;
+  }
+  float t = __fdividef(bax * (px - ax) + bay * (py - ay), l2);
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  t_out = t;
+  const float dx = ax + t * bax - px, dy = ay + t * bay - py;
+  return dx * dx + dy * dy;
+}
+
+__device__ __forceinline__ void sample_backward_fast(const FaceXYZ& v, float px, float py, bool persp,
+                                                     bool clip, bool inside, float gz, float gb0, float gb1,
+                                                     float gb2, float gd, float g[9]) {
+  const float area = edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1) + kEps;
+  const float inv_area = __frcp_rn(area);
+  const float e0 = (px - v.x1) * (v.y2 - v.y1) - (py - v.y1) * (v.x2 - v.x1);
+  const float e1 = (px - v.x2) * (v.y0 - v.y2) - (py - v.y2) * (v.x0 - v.x2);
+  const float e2 = (px - v.x0) * (v.y1 - v.y0) - (py - v.y0) * (v.x1 - v.x0);
+  const float w0 = e0 * inv_area, w1 = e1 * inv_area, w2 = e2 * inv_area;
+  float b0 = w0, b1 = w1, b2 = w2, inv_den = 1.0f, t0 = 0.f, t1 = 0.f, t2 = 0.f, tsum = 1.0f;
+  if (persp) {
+    t0 = w0 * v.z1 * v.z2; t1 = w1 * v.z0 * v.z2; t2 = w2 * v.z0 * v.z1;
+    tsum = t0 + t1 + t2;
+    inv_den = __frcp_rn(fmaxf(tsum, kEps));
+    b0 = t0 * inv_den; b1 = t1 * inv_den; b2 = t2 * inv_den;
+  }
+  float c0 = b0, c1 = b1, c2 = b2, m0 = b0, m1 = b1, m2 = b2, inv_s = 1.0f, ssum = 1.0f;
+  if (clip) {
+    m0 = fmaxf(b0, 0.0f); m1 = fmaxf(b1, 0.0f); m2 = fmaxf(b2, 0.0f);
+    ssum = m0 + m1 + m2;
+    inv_s = __frcp_rn(fmaxf(ssum, 1e-5f));
+    c0 = m0 * inv_s; c1 = m1 * inv_s; c2 = m2 * inv_s;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) g[i] = 0.0f;
+  g[2] = gz * c0; g[5] = gz * c1; g[8] = gz * c2;
+  const float gc0 = gb0 + gz * v.z0, gc1 = gb1 + gz * v.z1, gc2 = gb2 + gz * v.z2;
+  float gbb0 = gc0, gbb1 = gc1, gbb2 = gc2;
+  if (clip) {
+    float gs = -(gc0 * m0 + gc1 * m1 + gc2 * m2) * inv_s * inv_s;
+    if (!(ssum > 1e-5f)) gs = 0.0f;
+    gbb0 = b0 > 0.0f ? gc0 * inv_s + gs : 0.0f;
+    gbb1 = b1 > 0.0f ? gc1 * inv_s + gs : 0.0f;
+    gbb2 = b2 > 0.0f ? gc2 * inv_s + gs : 0.0f;
+  }
+  float gw0 = gbb0, gw1 = gbb1, gw2 = gbb2;
+  if (persp) {
+    float gden = -(gbb0 * t0 + gbb1 * t1 + gbb2 * t2) * inv_den * inv_den;
+    if (!(tsum > kEps)) gden = 0.0f;
+    const float gt0 = gbb0 * inv_den + gden, gt1 = gbb1 * inv_den + gden, gt2 = gbb2 * inv_den + gden;
+    gw0 = gt0 * v.z1 * v.z2; gw1 = gt1 * v.z0 * v.z2; gw2 = gt2 * v.z0 * v.z1;
+    g[2] += gt1 * w1 * v.z2 + gt2 * w2 * v.z1;
+    g[5] += gt0 * w0 * v.z2 + gt2 * w2 * v.z0;
+    g[8] += gt0 * w0 * v.z1 + gt1 * w1 * v.z0;
+  }
+  const float ge0 = gw0 * inv_area, ge1 = gw1 * inv_area, ge2 = gw2 * inv_area;
+  const float garea = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * inv_area * inv_area;
+  edge_bwd(px, py, v.x1, v.y1, v.x2, v.y2, ge0, g[3], g[4], g[6], g[7]);
+  edge_bwd(px, py, v.x2, v.y2, v.x0, v.y0, ge1, g[6], g[7], g[0], g[1]);
+  edge_bwd(px, py, v.x0, v.y0, v.x1, v.y1, ge2, g[0], g[1], g[3], g[4]);
+  g[6] += garea * (v.y1 - v.y0); g[7] += garea * (v.x0 - v.x1);
+  g[0] += garea * (v.y2 - v.y1); g[1] += garea * (v.x1 - v.x2);
+  g[3] += garea * (v.y0 - v.y2); g[4] += garea * (v.x2 - v.x0);
+  if (gd != 0.0f) {
+    float t01, t02, t12;
+    bool d01, d02, d12;
+    const float e01 = seg_d2_fast(px, py, v.x0, v.y0, v.x1, v.y1, t01, d01);
+    const float e02 = seg_d2_fast(px, py, v.x0, v.y0, v.x2, v.y2, t02, d02);
+    const float e12 = seg_d2_fast(px, py, v.x1, v.y1, v.x2, v.y2, t12, d12);
+    const float gsd = inside ? -gd : gd;
+    // arg-min edge (a, b): d/da = 2(1-t)(proj-p), d/db = 2t(proj-p); degenerate: d/db = 2(b-p)
+    float ax, ay, bx, by, t; bool deg; int ia, ib;
+    if (e01 <= e02 && e01 <= e12) { ax = v.x0; ay = v.y0; bx = v.x1; by = v.y1; t = t01; deg = d01; ia = 0; ib = 3; }
+    else if (e02 <= e01 && e02 <= e12) { ax = v.x0; ay = v.y0; bx = v.x2; by = v.y2; t = t02; deg = d02; ia = 0; ib = 6; }
+    else { ax = v.x1; ay = v.y1; bx = v.x2; by = v.y2; t = t12; deg = d12; ia = 3; ib = 6; }
+    const float qx = deg ? bx : ax + t * (bx - ax), qy = deg ? by : ay + t * (by - ay);
+    const float dx = qx - px, dy = qy - py;
+    const float ga = deg ? 0.0f : gsd * (1.0f - t) * 2.0f, gb = gsd * t * 2.0f;
+    // (ia, ib) are compile-time constants per branch after inlining; written generically here
+    if (ia == 0) { g[0] += ga * dx; g[1] += ga * dy; } else { g[3] += ga * dx; g[4] += ga * dy; }
+    if (ib == 3) { g[3] += gb * dx; g[4] += gb * dy; } else { g[6] += gb * dx; g[7] += gb * dy; }
   }
 }
 

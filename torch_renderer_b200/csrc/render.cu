@@ -337,35 +337,62 @@ __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
   return ((unsigned long long)zb << 32) | (unsigned)f;
 }
 
+// Background of one tile whose face list is empty: a pure streaming store of -1 Fragments and
+// the background colour.
+template <int SHADER>
+__device__ __forceinline__ void fill_empty_tile(const FineArgs& a, int n, int tbx, int tby) {
+  const int tid = threadIdx.x;
+  const int xi = tbx * 16 + (tid & 15), yi = tby * 16 + (tid >> 4);
+  if (xi >= a.W || yi >= a.H) return;
+  const size_t pix = ((size_t)n * a.H + yi) * a.W + xi;
+  st_cs(a.p2f + pix, -1ll);
+  st_cs(a.zbuf + pix, -1.0f);
+  st_cs(a.dists + pix, -1.0f);
+  st_cs(a.bary + pix * 3 + 0, -1.0f);
+  st_cs(a.bary + pix * 3 + 1, -1.0f);
+  st_cs(a.bary + pix * 3 + 2, -1.0f);
+  if (SHADER == TRB_SHADER_NONE) return;
+  const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                            : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+  st_cs(reinterpret_cast<float4*>(a.images) + pix, bgv);
+}
+
+template <int SHADER, int LIGHT>
+__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx, int tby, int nlist);
+
+// One CTA owns a strip of kStrip horizontally adjacent tiles.  It fetches all their list lengths
+// with one round trip, streams out every empty tile first (94% of the tiles for the cow at 512^2 --
+// with one tile per CTA the kernel was bound by CTA turnover x the latency of that single load, ncu:
+// 28% of all stall samples), then rasterises the non-empty ones.
+constexpr int kStrip = 8;
+
 template <int SHADER, int LIGHT>
 __global__ void __launch_bounds__(256)
 render_fine_k1_kernel(const FineArgs a) {
+  const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * kStrip;
+  const int* counts = a.tile_count + (size_t)(n * a.tg.tiles_y + tby) * a.tg.tiles_x;
+  int cnt[kStrip];
+#pragma unroll
+  for (int s = 0; s < kStrip; ++s) cnt[s] = (tbx0 + s < a.tg.tiles_x) ? __ldg(counts + tbx0 + s) : -1;
+#pragma unroll
+  for (int s = 0; s < kStrip; ++s)
+    if (cnt[s] == 0) fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
+#pragma unroll 1
+  for (int s = 0; s < kStrip; ++s)
+    if (cnt[s] > 0) raster_tile_k1<SHADER, LIGHT>(a, n, tbx0 + s, tby, cnt[s]);
+}
+
+template <int SHADER, int LIGHT>
+__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx, int tby, int nlist) {
   constexpr int TX = 16, TY = 16, NT = 256;
-  const int n = blockIdx.z;
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W;
   const int lx = tid & (TX - 1), ly = tid >> 4;
-  const int tile_x0 = blockIdx.x * TX, tile_y0 = blockIdx.y * TY;
+  const int tile_x0 = tbx * TX, tile_y0 = tby * TY;
   const int xi = tile_x0 + lx, yi = tile_y0 + ly;
   const bool live = (xi < W) && (yi < H);
   const size_t pix = ((size_t)n * H + yi) * W + xi;
-  const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
-  int nlist = a.tile_count[t];
-
-  if (nlist == 0) {  // uniform: nothing can cover this tile
-    if (!live) return;
-    st_cs(a.p2f + pix, -1ll);
-    st_cs(a.zbuf + pix, -1.0f);
-    st_cs(a.dists + pix, -1.0f);
-    st_cs(a.bary + pix * 3 + 0, -1.0f);
-    st_cs(a.bary + pix * 3 + 1, -1.0f);
-    st_cs(a.bary + pix * 3 + 2, -1.0f);
-    if (SHADER == TRB_SHADER_NONE) return;
-    const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
-                                                              : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
-    st_cs(reinterpret_cast<float4*>(a.images) + pix, bgv);
-    return;
-  }
+  const int t = (n * a.tg.tiles_y + tby) * a.tg.tiles_x + tbx;
 
   __shared__ unsigned long long s_key[NT];
   __shared__ float s_px[TX], s_py[TY];
@@ -562,8 +589,11 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
 // (hit_pixels[0] = count, [1..] = linear pixel ids): every lane that enters the body has a pixel with
 // at least one face, however sparse the image is (cow at 512^2: 1.5% of the pixels).  Whole warps
 // enter together so the warp-level reductions inside stay legal.
+template <int SHADER, int LIGHT>
+__device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
+
 template <bool K1, int SHADER, int LIGHT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, K1 ? 4 : 1)
 render_backward_kernel(const BwdArgs a) {
   extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
   const int count = a.hit_pixels[0];
@@ -571,8 +601,160 @@ render_backward_kernel(const BwdArgs a) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count_up; i += stride) {
     const bool live = i < count;
-    render_backward_pixel<K1, SHADER, LIGHT>(a, live, live ? a.hit_pixels[1 + i] : 0, s_park);
+    const int pixi = live ? a.hit_pixels[1 + i] : 0;
+    if (K1) render_backward_pixel_k1<SHADER, LIGHT>(a, live, pixi);
+    else render_backward_pixel<false, SHADER, LIGHT>(a, live, pixi, s_park);
   }
+}
+
+// faces_per_pixel == 1: straight-line code, every quantity computed once, fast-math divisions and
+// transcendentals, all pixel-indexed loads issued up front, one match.any shared by the four scatters.
+template <int SHADER, int LIGHT>
+__device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi) {
+  constexpr bool PHONG = (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG);
+  constexpr bool SOFT = (SHADER == TRB_SHADER_SOFT_PHONG);
+  constexpr bool SIL = (SHADER == TRB_SHADER_SOFT_SILHOUETTE);
+  constexpr bool LIT = PHONG && LIGHT != TRB_LIGHT_AMBIENT;
+  const int H = a.H, W = a.W, HW = H * W;
+  const int n = pixi / HW;
+  const int prem = pixi - n * HW;
+  const int yi = prem / W, xi = prem - yi * W;
+  const size_t pix = (size_t)pixi;
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+
+  // ---- every pixel-indexed load first (independent of each other: one DRAM round trip)
+  const long long f = live ? a.p2f[pix] : -1;
+  const bool on = f >= 0;
+  float4 g = make_float4(0, 0, 0, 0);
+  float z = 0.0f, d = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+  float gz = 0.0f, gd = 0.0f, gb0 = 0.0f, gb1 = 0.0f, gb2 = 0.0f;
+  if (on) {
+    if (SHADER != TRB_SHADER_NONE) g = __ldg(reinterpret_cast<const float4*>(a.g_images) + pix);
+    z = a.zbuf[pix]; d = a.dists[pix];
+    if (PHONG) { b0 = a.bary[pix * 3]; b1 = a.bary[pix * 3 + 1]; b2 = a.bary[pix * 3 + 2]; }
+    if (a.g_zbuf) gz = a.g_zbuf[pix];
+    if (a.g_dists) gd = a.g_dists[pix];
+    if (a.g_bary) { gb0 = a.g_bary[pix * 3]; gb1 = a.g_bary[pix * 3 + 1]; gb2 = a.g_bary[pix * 3 + 2]; }
+  }
+  const trb_view vd = a.views[n];
+  const int lf = on ? (int)(f - vd.p2f_base) : 0;
+  const size_t r = (size_t)(vd.face_start + lf);
+  int w0i = 0, w1i = 0, w2i = 0;  // world-space vertex rows
+  if (on && a.faces != nullptr) { w0i = __ldg(a.faces + 3 * r); w1i = __ldg(a.faces + 3 * r + 1); w2i = __ldg(a.faces + 3 * r + 2); }
+  const int key = on ? (int)f : -1;
+  const WarpGroups wg = warp_groups(key);
+
+  // ---- blend (K = 1) and lighting
+  if (SOFT || SIL || PHONG) {
+    float p = 0.0f, q = 1.0f;
+    if (SOFT || SIL) { p = __frcp_rn(1.0f + __expf(d / a.sigma)); q = 1.0f - p; }  // sigmoid(-d/sigma)
+    float g_p = g.w;  // alpha = p for a single layer
+    if (PHONG) {
+      ViewParams vp = load_view_params(a.view_params, n);
+      F3 C0 = {0, 0, 0}, C1 = C0, C2 = C0, X0 = C0, X1 = C0, X2 = C0, N0 = C0, N1 = C0, N2 = C0;
+      if (on) {
+        C0 = ld3(a.colors, w0i); C1 = ld3(a.colors, w1i); C2 = ld3(a.colors, w2i);
+        if (LIT) {
+          X0 = ld3(a.verts_world, w0i); X1 = ld3(a.verts_world, w1i); X2 = ld3(a.verts_world, w2i);
+          N0 = ld3(a.normals, w0i); N1 = ld3(a.normals, w1i); N2 = ld3(a.normals, w2i);
+        }
+      }
+      const F3 tex = interp3(b0, b1, b2, C0, C1, C2);
+      const F3 P = interp3(b0, b1, b2, X0, X1, X2);
+      const F3 nr = interp3(b0, b1, b2, N0, N1, N2);
+      Lit lit;
+      const F3 c = phong_color<LIGHT>(vp, P, nr, tex, lit);
+      float wn = 1.0f;
+      if (SOFT) {
+        const float eps = 1e-10f;
+        const float inv_zrange = __frcp_rn(vp.zfar - vp.znear);
+        const float inv_gamma = __frcp_rn(a.gamma);
+        const float zinv = (vp.zfar - z) * inv_zrange;
+        const float zmax = fmaxf(zinv, eps);
+        const float E = __expf((zinv - zmax) * inv_gamma);
+        const float w = p * E;
+        const float dexp = __expf((eps - zmax) * inv_gamma);
+        const float delta = fmaxf(dexp, eps);
+        const float inv_den = __frcp_rn(w + delta);
+        const F3 rgb = {(w * c.x + delta * a.bg0) * inv_den, (w * c.y + delta * a.bg1) * inv_den,
+                        (w * c.z + delta * a.bg2) * inv_den};
+        const float g_rgb = g.x * rgb.x + g.y * rgb.y + g.z * rgb.z;
+        const float g_w = ((g.x * c.x + g.y * c.y + g.z * c.z) - g_rgb) * inv_den;
+        const float g_delta = ((g.x * a.bg0 + g.y * a.bg1 + g.z * a.bg2) - g_rgb) * inv_den;
+        g_p += g_w * E;
+        // d/dz_inv: directly through w and (when z_inv is the softmax max) through z_max
+        const float g_zinv = g_w * w * inv_gamma;
+        float g_zmax = (dexp > eps ? -g_delta * delta * inv_gamma : 0.0f) - g_zinv;
+        const float g_zinv_total = g_zinv + (zinv > eps ? g_zmax : 0.0f);
+        gz += -g_zinv_total * inv_zrange;
+        wn = w * inv_den;
+      }
+      const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
+      F3 gT, gP, gN, g_lv, g_cam;
+      phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
+      gb0 += dot3(gT, C0); gb1 += dot3(gT, C1); gb2 += dot3(gT, C2);
+      if (LIT) {
+        gb0 += dot3(gP, X0) + dot3(gN, N0); gb1 += dot3(gP, X1) + dot3(gN, N1); gb2 += dot3(gP, X2) + dot3(gN, N2);
+      }
+      auto scatter = [&](float* base, F3 gv) {
+        const float v[9] = {b0 * gv.x, b0 * gv.y, b0 * gv.z, b1 * gv.x, b1 * gv.y, b1 * gv.z,
+                            b2 * gv.x, b2 * gv.y, b2 * gv.z};
+        float* const dptr[9] = {base + 3 * (size_t)w0i, base + 3 * (size_t)w0i + 1, base + 3 * (size_t)w0i + 2,
+                                base + 3 * (size_t)w1i, base + 3 * (size_t)w1i + 1, base + 3 * (size_t)w1i + 2,
+                                base + 3 * (size_t)w2i, base + 3 * (size_t)w2i + 1, base + 3 * (size_t)w2i + 2};
+        warp_groups_add<9>(wg, key, v, dptr);
+      };
+      if (a.g_colors) scatter(a.g_colors, gT);
+      if (LIT) {
+        if (a.g_verts_world) scatter(a.g_verts_world, gP);
+        if (a.g_normals) scatter(a.g_normals, gN);
+        if (a.g_view_params) {
+          float vals[6] = {g_lv.x, g_lv.y, g_lv.z, g_cam.x, g_cam.y, g_cam.z};
+          const int n0 = __shfl_sync(0xffffffffu, n, 0);
+          if (__all_sync(0xffffffffu, !on || n == n0)) {
+            float* gp0 = a.g_view_params + (size_t)n0 * TRB_VIEW_PARAM_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const float sum = warp_sum(on ? vals[i] : 0.0f);
+              if ((threadIdx.x & 31) == 0 && sum != 0.0f) atomicAdd(gp0 + (i < 3 ? i : 10 + i), sum);
+            }
+          } else if (on) {
+            float* gp = a.g_view_params + (size_t)n * TRB_VIEW_PARAM_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+              if (vals[i] != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), vals[i]);
+          }
+        }
+      }
+    }
+    if (SOFT || SIL) gd += g_p * p * q * (-1.0f / a.sigma);
+  }
+
+  // ---- rasteriser backward
+  if (!a.g_verts_ndc) return;
+  float gv[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gv[i] = 0.0f;
+  int i0 = 0, i1 = 0, i2 = 0;
+  if (on) {
+    if (a.faces != nullptr) { i0 = w0i + vd.vert_delta; i1 = w1i + vd.vert_delta; i2 = w2i + vd.vert_delta; }
+    else { i0 = 3 * (int)r; i1 = i0 + 1; i2 = i0 + 2; }
+    FaceXYZ v;
+    const float* p0 = a.verts_ndc + 3 * (size_t)i0; const float* p1 = a.verts_ndc + 3 * (size_t)i1;
+    const float* p2 = a.verts_ndc + 3 * (size_t)i2;
+    v.x0 = __ldg(p0); v.y0 = __ldg(p0 + 1); v.z0 = __ldg(p0 + 2);
+    v.x1 = __ldg(p1); v.y1 = __ldg(p1 + 1); v.z1 = __ldg(p1 + 2);
+    v.x2 = __ldg(p2); v.y2 = __ldg(p2 + 1); v.z2 = __ldg(p2 + 2);
+    const float px = pix_to_ndc_fast(W - 1 - xi, W, H), py = pix_to_ndc_fast(H - 1 - yi, H, W);
+    // the saved distance is negative (or -0) exactly when the forward found the sample inside
+    sample_backward_fast(v, px, py, persp, clip, signbit(d), gz, gb0, gb1, gb2, gd, gv);
+  }
+  float* const dst[9] = {a.g_verts_ndc + 3 * (size_t)i0, a.g_verts_ndc + 3 * (size_t)i0 + 1,
+                         a.g_verts_ndc + 3 * (size_t)i0 + 2, a.g_verts_ndc + 3 * (size_t)i1,
+                         a.g_verts_ndc + 3 * (size_t)i1 + 1, a.g_verts_ndc + 3 * (size_t)i1 + 2,
+                         a.g_verts_ndc + 3 * (size_t)i2, a.g_verts_ndc + 3 * (size_t)i2 + 1,
+                         a.g_verts_ndc + 3 * (size_t)i2 + 2};
+  warp_groups_add<9>(wg, key, gv, dst);
 }
 
 template <bool K1, int SHADER, int LIGHT>
@@ -950,7 +1132,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   const dim3 grid(tg.tiles_x, tg.tiles_y, N);
   TRB_CUDA_TRY(cudaMemsetAsync(tile_hit, 0, sizeof(int), st));
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
-  if (K == 1) rc = launch_render_fine_k1(sc.shader, sc.light_kind, grid, st, a);
+  if (K == 1) rc = launch_render_fine_k1(sc.shader, sc.light_kind, dim3(ceil_div(tg.tiles_x, kStrip), tg.tiles_y, N), st, a);
   else if (tg.ltx == 4) rc = launch_render_fine<4, 4, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 256, st, a);
   else rc = launch_render_fine<3, 3, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 64, st, a);
   if (rc != TRB_OK) return rc;

@@ -53,7 +53,7 @@ bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
 // Hands every non-empty tile a contiguous slice of `pairs` (order between tiles is irrelevant).
 __global__ void __launch_bounds__(256)
 alloc_tiles_kernel(const int* __restrict__ tile_count, int* __restrict__ tile_offset, int ntiles,
-                   int* __restrict__ header, long long pair_capacity) {
+                   int* __restrict__ header, long long pair_capacity, int* __restrict__ busy_list) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = t < ntiles ? tile_count[t] : 0;
   // warp-aggregated reservation
@@ -77,6 +77,14 @@ alloc_tiles_kernel(const int* __restrict__ tile_count, int* __restrict__ tile_of
     const bool fits = off + c <= pair_capacity;
     tile_offset[t] = (c == 0) ? 0 : (fits ? (int)off : -1);
     if (c > 0 && !fits) atomicAdd(header + 2, 1);
+  }
+  // compact list of non-empty tiles: the fused fine pass spreads them over its CTAs
+  const unsigned busy = __ballot_sync(0xffffffffu, c > 0);
+  if (busy) {
+    int bbase = 0;
+    if (lane == 0) bbase = atomicAdd(header + 4, __popc(busy));
+    bbase = __shfl_sync(0xffffffffu, bbase, 0);
+    if (c > 0) busy_list[bbase + __popc(busy & ((1u << lane) - 1u))] = t;
   }
 }
 
@@ -285,7 +293,7 @@ int run_binning(const float* verts_ndc, const int* faces, const trb_view* views,
                                                    tile_count, tile_fill, tile_offset, pairs);
     TRB_LAUNCH_CHECK();
     alloc_tiles_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(tile_count, tile_offset, ntiles, header,
-                                                              pair_capacity);
+                                                              pair_capacity, (int*)(wsb + ws.busy));
     TRB_LAUNCH_CHECK();
     bin_faces_kernel<true><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
                                                   tile_count, tile_fill, tile_offset, pairs);

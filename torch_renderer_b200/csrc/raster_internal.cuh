@@ -18,7 +18,7 @@ __host__ inline TileGrid make_tile_grid(int H, int W, int K) {
 }
 
 struct WsLayout {
-  size_t header, count, offset, fill, pairs, total;
+  size_t header, count, offset, fill, busy, pairs, total;
 };
 
 __host__ inline WsLayout make_ws_layout(int N, const TileGrid& g, int64_t pair_capacity) {
@@ -29,7 +29,8 @@ __host__ inline WsLayout make_ws_layout(int N, const TileGrid& g, int64_t pair_c
   w.count = align(64);
   w.fill = w.count + align(ntiles * 4);
   w.offset = w.fill + align(ntiles * 4);
-  w.pairs = w.offset + align(ntiles * 4);
+  w.busy = w.offset + align(ntiles * 4);   // compact list of non-empty tiles (header[4] = its length)
+  w.pairs = w.busy + align(ntiles * 4);
   w.total = w.pairs + align((size_t)pair_capacity * 4);
   return w;
 }

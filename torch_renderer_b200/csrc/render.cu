@@ -72,6 +72,7 @@ struct FineArgs {
   int H, W, K; float blur_radius, sqrt_blur; unsigned flags; TileGrid tg;
   const int* tile_count; const int* tile_offset; const int* pairs;
   long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
+  const int* ws_header; const int* busy_tiles;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   float sigma, gamma, bg0, bg1, bg2;
 };
@@ -330,7 +331,6 @@ render_fine_kernel(const FineArgs a) {
 // Faces whose clipped bbox is large go to a second, pixel-parallel pass (one thread per pixel walking
 // the few big faces), so neither regime degenerates.  Tiles with an empty list only stream out the
 // background.
-constexpr int kSmallFaceMaxPixels = 64;
 
 __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
   const unsigned zb = (z == 0.0f) ? 0u : __float_as_uint(z);  // -0.0f must not sort last
@@ -358,12 +358,15 @@ __device__ __forceinline__ void fill_empty_tile(const FineArgs& a, int n, int tb
 }
 
 template <int SHADER, int LIGHT>
-__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx, int tby, int nlist);
+__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 
-// One CTA owns a strip of kStrip horizontally adjacent tiles.  It fetches all their list lengths
-// with one round trip, streams out every empty tile first (94% of the tiles for the cow at 512^2 --
-// with one tile per CTA the kernel was bound by CTA turnover x the latency of that single load, ncu:
-// 28% of all stall samples), then rasterises the non-empty ones.
+// Every CTA (a) owns a strip of kStrip horizontally adjacent tiles, fetches their list lengths with
+// one round trip and streams out the empty ones (94% of the tiles for the cow at 512^2), and (b)
+// rasterises its share of the compact list of non-empty tiles the binning pass left in the workspace.
+// The non-empty tiles are dealt out evenly over the whole grid, so at any moment a fraction of the
+// resident CTAs is doing latency-bound raster work while the rest keeps the HBM write stream busy
+// (one tile per CTA bound the kernel by CTA turnover x the latency of the list-length load;
+// rasterising the strip's own tiles serialised the 4-8 neighbouring busy tiles of an object in one CTA).
 constexpr int kStrip = 8;
 
 template <int SHADER, int LIGHT>
@@ -374,25 +377,35 @@ render_fine_k1_kernel(const FineArgs a) {
   int cnt[kStrip];
 #pragma unroll
   for (int s = 0; s < kStrip; ++s) cnt[s] = (tbx0 + s < a.tg.tiles_x) ? __ldg(counts + tbx0 + s) : -1;
+  const int nbusy = __ldg(a.ws_header + 4);
 #pragma unroll
   for (int s = 0; s < kStrip; ++s)
     if (cnt[s] == 0) fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
-#pragma unroll 1
-  for (int s = 0; s < kStrip; ++s)
-    if (cnt[s] > 0) raster_tile_k1<SHADER, LIGHT>(a, n, tbx0 + s, tby, cnt[s]);
+  const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
+  const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int lo = (int)(cta * nbusy / ncta), hi = (int)((cta + 1) * nbusy / ncta);
+  for (int i = lo; i < hi; ++i) raster_tile_k1<SHADER, LIGHT>(a, __ldg(a.busy_tiles + i));
 }
 
+// Rasterises one non-empty tile.  The unit of parallel work is a (face, pixel-of-its-clipped-bbox)
+// pair: the pairs of up to 256 staged faces are numbered with a block-wide prefix sum and dealt out in
+// equal contiguous runs to the 256 threads, so a tile with 200 three-pixel faces and a tile with
+// three 200-pixel faces cost the same.  Candidates are published with a shared-memory atomicMin on a
+// 64-bit key (z bits << 32 | face), which is exactly the (z, face index) order of A5 because z >= 0.
 template <int SHADER, int LIGHT>
-__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx, int tby, int nlist) {
+__device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   constexpr int TX = 16, TY = 16, NT = 256;
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W;
+  const int tiles_per_view = a.tg.tiles_x * a.tg.tiles_y;
+  const int n = t / tiles_per_view;
+  const int trem = t - n * tiles_per_view;
+  const int tby = trem / a.tg.tiles_x, tbx = trem - tby * a.tg.tiles_x;
   const int lx = tid & (TX - 1), ly = tid >> 4;
   const int tile_x0 = tbx * TX, tile_y0 = tby * TY;
   const int xi = tile_x0 + lx, yi = tile_y0 + ly;
   const bool live = (xi < W) && (yi < H);
   const size_t pix = ((size_t)n * H + yi) * W + xi;
-  const int t = (n * a.tg.tiles_y + tby) * a.tg.tiles_x + tbx;
 
   __shared__ unsigned long long s_key[NT];
   __shared__ float s_px[TX], s_py[TY];
@@ -401,14 +414,16 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx
   __shared__ float4 s_vb[NT];
   __shared__ float2 s_vc[NT];
   __shared__ int s_id[NT];
-  __shared__ int s_big[NT];
-  __shared__ int s_nbig;
+  __shared__ int s_rng[NT];        // c0 - tile_x0 | (r0 - tile_y0) << 4 | (bbox width - 1) << 8
+  __shared__ int s_start[NT + 1];  // exclusive prefix sum of bbox pixel counts
+  __shared__ int s_wtot[NT / 32];
 
   const trb_view vd = a.views[n];
   const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
   const bool cull = a.flags & TRB_CULL_BACKFACES;
   const bool hard_edges = a.blur_radius == 0.0f;
   const float blur = a.blur_radius;
+  int nlist = a.tile_count[t];
   const int off = a.tile_offset[t];
   const bool overflow = off < 0;
   if (overflow) nlist = vd.face_count;
@@ -416,15 +431,14 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx
   s_key[tid] = ~0ull;
   if (tid < TX) s_px[tid] = pix_to_ndc(W - 1 - (tile_x0 + tid), W, H);
   else if (tid < TX + TY) s_py[tid - TX] = pix_to_ndc(H - 1 - (tile_y0 + tid - TX), H, W);
-  if (tid == 0) s_nbig = 0;
-  __syncthreads();
-  const float px = s_px[lx], py = s_py[ly];
-  unsigned long long best_key = ~0ull;
   // last pixel column / row of the tile that exists in the image
   const int x_hi = min(tile_x0 + TX, W) - 1, y_hi = min(tile_y0 + TY, H) - 1;
+  const int lane = tid & 31, warp = tid >> 5;
 
   for (int base = 0; base < nlist; base += NT) {
+    // ---- stage up to NT faces and the size of their clipped bounding boxes
     const int j = base + tid;
+    int npx = 0;
     if (j < nlist) {
       const int lf = overflow ? j : a.pairs[off + j];
       const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
@@ -433,89 +447,101 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int n, int tbx
         float4 bb;
         bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
         bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
-        const float area = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
         int c0, c1, r0, r1;
         pixel_range(bb.x, bb.y, W, H, c0, c1);
         pixel_range(bb.z, bb.w, H, W, r0, r1);
         c0 = max(c0, tile_x0); c1 = min(c1, x_hi); r0 = max(r0, tile_y0); r1 = min(r1, y_hi);
-        const int npx = (c1 >= c0 && r1 >= r0) ? (c1 - c0 + 1) * (r1 - r0 + 1) : 0;
-        if (npx > kSmallFaceMaxPixels) {
-          // big face: stage it for the pixel-parallel pass
-          const int slot = atomicAdd(&s_nbig, 1);
-          s_big[slot] = tid;
+        if (c1 >= c0 && r1 >= r0) {
+          npx = (c1 - c0 + 1) * (r1 - r0 + 1);
           s_bb[tid] = bb;
           s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
           s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
-          s_vc[tid] = make_float2(v.z2, area);
+          s_vc[tid] = make_float2(v.z2, fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps));
           s_id[tid] = lf;
-        } else if (npx > 0) {
-          for (int r = r0; r <= r1; ++r) {
-            const float qy = s_py[r - tile_y0];
-            if ((qy > bb.w) || (qy < bb.z)) continue;
-            for (int c = c0; c <= c1; ++c) {
-              const float qx = s_px[c - tile_x0];
-              if ((qx > bb.y) || (qx < bb.x)) continue;
-              const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
-              const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
-              const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
-              if (hard_edges) {
-                // blur 0: w_i = e_i / area keeps the sign of e_i * area exactly => exact reject
-                if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
-                                : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
-                  continue;
-              }
-              float pz, b0, b1, b2;
-              bool inside;
-              if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
-              if (!inside) {
-                if (hard_edges) continue;
-                if (triangle_d2(v, qx, qy) >= blur) continue;
-              }
-              atomicMin(&s_key[(r - tile_y0) * TX + (c - tile_x0)], pack_key(pz, lf));
-            }
-          }
+          s_rng[tid] = (c0 - tile_x0) | ((r0 - tile_y0) << 4) | ((c1 - c0) << 8);
         }
       }
     }
+    // ---- block-wide exclusive prefix sum of npx
+    int incl = npx;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();  // also publishes s_key / s_px / s_py on the first pass and the staging arrays
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+      const int c = s_wtot[w];
+      if (w < warp) wbase += c;
+      total += c;
+    }
+    s_start[tid] = wbase + incl - npx;
+    if (tid == 0) s_start[NT] = total;
     __syncthreads();
-    const int nbig = s_nbig;
-    if (live) {
-      for (int i = 0; i < nbig; ++i) {
-        const int q = s_big[i];
-        const float4 b = s_bb[q];
-        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
-        const float4 va = s_va[q], vb = s_vb[q];
-        const float2 vc = s_vc[q];
+
+    // ---- deal the (face, pixel) pairs out in equal contiguous runs
+    const int ipt = (total + NT - 1) / NT;
+    int item = tid * ipt;
+    const int item_end = min(item + ipt, total);
+    if (item < item_end) {
+      int lo = 0, hi = NT - 1;  // last staged face whose run starts at or before `item`
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_start[mid] <= item) lo = mid; else hi = mid - 1;
+      }
+      int fj = lo;
+      int k = item - s_start[fj];
+      int fend = s_start[fj + 1] - s_start[fj];
+      while (item < item_end) {
+        const float4 bb = s_bb[fj], va = s_va[fj], vb = s_vb[fj];
+        const float2 vc = s_vc[fj];
+        const int rng = s_rng[fj], lf = s_id[fj];
         FaceXYZ v;
         v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
         v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
         const float area = vc.y;
-        const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
-        const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
-        const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
-        if (hard_edges) {
-          if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
-                          : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
-            continue;
+        const int c0 = rng & 15, r0 = (rng >> 4) & 15, bw = ((rng >> 8) & 15) + 1;
+        const int inv_bw = 65536 / bw + 1;
+        const int kend = min(fend, k + (item_end - item));
+        item += kend - k;
+        for (; k < kend; ++k) {
+          const int dr = (k * inv_bw) >> 16;
+          const int lr = r0 + dr, lc = c0 + (k - dr * bw);
+          const float qx = s_px[lc], qy = s_py[lr];
+          if ((qx > bb.y) || (qx < bb.x) || (qy > bb.w) || (qy < bb.z)) continue;
+          const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
+          const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
+          const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
+          if (hard_edges) {
+            // blur 0: w_i = e_i / area keeps the sign of e_i * area exactly => exact reject
+            if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                            : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+              continue;
+          }
+          float pz, b0, b1, b2;
+          bool inside;
+          if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
+          if (!inside) {
+            if (hard_edges) continue;
+            if (triangle_d2(v, qx, qy) >= blur) continue;
+          }
+          atomicMin(&s_key[lr * TX + lc], pack_key(pz, lf));
         }
-        float pz, b0, b1, b2;
-        bool inside;
-        if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
-        if (!inside) {
-          if (hard_edges) continue;
-          if (triangle_d2(v, px, py) >= blur) continue;
-        }
-        const unsigned long long key = pack_key(pz, s_id[q]);
-        if (key < best_key) best_key = key;
+        // next staged face with a non-empty box
+        do { ++fj; } while (fj < NT && s_start[fj + 1] == s_start[fj]);
+        if (fj >= NT) break;
+        k = 0;
+        fend = s_start[fj + 1] - s_start[fj];
       }
     }
-    __syncthreads();
-    if (tid == 0) s_nbig = 0;
-    // (the next iteration's first barrier orders this reset before any atomicAdd consumer reads it)
-    __syncthreads();
+    __syncthreads();  // staging arrays are rewritten by the next chunk
   }
+  const float px = s_px[lx], py = s_py[ly];
 
-  const unsigned long long key = min(best_key, s_key[tid]);
+  const unsigned long long key = s_key[tid];
   const bool hit = live && (key != ~0ull);
   append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
   if (!live) return;
@@ -1124,6 +1150,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.flags = cfg->raster_flags; a.tg = tg;
   a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
   a.pairs = (const int*)(wsb + ws.pairs);
+  a.ws_header = (const int*)(wsb + ws.header); a.busy_tiles = (const int*)(wsb + ws.busy);
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
   a.hit_pixels = tile_hit;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;

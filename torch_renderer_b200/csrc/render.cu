@@ -332,6 +332,10 @@ render_fine_kernel(const FineArgs a) {
 // the few big faces), so neither regime degenerates.  Tiles with an empty list only stream out the
 // background.
 
+// (k * kInvWidth[w]) >> 16 == k / w for k < 256, w in 1..16
+__constant__ int kInvWidth[17] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193,
+                                  7282, 6554, 5958, 5462, 5042, 4682, 4370, 4097};
+
 __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
   const unsigned zb = (z == 0.0f) ? 0u : __float_as_uint(z);  // -0.0f must not sort last
   return ((unsigned long long)zb << 32) | (unsigned)f;
@@ -381,10 +385,21 @@ render_fine_k1_kernel(const FineArgs a) {
 #pragma unroll
   for (int s = 0; s < kStrip; ++s)
     if (cnt[s] == 0) fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
-  const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
-  const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  const int lo = (int)(cta * nbusy / ncta), hi = (int)((cta + 1) * nbusy / ncta);
-  for (int i = lo; i < hi; ++i) raster_tile_k1<SHADER, LIGHT>(a, __ldg(a.busy_tiles + i));
+  // deal the non-empty tiles out evenly over the grid (32-bit arithmetic only)
+  const unsigned ncta = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  unsigned lo, hi;
+  if ((unsigned)nbusy <= ncta) {
+    const unsigned step = ncta / max(nbusy, 1);          // every step-th CTA takes one tile
+    const unsigned q = cta / step;
+    const bool mine = (cta - q * step == 0) && (q < (unsigned)nbusy);
+    lo = q; hi = mine ? q + 1 : q;
+  } else {
+    const unsigned per = (unsigned)nbusy / ncta, rem = (unsigned)nbusy - per * ncta;
+    lo = cta * per + min(cta, rem);
+    hi = lo + per + (cta < rem ? 1u : 0u);
+  }
+  for (unsigned i = lo; i < hi; ++i) raster_tile_k1<SHADER, LIGHT>(a, __ldg(a.busy_tiles + i));
 }
 
 // Rasterises one non-empty tile.  The unit of parallel work is a (face, pixel-of-its-clipped-bbox)
@@ -483,19 +498,20 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     __syncthreads();
 
     // ---- deal the (face, pixel) pairs out in equal contiguous runs
+    const int m = min(NT, nlist - base);  // staged faces
     const int ipt = (total + NT - 1) / NT;
     int item = tid * ipt;
     const int item_end = min(item + ipt, total);
     if (item < item_end) {
-      int lo = 0, hi = NT - 1;  // last staged face whose run starts at or before `item`
+      int lo = 0, hi = m - 1;  // last staged face whose run starts at or before `item`
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (s_start[mid] <= item) lo = mid; else hi = mid - 1;
       }
       int fj = lo;
       int k = item - s_start[fj];
-      int fend = s_start[fj + 1] - s_start[fj];
-      while (item < item_end) {
+      for (;;) {
+        const int fend = s_start[fj + 1] - s_start[fj];
         const float4 bb = s_bb[fj], va = s_va[fj], vb = s_vb[fj];
         const float2 vc = s_vc[fj];
         const int rng = s_rng[fj], lf = s_id[fj];
@@ -503,8 +519,21 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
         v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
         v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
         const float area = vc.y;
+        // Early depth reject (blur 0 only, where every candidate is strictly inside its face): the
+        // interpolated depth is then a convex combination of the vertex depths up to a few ulp -- times
+        // area_raw / (area_raw + kEps) without perspective correction or clipping, where the weights
+        // are not renormalised -- so a pixel whose current front-most candidate is nearer than that
+        // bound cannot be won by this face and the six IEEE divisions are skipped.  zlo = 0 disables it.
+        float zlo = 0.0f;
+        if (hard_edges) {
+          const float zmin = min3f(v.z0, v.z1, v.z2);
+          if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
+          else if (clip) zlo = zmin * 0.99999f;
+          else zlo = zmin * 0.99999f * (area > 0.0f ? fmaxf(0.0f, (area - 2e-8f) / area) : 1.0f);
+        }
+        const unsigned zlo_bits = __float_as_uint(zlo);
         const int c0 = rng & 15, r0 = (rng >> 4) & 15, bw = ((rng >> 8) & 15) + 1;
-        const int inv_bw = 65536 / bw + 1;
+        const int inv_bw = kInvWidth[bw];
         const int kend = min(fend, k + (item_end - item));
         item += kend - k;
         for (; k < kend; ++k) {
@@ -512,6 +541,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
           const int lr = r0 + dr, lc = c0 + (k - dr * bw);
           const float qx = s_px[lc], qy = s_py[lr];
           if ((qx > bb.y) || (qx < bb.x) || (qy > bb.w) || (qy < bb.z)) continue;
+          if (reinterpret_cast<const unsigned*>(s_key)[2 * (lr * TX + lc) + 1] < zlo_bits) continue;
           const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
           const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
           const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
@@ -530,11 +560,10 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
           }
           atomicMin(&s_key[lr * TX + lc], pack_key(pz, lf));
         }
+        if (item >= item_end) break;
         // next staged face with a non-empty box
-        do { ++fj; } while (fj < NT && s_start[fj + 1] == s_start[fj]);
-        if (fj >= NT) break;
+        do { ++fj; } while (fj < m - 1 && s_start[fj + 1] == s_start[fj]);
         k = 0;
-        fend = s_start[fj + 1] - s_start[fj];
       }
     }
     __syncthreads();  // staging arrays are rewritten by the next chunk

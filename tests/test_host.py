@@ -185,3 +185,24 @@ def test_golden_meshes_fixture():
     assert v.shape == (1292, 3) and f.shape == (2464, 3)
     v, f = load_mesh("cow")
     assert v.shape == (2930, 3) and f.shape == (5856, 3) and int(f.max()) == 2929
+
+
+def test_compat_alias_keeps_reference_import_lines_working():
+    import subprocess, sys
+    code = (
+        "import torch_renderer_b200.compat as c; c.install()\n"
+        "from pytorch3d.io import load_objs_as_meshes, load_obj\n"
+        "from pytorch3d.utils import cameras_from_opencv_projection, ico_sphere\n"
+        "from pytorch3d.structures import Meshes, Pointclouds\n"
+        "from pytorch3d.renderer import (PerspectiveCameras, PointLights, DirectionalLights, Materials,"
+        " RasterizationSettings, MeshRenderer, MeshRasterizer, SoftPhongShader, SoftSilhouetteShader, BlendParams,"
+        " PointsRasterizationSettings, PointsRenderer, PulsarPointsRenderer, PointsRasterizer, AlphaCompositor,"
+        " NormWeightedCompositor, FoVPerspectiveCameras, look_at_view_transform, TexturesVertex, HardPhongShader,"
+        " AmbientLights)\n"
+        "from pytorch3d.transforms import quaternion_to_matrix, quaternion_apply, matrix_to_quaternion, Rotate,"
+        " Translate, axis_angle_to_matrix\n"
+        "from pytorch3d.loss import chamfer_distance\n"
+        "import torch_renderer_b200 as t; assert MeshRenderer is t.MeshRenderer\n"
+        "try:\n    Pointclouds()\nexcept NotImplementedError:\n    print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

@@ -211,6 +211,9 @@ typedef struct trb_render_config {
   int32_t max_vert_count;
   int32_t camera_center_from_rt; /* 1: view_params[n][13:16] := -T[n] * inv(R[n]) (and its gradient
                                     flows back into grad_R / grad_T) */
+  int32_t want_light_grad;       /* backward: also accumulate d/d(light location|direction) into
+                                    grad_view_params[:, 0:3] (camera centre is handled automatically) */
+  int32_t reserved;
   int64_t num_world_verts;       /* rows of verts_world / vert_colors */
   int64_t num_faces;             /* rows of faces */
   int64_t num_ndc_verts;         /* rows of verts_ndc = sum_n vert_count */

@@ -321,6 +321,41 @@ __device__ __forceinline__ void warp_groups_add(const WarpGroups& wg, int key, c
   }
 }
 
+// Same, for three xyz triples going to rows i0, i1, i2 of a float4-strided accumulator: one
+// REDG.ADD.F32x4 per vertex instead of three scalar reductions (the fp32 reduction rate of the L2 --
+// measured ~60 G sector-ops/s on B200 -- is what bounds the backward scatter).
+__device__ __forceinline__ void warp_groups_add_xyz3(const WarpGroups& wg, int key, const float (&val)[9],
+                                                     float4* base, int i0, int i1, int i2) {
+  if (!wg.any) return;
+  if (wg.aggregate) {
+    const int lane = threadIdx.x & 31;
+    unsigned todo = wg.leaders;
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int k = __shfl_sync(0xffffffffu, key, l);
+      const bool mine = (key == k);
+      float s[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float t = mine ? val[i] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        s[i] = t;
+      }
+      if (lane == l) {
+        atomicAdd(base + i0, make_float4(s[0], s[1], s[2], 0.0f));
+        atomicAdd(base + i1, make_float4(s[3], s[4], s[5], 0.0f));
+        atomicAdd(base + i2, make_float4(s[6], s[7], s[8], 0.0f));
+      }
+    }
+  } else if (key >= 0) {
+    atomicAdd(base + i0, make_float4(val[0], val[1], val[2], 0.0f));
+    atomicAdd(base + i1, make_float4(val[3], val[4], val[5], 0.0f));
+    atomicAdd(base + i2, make_float4(val[6], val[7], val[8], 0.0f));
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void warp_aggregated_add(int key, const float (&val)[NV],
                                                     float* const (&dst)[NV]) {

@@ -14,6 +14,7 @@
 // forward leaves a compact list of covered pixels (`hit_pixels`); the backward visits only those.
 #include "raster_internal.cuh"
 #include "shade_math.cuh"
+#include "trb_internal.cuh"
 
 namespace trb {
 
@@ -624,26 +625,18 @@ struct BwdArgs {
   const long long* p2f; const float* zbuf; const float* bary; const float* dists;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   const float* g_images; const float* g_zbuf; const float* g_bary; const float* g_dists;
-  float* g_verts_ndc; float* g_verts_world; float* g_normals; float* g_colors; float* g_view_params;
+  float4* g_verts_ndc; float4* g_verts_world; float4* g_normals; float4* g_colors;  // xyz_ accumulators
+  float* g_view_params; int want_light_grad, want_cam_grad;
   float sigma, gamma, bg0, bg1, bg2;
 };
 
-__device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, F3 g, float* base, int i0,
+__device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, F3 g, float4* base, int i0,
                                          int i1, int i2) {
   const float v[9] = {b0 * g.x, b0 * g.y, b0 * g.z, b1 * g.x, b1 * g.y, b1 * g.z, b2 * g.x, b2 * g.y, b2 * g.z};
-  float* const d[9] = {base + 3 * (size_t)i0, base + 3 * (size_t)i0 + 1, base + 3 * (size_t)i0 + 2,
-                       base + 3 * (size_t)i1, base + 3 * (size_t)i1 + 1, base + 3 * (size_t)i1 + 2,
-                       base + 3 * (size_t)i2, base + 3 * (size_t)i2 + 1, base + 3 * (size_t)i2 + 2};
-  warp_aggregated_add<9>(key, v, d);
+  const WarpGroups wg = warp_groups(key);
+  warp_groups_add_xyz3(wg, key, v, base, i0, i1, i2);
 }
 
-template <bool K1, int SHADER, int LIGHT>
-__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
-
-// Persistent CTAs walk the compact list of covered pixels the forward pass left behind
-// (hit_pixels[0] = count, [1..] = linear pixel ids): every lane that enters the body has a pixel with
-// at least one face, however sparse the image is (cow at 512^2: 1.5% of the pixels).  Whole warps
-// enter together so the warp-level reductions inside stay legal.
 template <int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
 
@@ -751,13 +744,10 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
       if (LIT) {
         gb0 += dot3(gP, X0) + dot3(gN, N0); gb1 += dot3(gP, X1) + dot3(gN, N1); gb2 += dot3(gP, X2) + dot3(gN, N2);
       }
-      auto scatter = [&](float* base, F3 gv) {
+      auto scatter = [&](float4* base, F3 gv) {
         const float v[9] = {b0 * gv.x, b0 * gv.y, b0 * gv.z, b1 * gv.x, b1 * gv.y, b1 * gv.z,
                             b2 * gv.x, b2 * gv.y, b2 * gv.z};
-        float* const dptr[9] = {base + 3 * (size_t)w0i, base + 3 * (size_t)w0i + 1, base + 3 * (size_t)w0i + 2,
-                                base + 3 * (size_t)w1i, base + 3 * (size_t)w1i + 1, base + 3 * (size_t)w1i + 2,
-                                base + 3 * (size_t)w2i, base + 3 * (size_t)w2i + 1, base + 3 * (size_t)w2i + 2};
-        warp_groups_add<9>(wg, key, v, dptr);
+        warp_groups_add_xyz3(wg, key, v, base, w0i, w1i, w2i);
       };
       if (a.g_colors) scatter(a.g_colors, gT);
       if (LIT) {
@@ -766,18 +756,17 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
         if (a.g_view_params) {
           float vals[6] = {g_lv.x, g_lv.y, g_lv.z, g_cam.x, g_cam.y, g_cam.z};
           const int n0 = __shfl_sync(0xffffffffu, n, 0);
-          if (__all_sync(0xffffffffu, !on || n == n0)) {
-            float* gp0 = a.g_view_params + (size_t)n0 * TRB_VIEW_PARAM_STRIDE;
+          const bool uniform = __all_sync(0xffffffffu, !on || n == n0);
+          float* gp = a.g_view_params + (size_t)(uniform ? n0 : n) * TRB_VIEW_PARAM_STRIDE;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
+          for (int i = 0; i < 6; ++i) {
+            if (i < 3 ? !a.want_light_grad : !a.want_cam_grad) continue;  // uniform
+            if (uniform) {
               const float sum = warp_sum(on ? vals[i] : 0.0f);
-              if ((threadIdx.x & 31) == 0 && sum != 0.0f) atomicAdd(gp0 + (i < 3 ? i : 10 + i), sum);
+              if ((threadIdx.x & 31) == 0 && sum != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), sum);
+            } else if (on && vals[i] != 0.0f) {
+              atomicAdd(gp + (i < 3 ? i : 10 + i), vals[i]);
             }
-          } else if (on) {
-            float* gp = a.g_view_params + (size_t)n * TRB_VIEW_PARAM_STRIDE;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-              if (vals[i] != 0.0f) atomicAdd(gp + (i < 3 ? i : 10 + i), vals[i]);
           }
         }
       }
@@ -804,12 +793,7 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
     // the saved distance is negative (or -0) exactly when the forward found the sample inside
     sample_backward_fast(v, px, py, persp, clip, signbit(d), gz, gb0, gb1, gb2, gd, gv);
   }
-  float* const dst[9] = {a.g_verts_ndc + 3 * (size_t)i0, a.g_verts_ndc + 3 * (size_t)i0 + 1,
-                         a.g_verts_ndc + 3 * (size_t)i0 + 2, a.g_verts_ndc + 3 * (size_t)i1,
-                         a.g_verts_ndc + 3 * (size_t)i1 + 1, a.g_verts_ndc + 3 * (size_t)i1 + 2,
-                         a.g_verts_ndc + 3 * (size_t)i2, a.g_verts_ndc + 3 * (size_t)i2 + 1,
-                         a.g_verts_ndc + 3 * (size_t)i2 + 2};
-  warp_groups_add<9>(wg, key, gv, dst);
+  warp_groups_add_xyz3(wg, key, gv, a.g_verts_ndc, i0, i1, i2);
 }
 
 template <bool K1, int SHADER, int LIGHT>
@@ -1011,12 +995,43 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
       sample_backward_rt(v, px, py, persp, clip, gz, gb0, gb1, gb2, gd, gv);
       key = (int)f;
     }
-    float* const dst[9] = {a.g_verts_ndc + 3 * (size_t)i0, a.g_verts_ndc + 3 * (size_t)i0 + 1,
-                           a.g_verts_ndc + 3 * (size_t)i0 + 2, a.g_verts_ndc + 3 * (size_t)i1,
-                           a.g_verts_ndc + 3 * (size_t)i1 + 1, a.g_verts_ndc + 3 * (size_t)i1 + 2,
-                           a.g_verts_ndc + 3 * (size_t)i2, a.g_verts_ndc + 3 * (size_t)i2 + 1,
-                           a.g_verts_ndc + 3 * (size_t)i2 + 2};
-    warp_aggregated_add<9>(key, gv, dst);
+    {
+      const WarpGroups wg = warp_groups(key);
+      warp_groups_add_xyz3(wg, key, gv, a.g_verts_ndc, i0, i1, i2);
+    }
+  }
+}
+
+// Per-vertex epilogue of the fused backward: unpacks the float4 accumulators.  grad_verts += pixel-
+// coordinate path, grad_colors += colour path, and the gradient of the unit vertex normals is pushed
+// through the normalisation (raw / max(|raw|, 1e-6)) into g_raw for the per-face scatter that follows.
+__global__ void __launch_bounds__(256)
+finalize_vertex_grads_kernel(long long V, const float* __restrict__ raw, const float4* __restrict__ g_norm4,
+                             const float4* __restrict__ g_world4, const float4* __restrict__ g_col4,
+                             float* __restrict__ g_raw, float* __restrict__ grad_verts,
+                             float* __restrict__ grad_colors) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  if (g_world4 && grad_verts) {
+    const float4 g = g_world4[v];
+    grad_verts[3 * v] += g.x; grad_verts[3 * v + 1] += g.y; grad_verts[3 * v + 2] += g.z;
+  }
+  if (g_col4 && grad_colors) {
+    const float4 g = g_col4[v];
+    grad_colors[3 * v] += g.x; grad_colors[3 * v + 1] += g.y; grad_colors[3 * v + 2] += g.z;
+  }
+  if (g_norm4 && g_raw) {
+    const float4 g = g_norm4[v];
+    const float x = raw[3 * v], y = raw[3 * v + 1], z = raw[3 * v + 2];
+    const float len = sqrtf(x * x + y * y + z * z);
+    if (len > 1e-6f) {
+      const float inv = 1.0f / len;
+      const float ux = x * inv, uy = y * inv, uz = z * inv;
+      const float d = ux * g.x + uy * g.y + uz * g.z;
+      g_raw[3 * v] = (g.x - ux * d) * inv; g_raw[3 * v + 1] = (g.y - uy * d) * inv; g_raw[3 * v + 2] = (g.z - uz * d) * inv;
+    } else {
+      g_raw[3 * v] = g.x * 1e6f; g_raw[3 * v + 1] = g.y * 1e6f; g_raw[3 * v + 2] = g.z * 1e6f;
+    }
   }
 }
 
@@ -1126,8 +1141,9 @@ extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_
   if (workspace_bytes) *workspace_bytes = make_ws_layout(s.N, tg, cfg->pair_capacity).total;
   // hit_pixels = [count, pixel ids...]
   if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W + 1;
-  // backward scratch: grad of NDC verts [num_ndc_verts,3] + grad normals [V,3] + grad raw normals [V,3]
-  if (backward_scratch_floats) *backward_scratch_floats = 3 * cfg->num_ndc_verts + 6 * cfg->num_world_verts;
+  // backward scratch: float4 accumulators for grad NDC verts [num_ndc_verts], world verts, colours and
+  // normals [V each], then grad of the raw normals [V,3]
+  if (backward_scratch_floats) *backward_scratch_floats = 4 * cfg->num_ndc_verts + 15 * cfg->num_world_verts;
   return TRB_OK;
 }
 
@@ -1226,10 +1242,12 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_ndc = (size_t)cfg->num_ndc_verts, V = (size_t)cfg->num_world_verts;
-  TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (3 * n_ndc + 6 * V) * sizeof(float), st));
-  float* g_ndc = scratch;
-  float* g_normals = scratch + 3 * n_ndc;
-  float* g_raw = g_normals + 3 * V;
+  TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (4 * n_ndc + 15 * V) * sizeof(float), st));
+  float4* g_ndc4 = reinterpret_cast<float4*>(scratch);
+  float4* g_world4 = g_ndc4 + n_ndc;
+  float4* g_col4 = g_world4 + V;
+  float4* g_norm4 = g_col4 + V;
+  float* g_raw = reinterpret_cast<float*>(g_norm4 + V);
   const bool geom = grad_verts_world || grad_R || grad_T || grad_proj;
   // the camera centre (when derived from R, T) feeds grad_R / grad_T through grad_view_params
   float* g_vp = grad_view_params;
@@ -1242,11 +1260,13 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   a.p2f = (const long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.g_images = grad_images; a.g_zbuf = grad_zbuf; a.g_bary = grad_bary; a.g_dists = grad_dists;
-  a.g_verts_ndc = geom ? g_ndc : nullptr;
-  a.g_verts_world = (lit && grad_verts_world) ? grad_verts_world : nullptr;
-  a.g_normals = (lit && grad_verts_world) ? g_normals : nullptr;
-  a.g_colors = phong ? grad_vert_colors : nullptr;
+  a.g_verts_ndc = geom ? g_ndc4 : nullptr;
+  a.g_verts_world = (lit && grad_verts_world) ? g_world4 : nullptr;
+  a.g_normals = (lit && grad_verts_world) ? g_norm4 : nullptr;
+  a.g_colors = (phong && grad_vert_colors) ? g_col4 : nullptr;
   a.g_view_params = lit ? g_vp : nullptr;
+  a.want_light_grad = (lit && g_vp && cfg->want_light_grad) ? 1 : 0;
+  a.want_cam_grad = (lit && g_vp && (cam_chain || cfg->want_light_grad)) ? 1 : 0;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
   // block size: the K>1 Phong path parks 16 B per (layer, thread) in shared memory
@@ -1264,13 +1284,20 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
     TRB_LAUNCH_CHECK();
   }
   if (geom) {
-    rc = trb_transform_backward(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective, g_ndc,
-                                grad_verts_world, grad_R, grad_T, grad_proj, device, stream);
+    rc = transform_backward_strided(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective,
+                                    reinterpret_cast<const float*>(g_ndc4), 4, grad_verts_world, grad_R, grad_T,
+                                    grad_proj, device, stream);
     if (rc != TRB_OK) return rc;
   }
-  if (lit && grad_verts_world) {
-    rc = trb_vertex_normals_backward(verts_world, faces, cfg->num_world_verts, cfg->num_faces, normals_raw,
-                                     g_normals, g_raw, grad_verts_world, device, stream);
+  const bool normals_chain = lit && grad_verts_world;
+  if (a.g_verts_world || a.g_colors || normals_chain) {
+    finalize_vertex_grads_kernel<<<(unsigned)ceil_div64((long long)V, 256), 256, 0, st>>>(
+        (long long)V, normals_raw, normals_chain ? g_norm4 : nullptr, a.g_verts_world ? g_world4 : nullptr,
+        a.g_colors ? g_col4 : nullptr, g_raw, grad_verts_world, grad_vert_colors);
+    TRB_LAUNCH_CHECK();
+  }
+  if (normals_chain) {
+    rc = face_normals_backward(verts_world, faces, cfg->num_faces, g_raw, grad_verts_world, st);
     if (rc != TRB_OK) return rc;
   }
   return TRB_OK;

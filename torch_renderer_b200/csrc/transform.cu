@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256)
 transform_backward_kernel(const float* __restrict__ verts, const float* __restrict__ R,
                           const float* __restrict__ T, const float* __restrict__ proj,
                           const trb_view* __restrict__ views, int perspective,
-                          const float* __restrict__ grad_ndc, float* __restrict__ grad_verts,
+                          const float* __restrict__ grad_ndc, int gstride, float* __restrict__ grad_verts,
                           float* __restrict__ grad_R, float* __restrict__ grad_T,
                           float* __restrict__ grad_proj) {
   const int n = blockIdx.y;
@@ -56,7 +56,7 @@ transform_backward_kernel(const float* __restrict__ verts, const float* __restri
     const float xv = X * __ldg(r + 0) + Y * __ldg(r + 3) + Z * __ldg(r + 6) + __ldg(t + 0);
     const float yv = X * __ldg(r + 1) + Y * __ldg(r + 4) + Z * __ldg(r + 7) + __ldg(t + 1);
     const float zv = X * __ldg(r + 2) + Y * __ldg(r + 5) + Z * __ldg(r + 8) + __ldg(t + 2);
-    const float* g = grad_ndc + 3 * (size_t)(vd.ndc_vert_start + lv);
+    const float* g = grad_ndc + (size_t)gstride * (size_t)(vd.ndc_vert_start + lv);
     const float gx = g[0], gy = g[1], gz = g[2];
     const float fx = __ldg(p + 0), fy = __ldg(p + 1);
     float gxv, gyv, gzv = gz, gfx, gfy;
@@ -166,6 +166,18 @@ face_normal_backward_kernel(const float* __restrict__ verts, const int* __restri
 
 }  // namespace trb
 
+#include "trb_internal.cuh"
+
+namespace trb {
+int face_normals_backward(const float* verts, const int32_t* faces, int64_t F, const float* grad_raw,
+                          float* grad_verts, cudaStream_t st) {
+  if (F <= 0) return TRB_OK;
+  face_normal_backward_kernel<<<(unsigned)ceil_div64(F, 256), 256, 0, st>>>(verts, faces, F, grad_raw, grad_verts);
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+}  // namespace trb
+
 using namespace trb;
 
 extern "C" int trb_transform_forward(const float* verts_world, const float* R, const float* T,
@@ -188,6 +200,16 @@ extern "C" int trb_transform_backward(const float* verts_world, const float* R, 
                                       int perspective, const float* grad_verts_ndc, float* grad_verts_world,
                                       float* grad_R, float* grad_T, float* grad_proj, int device,
                                       trb_stream_t stream) {
+  return trb::transform_backward_strided(verts_world, R, T, proj, views, N, max_vert_count, perspective,
+                                         grad_verts_ndc, 3, grad_verts_world, grad_R, grad_T, grad_proj, device,
+                                         stream);
+}
+
+int trb::transform_backward_strided(const float* verts_world, const float* R, const float* T, const float* proj,
+                                    const trb_view* views, int N, int max_vert_count, int perspective,
+                                    const float* grad_verts_ndc, int grad_stride, float* grad_verts_world,
+                                    float* grad_R, float* grad_T, float* grad_proj, int device,
+                                    trb_stream_t stream) {
   if (N < 0 || max_vert_count < 0) return TRB_ERR_BAD_ARG;
   if (N == 0 || max_vert_count == 0) return TRB_OK;
   if (N > 65535) return TRB_ERR_BAD_ARG;
@@ -195,8 +217,8 @@ extern "C" int trb_transform_backward(const float* verts_world, const float* R, 
   TRB_ENTER(device);
   dim3 grid(ceil_div(max_vert_count, 256), N);
   transform_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      verts_world, R, T, proj, views, perspective, grad_verts_ndc, grad_verts_world, grad_R, grad_T,
-      grad_proj);
+      verts_world, R, T, proj, views, perspective, grad_verts_ndc, grad_stride, grad_verts_world, grad_R,
+      grad_T, grad_proj);
   TRB_LAUNCH_CHECK();
   return TRB_OK;
 }

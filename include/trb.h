@@ -78,6 +78,9 @@ typedef struct trb_view {
 int trb_abi_version(void);
 const char* trb_status_string(int status);
 int trb_last_cuda_error(void);
+/* sizeof(trb_view | trb_shade_config | trb_render_config) for which = 0 | 1 | 2 as compiled into the
+ * library: bindings compare it with their own layout and refuse a stale build. */
+int trb_abi_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Camera transform (replaces MeshRasterizer.transform):

@@ -45,6 +45,7 @@ class RenderConfig(ctypes.Structure):
 _SIGNATURES = {
     "trb_abi_version": [],
     "trb_last_cuda_error": [],
+    "trb_abi_struct_size": [_i],
     "trb_transform_forward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "trb_transform_backward": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "trb_raster_workspace_bytes": [_i, _i, _i, _i, _i64, _c.POINTER(_sz)],
@@ -94,6 +95,11 @@ def lib() -> ctypes.CDLL:
         handle.trb_status_string.restype = _c.c_char_p
         if handle.trb_abi_version() != 1:
             raise TrbLibraryError("libtrb.so ABI version mismatch; rebuild it")
+        for which, (name, size) in enumerate((("trb_view", 32), ("trb_shade_config", _c.sizeof(ShadeConfig)),
+                                              ("trb_render_config", _c.sizeof(RenderConfig)))):
+            if handle.trb_abi_struct_size(which) != size:
+                raise TrbLibraryError(f"libtrb.so is stale: sizeof({name}) is {handle.trb_abi_struct_size(which)} in "
+                                      f"the library but {size} in the binding; run python -m torch_renderer_b200.build")
         _lib = handle
     return _lib
 

@@ -9,6 +9,16 @@ extern "C" int trb_abi_version(void) { return TRB_ABI_VERSION; }
 
 extern "C" int trb_last_cuda_error(void) { return trb::g_last_cuda_error; }
 
+// sizeof() of the structs that cross the ABI, so that a binding can refuse a stale library.
+extern "C" int trb_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(trb_view);
+    case 1: return (int)sizeof(trb_shade_config);
+    case 2: return (int)sizeof(trb_render_config);
+    default: return -1;
+  }
+}
+
 extern "C" const char* trb_status_string(int status) {
   switch (status) {
     case TRB_OK: return "ok";

@@ -639,6 +639,8 @@ __device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, 
 
 template <int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
+template <bool K1, int SHADER, int LIGHT>
+__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
 
 template <bool K1, int SHADER, int LIGHT>
 __global__ void __launch_bounds__(128, K1 ? 4 : 1)

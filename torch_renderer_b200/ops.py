@@ -449,7 +449,9 @@ class _RenderFn(torch.autograd.Function):
         images = (torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if shader != _lib.SHADER_NONE
                   else torch.empty((0,), dtype=torch.float32, device=dev))
         tile_hit = torch.empty((max(n_tiles.value, 1),), dtype=torch.int32, device=dev)
-        stats = torch.empty((4,), dtype=torch.int32, device=dev)
+        # bin statistics are only fetched when no earlier read-back is still pending
+        want_stats = table._pending is None and not torch.cuda.is_current_stream_capturing()
+        stats = torch.empty((4,), dtype=torch.int32, device=dev) if want_stats else None
         with _timed("render_forward", dev):
             check(L.trb_render_forward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
@@ -458,7 +460,7 @@ class _RenderFn(torch.autograd.Function):
                 _ptr(ws), ws_bytes.value, _ptr(stats), dev.index, _stream(dev)), "render")
         lit = phong and spec["light_kind"] != _lib.LIGHT_AMBIENT
         _bump(7 + (3 if lit else 0))
-        if table._pending is None and not torch.cuda.is_current_stream_capturing():
+        if want_stats:
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
             host_stats.copy_(stats, non_blocking=True)
             ev = torch.cuda.Event()

@@ -135,7 +135,7 @@ class ViewTable:
         that some tiles had to fall back to a whole-mesh scan.  Never synchronises."""
         if self.pair_capacity == 0:
             self.pair_capacity = self.default_pair_capacity()
-        if self._pending is not None:
+        if self._pending is not None and not torch.cuda.is_current_stream_capturing():
             stats, event = self._pending
             if event.query():
                 needed = int(stats[0])

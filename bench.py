@@ -144,6 +144,11 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # Everything runs on a non-default stream: autograd binds each leaf's gradient accumulator to the
+    # stream that was current when the leaf was first used, and work bound to the legacy default stream
+    # cannot take part in a CUDA-graph capture.
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
 
     v, f, colors, R, T = _scene(dev)
     V, F, N = v.shape[0], f.shape[0], VIEWS_PER_GPU

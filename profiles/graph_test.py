@@ -3,6 +3,7 @@ sys.path[:0] = ["/root/repo", "/root/repo/tests"]
 import torch_renderer_b200 as trb
 from helpers import load_mesh
 dev = torch.device("cuda:0"); N, H = 8, 256
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 v, f = load_mesh("cow")
 R, T = trb.look_at_view_transform(dist=0.7, elev=torch.linspace(0, 360, N), azim=torch.linspace(-180, 180, N))
 verts = v.to(dev).requires_grad_(True); cols = torch.rand(v.shape[0], 3, device=dev).requires_grad_(True)

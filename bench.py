@@ -173,28 +173,32 @@ def run_ours(args):
     grad_img = torch.randn(N, H, W, 4, device=dev) / (N * H * W)
     params = [verts, cols, Rd, Td]
 
-    def step_device():
+    def core_device():          # zero grads + forward + backward: the graph-captured part
         for p in params:
             p.grad = None
         images = renderer(meshes, R=Rd, T=Td)
         images.backward(grad_img)
-        allreduce_shared_grads([verts.grad, cols.grad])
         return images
+
+    def step_device():
+        core_device()
+        allreduce_shared_grads([verts.grad, cols.grad])
 
     # pinned host buffers for the end-to-end leg: inputs in, gradients + a scalar metric out
     host = [t.detach().cpu().pin_memory() for t in params]
     host_out = [torch.empty_like(h).pin_memory() for h in host]
     metric_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step_e2e():
+    def core_e2e():             # H2D of this step's inputs + forward + backward + metric
         for p, h in zip(params, host):
             p.grad = None
             p.data.copy_(h, non_blocking=True)
         images = renderer(meshes, R=Rd, T=Td)
         images.backward(grad_img)
-        allreduce_shared_grads([verts.grad, cols.grad])
-        # the step's result read back by the host: mean alpha (silhouette coverage) + every gradient
+        # the step's result read back by the host: mean alpha (silhouette coverage)
         metric_host.copy_(images.detach()[..., 3].mean(), non_blocking=True)
+
+    def readback_e2e():         # ... and every gradient
         for p, o in zip(params, host_out):
             o.copy_(p.grad, non_blocking=True)
 
@@ -244,16 +248,21 @@ def run_ours(args):
     l0 = ops.launch_count()
     step_device()
     launches_per_step = ops.launch_count() - l0
-    run_device, mode_device = graphed(step_device)
+    core_run, mode_device = graphed(core_device)
+
+    def run_device():
+        core_run()
+        allreduce_shared_grads([verts.grad, cols.grad])
+
     for _ in range(args.warmup):
         run_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        # keep the GPU under the same load until nvidia-smi has a few samples (its period is 100 ms)
-        t_end = time.time() + 0.6
-        while time.time() < t_end:
-            run_device()
+    # keep the GPU under the same load until nvidia-smi has a few samples (its period is 100 ms);
+    # a fixed step count so that every rank issues the same number of all-reduces
+    for _ in range(1500):
+        run_device()
     ms_total = timed(run_device, args.steps)
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
@@ -290,7 +299,13 @@ def run_ours(args):
     traffic = TRAFFIC_BYTES_PER_LAUNCH.get(dominant)
 
     # end-to-end through the public API with host buffers
-    run_e2e, mode_e2e = graphed(step_e2e)
+    core_e2e_run, mode_e2e = graphed(core_e2e)
+
+    def run_e2e():
+        core_e2e_run()
+        allreduce_shared_grads([verts.grad, cols.grad])
+        readback_e2e()
+
     for _ in range(max(3, args.warmup)):
         run_e2e()
     ms_e2e = timed(run_e2e, args.steps) / args.steps

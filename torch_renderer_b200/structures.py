@@ -20,6 +20,38 @@ import torch
 from . import ops
 
 
+# Topology-only device data is shared between Meshes objects: optimisation loops build a new Meshes every
+# step (mesh_deformer.py:190, `src_mesh.offset_verts(deform)`), and rebuilding the int32 face table and the
+# per-view records each time costs a conversion kernel, a host loop and an H2D copy per step.
+_FACES_I32_CACHE: "dict[int, tuple]" = {}
+_VIEW_TABLE_CACHE: "dict[tuple, object]" = {}
+
+
+def _faces_i32_cached(src: torch.Tensor) -> torch.Tensor:
+    import weakref
+    key = id(src)
+    hit = _FACES_I32_CACHE.get(key)
+    if hit is not None:
+        ref, version, out = hit
+        if ref() is src and version == src._version:
+            return out
+    if len(_FACES_I32_CACHE) > 256:
+        _FACES_I32_CACHE.clear()
+    out = src.to(torch.int32).contiguous()
+    _FACES_I32_CACHE[key] = (weakref.ref(src), src._version, out)
+    return out
+
+
+def _view_table_cached(key, build):
+    table = _VIEW_TABLE_CACHE.get(key)
+    if table is None:
+        if len(_VIEW_TABLE_CACHE) > 256:
+            _VIEW_TABLE_CACHE.clear()
+        table = build()
+        _VIEW_TABLE_CACHE[key] = table
+    return table
+
+
 def _list_to_padded(xs: Sequence[torch.Tensor], pad_value, dtype, device, trailing) -> torch.Tensor:
     n = len(xs)
     m = max((x.shape[0] for x in xs), default=0)
@@ -199,8 +231,8 @@ class Meshes:
     def faces_packed_i32(self) -> torch.Tensor:
         """int32 copy of the (unique) face table the kernels index; cached because topology is static."""
         if self._faces_i32 is None:
-            src = self._faces_list[0] if self._replicas > 1 else self.faces_packed()
-            self._faces_i32 = src.to(torch.int32).contiguous()
+            src = self._faces_list[0] if (self._replicas > 1 or self._N == 1) else self.faces_packed()
+            self._faces_i32 = _faces_i32_cached(src)
         return self._faces_i32
 
     def _unique_verts(self) -> torch.Tensor:
@@ -238,17 +270,21 @@ class Meshes:
         if self._view_table is None:
             if self._replicas > 1:
                 V, F, r = self._verts_list[0].shape[0], self._faces_list[0].shape[0], self._replicas
-                self._view_table = ops.ViewTable.build(
-                    face_start=[0] * r, face_count=[F] * r, p2f_base=[i * F for i in range(r)],
-                    world_vert_start=[0] * r, vert_count=[V] * r, device=self.device, shared_mesh=True)
+                self._view_table = _view_table_cached(
+                    (str(self.device), "shared", V, F, r),
+                    lambda: ops.ViewTable.build(
+                        face_start=[0] * r, face_count=[F] * r, p2f_base=[i * F for i in range(r)],
+                        world_vert_start=[0] * r, vert_count=[V] * r, device=self.device, shared_mesh=True))
             else:
                 nv = [v.shape[0] for v in self._verts_list]
                 nf = [f.shape[0] for f in self._faces_list]
-                vs = [sum(nv[:i]) for i in range(len(nv))]
-                fs = [sum(nf[:i]) for i in range(len(nf))]
-                self._view_table = ops.ViewTable.build(
-                    face_start=fs, face_count=nf, p2f_base=fs, world_vert_start=vs, vert_count=nv,
-                    device=self.device, shared_mesh=False)
+
+                def build():
+                    vs = [sum(nv[:i]) for i in range(len(nv))]
+                    fs = [sum(nf[:i]) for i in range(len(nf))]
+                    return ops.ViewTable.build(face_start=fs, face_count=nf, p2f_base=fs, world_vert_start=vs,
+                                               vert_count=nv, device=self.device, shared_mesh=False)
+                self._view_table = _view_table_cached((str(self.device), "packed", tuple(nv), tuple(nf)), build)
         return self._view_table
 
     # ------------------------------------------------------------------ construction of new meshes

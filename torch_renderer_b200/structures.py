@@ -75,7 +75,9 @@ class Meshes:
             if len(verts) != len(faces):
                 raise ValueError("verts and faces lists must have the same length")
             self._verts_list = [v for v in verts]
-            self._faces_list = [f[(f >= 0).all(dim=1)].to(torch.int64) if f.numel() > 0 else
+            # list input is taken as is (like upstream: only padded tensors carry -1 filler rows);
+            # no boolean indexing here -- it would cost a host sync per Meshes construction
+            self._faces_list = [(f if f.dtype == torch.int64 else f.to(torch.int64)) if f.numel() > 0 else
                                 f.reshape(0, 3).to(torch.int64) for f in faces]
             if len(self._verts_list) > 0:
                 self.device = self._verts_list[0].device

@@ -216,7 +216,8 @@ typedef struct trb_render_config {
                                     flows back into grad_R / grad_T) */
   int32_t want_light_grad;       /* backward: also accumulate d/d(light location|direction) into
                                     grad_view_params[:, 0:3] (camera centre is handled automatically) */
-  int32_t reserved;
+  float z_clip_value;            /* > 0: faces whose three vertices are all nearer than this view depth
+                                    are culled (clip_faces' "fully behind the clip plane" case); 0: off */
   int64_t num_world_verts;       /* rows of verts_world / vert_colors */
   int64_t num_faces;             /* rows of faces */
   int64_t num_ndc_verts;         /* rows of verts_ndc = sum_n vert_count */

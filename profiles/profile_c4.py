@@ -36,3 +36,11 @@ ops.start_event_log()
 for _ in range(10): step()
 log = ops.stop_event_log()
 print({k: round(ms / n, 4) for k, (n, ms) in log.items()})
+if len(sys.argv) > 2 and sys.argv[2] == "cprofile":
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(200): step()
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(35)

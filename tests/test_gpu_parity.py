@@ -546,3 +546,38 @@ def test_fused_rasterizer_depth_gradient_and_fragment_grads():
     for k in ("v", "R", "T", "c"):
         e = rel_l2(out[k].grad.cpu(), ref[k].grad)
         assert e < 1e-3, f"grad {k}: rel L2 err {e}"
+
+
+def test_z_clip_culls_faces_entirely_nearer_than_the_plane():
+    """FoV cameras clip at znear/2 by default (upstream semantics); an explicit z_clip_value overrides.
+    Faces with all three vertices nearer than the plane disappear; the oracle sees the same face list
+    with those faces removed."""
+    trb = _trb()
+    v, f = uv_sphere(16, 20, 1.0, noise=0.02, seed=6)
+    R, T = _views(2, dist=1.6, seed=21)
+    z_clip = 1.0
+    mesh = trb.Meshes(verts=[v.to(DEV)], faces=[f.to(DEV)]).extend(2)
+    cams = trb.FoVPerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV))
+    rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=96, faces_per_pixel=2, z_clip_value=z_clip))
+    frag = rast(mesh)
+    ndc = rast.transform(mesh).cpu().reshape(2, -1, 3)
+    F = f.shape[0]
+    fz = ndc[:, f][..., 2]                       # [2, F, 3] view depths of the face corners
+    keep = ~(fz < z_clip).all(dim=-1)            # [2, F]
+    assert (~keep).sum() > 10 and keep.sum() > 100
+    fv, first, count, remap = [], [], [], []
+    for n in range(2):
+        idx = keep[n].nonzero().flatten()
+        first.append(sum(count)); count.append(len(idx))
+        fv.append(ndc[n][f[idx]])
+        remap.append(idx + n * F)
+    want = oracle.rasterize_forward(torch.cat(fv).numpy(), np.array(first, np.int64), np.array(count, np.int64),
+                                    (96, 96), 0.0, 2, True, False, False)
+    remap = torch.cat(remap).numpy()
+    want_p2f = np.where(want[0] >= 0, remap[np.clip(want[0], 0, None)], -1)
+    _assert_fragments_equal((frag.pix_to_face, frag.zbuf, frag.bary_coords, frag.dists),
+                            (want_p2f, want[1], want[2], want[3]))
+    # without clipping the nearer cap is visible instead
+    frag0 = trb.MeshRasterizer(trb.PerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV), focal_length=1.7320508),
+                               trb.RasterizationSettings(image_size=96, faces_per_pixel=2))(mesh)
+    assert (frag0.pix_to_face != frag.pix_to_face).any()

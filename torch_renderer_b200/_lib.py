@@ -36,7 +36,7 @@ class RenderConfig(ctypes.Structure):
     _fields_ = [("shade", ShadeConfig), ("blur_radius", _f), ("raster_flags", _u32),
                 ("perspective", _c.c_int32), ("max_face_count", _c.c_int32),
                 ("max_vert_count", _c.c_int32), ("camera_center_from_rt", _c.c_int32),
-                ("want_light_grad", _c.c_int32), ("reserved", _c.c_int32),
+                ("want_light_grad", _c.c_int32), ("z_clip_value", _f),
                 ("num_world_verts", _c.c_int64), ("num_faces", _c.c_int64),
                 ("num_ndc_verts", _c.c_int64), ("pair_capacity", _c.c_int64)]
 

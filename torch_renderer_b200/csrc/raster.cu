@@ -23,13 +23,13 @@ __global__ void __launch_bounds__(256)
 bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
                  const trb_view* __restrict__ views, int H, int W, TileGrid tg, float sqrt_blur,
                  bool cull, int* __restrict__ tile_count, int* __restrict__ tile_fill,
-                 const int* __restrict__ tile_offset, int* __restrict__ pairs) {
+                 const int* __restrict__ tile_offset, int* __restrict__ pairs, float z_cull) {
   const int n = blockIdx.y;
   const trb_view vd = views[n];
   const int lf = blockIdx.x * blockDim.x + threadIdx.x;
   if (lf >= vd.face_count) return;
   const FaceXYZ v = load_face(verts, faces, vd, lf);
-  if (!face_is_drawable(v, cull)) return;
+  if (!face_is_drawable(v, cull, z_cull)) return;
   const float xmin = min3f(v.x0, v.x1, v.x2) - sqrt_blur, xmax = max3f(v.x0, v.x1, v.x2) + sqrt_blur;
   const float ymin = min3f(v.y0, v.y1, v.y2) - sqrt_blur, ymax = max3f(v.y0, v.y1, v.y2) + sqrt_blur;
   int px0, px1, py0, py1;
@@ -277,7 +277,7 @@ raster_backward_kernel(const float* __restrict__ verts, const int* __restrict__ 
 
 int run_binning(const float* verts_ndc, const int* faces, const trb_view* views, int N, int max_face_count,
                 int H, int W, const TileGrid& tg, const WsLayout& ws, void* workspace, float sqrt_blur, bool cull,
-                long long pair_capacity, cudaStream_t st) {
+                long long pair_capacity, cudaStream_t st, float z_cull) {
   unsigned char* wsb = (unsigned char*)workspace;
   int* header = (int*)(wsb + ws.header);
   int* tile_count = (int*)(wsb + ws.count);
@@ -290,13 +290,13 @@ int run_binning(const float* verts_ndc, const int* faces, const trb_view* views,
   if (max_face_count > 0) {
     dim3 bgrid(ceil_div(max_face_count, 256), N);
     bin_faces_kernel<false><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
-                                                   tile_count, tile_fill, tile_offset, pairs);
+                                                   tile_count, tile_fill, tile_offset, pairs, z_cull);
     TRB_LAUNCH_CHECK();
     alloc_tiles_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(tile_count, tile_offset, ntiles, header,
                                                               pair_capacity, (int*)(wsb + ws.busy));
     TRB_LAUNCH_CHECK();
     bin_faces_kernel<true><<<bgrid, 256, 0, st>>>(verts_ndc, faces, views, H, W, tg, sqrt_blur, cull,
-                                                  tile_count, tile_fill, tile_offset, pairs);
+                                                  tile_count, tile_fill, tile_offset, pairs, z_cull);
     TRB_LAUNCH_CHECK();
   }
   return TRB_OK;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void pixel_range(float lo, float hi, int S1, int S2, 
 // make_ws_layout and is zeroed here.  Defined in raster.cu.
 int run_binning(const float* verts_ndc, const int* faces, const trb_view* views, int N, int max_face_count,
                 int H, int W, const TileGrid& tg, const WsLayout& ws, void* workspace, float sqrt_blur, bool cull,
-                long long pair_capacity, cudaStream_t st);
+                long long pair_capacity, cudaStream_t st, float z_cull = 0.0f);
 
 __global__ void write_stats_kernel(const int* __restrict__ header, long long pair_capacity,
                                    int* __restrict__ stats);

@@ -54,14 +54,17 @@ struct FaceXYZ {
 };
 
 // Per-face (pixel independent) validity, A4.2 minus the bbox/pixel part.
-__device__ __forceinline__ bool face_is_drawable(const FaceXYZ& v, bool cull_backfaces) {
+// `z_cull` = max(0, z_clip_value): a face whose three vertices are all nearer than the clip plane is
+// culled, which is what PyTorch3D's clip_faces does to such faces before rasterising (z_cull = 0
+// reproduces the rasteriser's own `zmax < 0` test).
+__device__ __forceinline__ bool face_is_drawable(const FaceXYZ& v, bool cull_backfaces, float z_cull = 0.0f) {
   const float zmin = min3f(v.z0, v.z1, v.z2), zmax = max3f(v.z0, v.z1, v.z2);
   const float face_area = edge_fn(v.x0, v.y0, v.x1, v.y1, v.x2, v.y2);
   const bool back_face = face_area < 0.0f;
   const bool zero_area = (face_area <= kEps) && (face_area >= -kEps);
   // written so that NaN coordinates make the face undrawable
   if (!(zmin >= kEps)) return false;
-  if (zmax < 0.0f || zero_area || (cull_backfaces && back_face)) return false;
+  if (zmax < z_cull || zero_area || (cull_backfaces && back_face)) return false;
   return true;
 }
 

@@ -70,7 +70,7 @@ __global__ void camera_center_backward_kernel(const float* __restrict__ R, const
 // ---- fused fine pass ---------------------------------------------------------------------------
 struct FineArgs {
   const float* verts_ndc; const int* faces; const trb_view* views;
-  int H, W, K; float blur_radius, sqrt_blur; unsigned flags; TileGrid tg;
+  int H, W, K; float blur_radius, sqrt_blur, z_cull; unsigned flags; TileGrid tg;
   const int* tile_count; const int* tile_offset; const int* pairs;
   long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
   const int* ws_header; const int* busy_tiles;
@@ -163,7 +163,7 @@ render_fine_kernel(const FineArgs a) {
     if (j < nlist) {
       const int lf = overflow ? j : a.pairs[off + j];
       const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
-      const bool ok = overflow ? face_is_drawable(v, cull) : true;
+      const bool ok = overflow ? face_is_drawable(v, cull, a.z_cull) : true;
       if (ok) {
         bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
         bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
@@ -475,7 +475,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     if (j < nlist) {
       const int lf = overflow ? j : a.pairs[off + j];
       const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
-      const bool ok = overflow ? face_is_drawable(v, cull) : true;
+      const bool ok = overflow ? face_is_drawable(v, cull, a.z_cull) : true;
       if (ok) {
         float4 bb;
         bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
@@ -1065,7 +1065,7 @@ static int check_render_cfg(const trb_render_config* c) {
   if (s.shader != TRB_SHADER_NONE && (!(s.sigma > 0.0f) || !(s.gamma > 0.0f))) return TRB_ERR_BAD_ARG;
   if (s.shader >= 0 && s.shader != TRB_SHADER_SOFT_SILHOUETTE && s.texture_mode != TRB_TEX_VERTEX)
     return TRB_ERR_BAD_ARG;
-  if (!(c->blur_radius >= 0.0f) || c->max_face_count < 0 || c->max_vert_count < 0 || c->pair_capacity < 0 ||
+  if (!(c->blur_radius >= 0.0f) || !(c->z_clip_value == c->z_clip_value) || c->max_face_count < 0 || c->max_vert_count < 0 || c->pair_capacity < 0 ||
       c->num_world_verts < 0 || c->num_faces < 0 || c->num_ndc_verts < 0)
     return TRB_ERR_BAD_ARG;
   return TRB_OK;
@@ -1203,14 +1203,15 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
                              verts_ndc, device, stream);
   if (rc != TRB_OK) return rc;
   const float sqrt_blur = sqrtf(cfg->blur_radius);
+  const float z_cull = fmaxf(cfg->z_clip_value, 0.0f);
   rc = run_binning(verts_ndc, faces, views, N, cfg->max_face_count, H, W, tg, ws, workspace, sqrt_blur,
-                   cfg->raster_flags & TRB_CULL_BACKFACES, (long long)cfg->pair_capacity, st);
+                   cfg->raster_flags & TRB_CULL_BACKFACES, (long long)cfg->pair_capacity, st, z_cull);
   if (rc != TRB_OK) return rc;
 
   unsigned char* wsb = (unsigned char*)workspace;
   FineArgs a;
   a.verts_ndc = verts_ndc; a.faces = faces; a.views = views;
-  a.H = H; a.W = W; a.K = K; a.blur_radius = cfg->blur_radius; a.sqrt_blur = sqrt_blur;
+  a.H = H; a.W = W; a.K = K; a.blur_radius = cfg->blur_radius; a.sqrt_blur = sqrt_blur; a.z_cull = z_cull;
   a.flags = cfg->raster_flags; a.tg = tg;
   a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
   a.pairs = (const int*)(wsb + ws.pairs);

@@ -431,6 +431,7 @@ class _RenderFn(torch.autograd.Function):
         cfg.camera_center_from_rt = int(spec["camera_center_from_rt"])
         # light / explicit camera-centre gradients are only reduced when the parameter block wants them
         cfg.want_light_grad = int(view_params is not None and view_params.requires_grad)
+        cfg.z_clip_value = float(spec.get("z_clip", 0.0) or 0.0)
         cfg.num_world_verts, cfg.num_faces = verts.shape[0], (0 if faces is None else faces.shape[0])
         cfg.num_ndc_verts = table.total_ndc_verts
         cfg.pair_capacity = table.poll_capacity()

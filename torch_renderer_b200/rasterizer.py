@@ -115,6 +115,22 @@ def _cached_projection(cameras, proj_kwargs):
     return cache[1]
 
 
+def _cached_half_znear(cameras):
+    """znear / 2 of a camera that defines znear (FoV cameras), else None; the host read of the tensor is
+    done once per (tensor, version)."""
+    znear = cameras.get_znear()
+    if znear is None:
+        return None
+    if not torch.is_tensor(znear):
+        return float(znear) / 2.0
+    key = (id(znear), znear._version)
+    cache = cameras.__dict__.get("_trb_znear_cache")
+    if cache is None or cache[0] != key:
+        cache = (key, float(znear.min()) / 2.0)
+        cameras.__dict__["_trb_znear_cache"] = cache
+    return cache[1]
+
+
 def _expand_views(t: torch.Tensor, N: int, what: str) -> torch.Tensor:
     if t.shape[0] == N:
         return t
@@ -173,15 +189,20 @@ class MeshRasterizer(nn.Module):
             persp_correct = cameras.is_perspective()
         if raster_settings.cull_to_frustum:
             raise NotImplementedError("cull_to_frustum (clip_faces) is not built yet (SURVEY 8f rank 3)")
-        # z_clip_value: PyTorch3D clips faces against z = znear/2 for cameras that define znear.
-        # Faces with a vertex at or behind the camera plane are dropped by the kernel (A4.2); proper
-        # near-plane clipping of crossing faces is the `next` row 8f-3 and not built yet.
+        # z_clip_value: like upstream, cameras that define znear clip at znear / 2 unless the settings say
+        # otherwise.  Faces entirely nearer than the plane are culled in the kernels; faces CROSSING it are
+        # not split into clipped polygons yet -- they are drawn whole, or dropped when a
+        # vertex is at/behind the camera plane (A4.2).
+        z_clip = raster_settings.z_clip_value
+        if z_clip is None and cameras.is_perspective():
+            z_clip = _cached_half_znear(cameras)
         K = int(raster_settings.faces_per_pixel)
         if K > _lib.MAX_FACES_PER_PIXEL:
             raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
         flags = ((_lib.PERSPECTIVE_CORRECT if persp_correct else 0) | (_lib.CLIP_BARYCENTRIC if clip_bary else 0)
                  | (_lib.CULL_BACKFACES if raster_settings.cull_backfaces else 0))
         spec = dict(image_size=(H, W), K=K, blur_radius=float(raster_settings.blur_radius), flags=flags,
+                    z_clip=float(z_clip or 0.0),
                     perspective=bool(perspective), shader=_lib.SHADER_NONE, light_kind=0, sigma=1.0, gamma=1.0,
                     background=(0.0, 0.0, 0.0), camera_center_from_rt=False)
         return cameras, R, T, proj, spec

@@ -347,7 +347,11 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
 # filled in after each profiling pass, None until a capture of that kernel exists.
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {
+    # profiles/r01_ncu_full_v7.txt (ncu --set full, one launch each, 64 views of C2)
+    "render_fine_kernel": 701_876_992,      # 4.52 MB read + 697.35 MB written (algorithmic: 751.7 MB)
+    "render_backward_kernel": 22_633_728,   # only covered pixels (6% of the image) are re-read
+}
 
 
 def cpu_baseline(sample_views=2, threads=0):

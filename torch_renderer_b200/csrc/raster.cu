@@ -11,43 +11,69 @@
 //  * the per-pixel queue keeps only (z, face) -- 8 B per entry, in registers for K=1 and in
 //    shared memory otherwise -- and barycentrics/distances are recomputed for the K survivors;
 //  * ties are broken by (z, face index), so the result does not depend on list order.
-#include "raster_internal.cuh"
+#include "render_internal.cuh"
 
 namespace trb {
 
 // ------------------------------------------------------------------------------------------
 // Binning.  One thread per (view, face): count (FILL=false) or write (FILL=true) the face into
-// every tile its blur-inflated bounding box can touch.
+// every tile its blur-inflated bounding box can touch.  Neighbouring faces of a mesh mostly land in
+// the same tiles, so the lanes of a warp that address the same tile in the same step are grouped with
+// match.any and issue ONE atomic per group (the same-address atomics of the naive version serialised
+// in the L2: 2.2 ms for 4 x 1M faces).  A pair is (face, bits of the face's min vertex depth); the
+// K > 1 fine pass orders its tile lists by that depth.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
                  const trb_view* __restrict__ views, int H, int W, TileGrid tg, float sqrt_blur,
                  bool cull, int* __restrict__ tile_count, int* __restrict__ tile_fill,
-                 const int* __restrict__ tile_offset, int* __restrict__ pairs, float z_cull) {
+                 const int* __restrict__ tile_offset, int2* __restrict__ pairs, float z_cull) {
   const int n = blockIdx.y;
   const trb_view vd = views[n];
   const int lf = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lf >= vd.face_count) return;
-  const FaceXYZ v = load_face(verts, faces, vd, lf);
-  if (!face_is_drawable(v, cull, z_cull)) return;
-  const float xmin = min3f(v.x0, v.x1, v.x2) - sqrt_blur, xmax = max3f(v.x0, v.x1, v.x2) + sqrt_blur;
-  const float ymin = min3f(v.y0, v.y1, v.y2) - sqrt_blur, ymax = max3f(v.y0, v.y1, v.y2) + sqrt_blur;
-  int px0, px1, py0, py1;
-  pixel_range(xmin, xmax, W, H, px0, px1);
-  pixel_range(ymin, ymax, H, W, py0, py1);
-  if (px0 > px1 || py0 > py1) return;
-  const int tx0 = px0 >> tg.ltx, tx1 = px1 >> tg.ltx, ty0 = py0 >> tg.lty, ty1 = py1 >> tg.lty;
-  const int tbase = n * tg.tiles_x * tg.tiles_y;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const int t = tbase + ty * tg.tiles_x + tx;
-      if (!FILL) {
-        atomicAdd(tile_count + t, 1);
-      } else {
-        const int off = tile_offset[t];
-        if (off >= 0) pairs[off + atomicAdd(tile_fill + t, 1)] = lf;
+  const int lane = threadIdx.x & 31;
+  int tx0 = 0, ty0 = 0, nx = 0, ny = 0;
+  float zmin = 0.0f;
+  if (lf < vd.face_count) {
+    const FaceXYZ v = load_face(verts, faces, vd, lf);
+    if (face_is_drawable(v, cull, z_cull)) {
+      const float xmin = min3f(v.x0, v.x1, v.x2) - sqrt_blur, xmax = max3f(v.x0, v.x1, v.x2) + sqrt_blur;
+      const float ymin = min3f(v.y0, v.y1, v.y2) - sqrt_blur, ymax = max3f(v.y0, v.y1, v.y2) + sqrt_blur;
+      int px0, px1, py0, py1;
+      pixel_range(xmin, xmax, W, H, px0, px1);
+      pixel_range(ymin, ymax, H, W, py0, py1);
+      if (px0 <= px1 && py0 <= py1) {
+        tx0 = px0 >> tg.ltx; ty0 = py0 >> tg.lty;
+        nx = (px1 >> tg.ltx) - tx0 + 1; ny = (py1 >> tg.lty) - ty0 + 1;
+        zmin = min3f(v.z0, v.z1, v.z2);
       }
     }
+  }
+  const int cnt = nx * ny;
+  const int steps = __reduce_max_sync(0xffffffffu, cnt);  // warp-uniform trip count
+  const int tbase = n * tg.tiles_x * tg.tiles_y;
+  int ix = 0, iy = 0;
+  for (int i = 0; i < steps; ++i) {
+    const bool have = i < cnt;
+    // lanes without a tile in this step get distinct negative keys: singleton groups, skipped
+    const int t = have ? tbase + (ty0 + iy) * tg.tiles_x + tx0 + ix : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, t);
+    if (have) {
+      const int leader = __ffs(peers) - 1;
+      const int npeers = __popc(peers);
+      if (!FILL) {
+        if (lane == leader) atomicAdd(tile_count + t, npeers);
+      } else {
+        const int off = tile_offset[t];
+        int base = 0;
+        if (lane == leader && off >= 0) base = atomicAdd(tile_fill + t, npeers);
+        base = __shfl_sync(peers, base, leader);
+        if (off >= 0)
+          pairs[(size_t)off + base + __popc(peers & ((1u << lane) - 1u))] = make_int2(lf, __float_as_int(zmin));
+      }
+      if (++ix == nx) { ix = 0; ++iy; }
+    }
+  }
 }
 
 // Hands every non-empty tile a contiguous slice of `pairs` (order between tiles is irrelevant).
@@ -95,125 +121,6 @@ __global__ void write_stats_kernel(const int* __restrict__ header, long long pai
   stats[1] = header[2];
   stats[2] = (int)min(pair_capacity, (long long)0x7fffffff);
   stats[3] = 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// Fine pass: one CTA per (view, tile), one thread per pixel.  The tile's face list is staged
-// through shared memory NT faces at a time (each thread fetches one face and precomputes its
-// inflated bbox); every thread then walks the staged faces with broadcast LDS reads.
-template <int LTX, int LTY, bool PERSP, bool CLIP, bool K1>
-__global__ void __launch_bounds__((1 << LTX) * (1 << LTY))
-raster_fine_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
-                   const trb_view* __restrict__ views, int H, int W, int K, float blur_radius,
-                   float sqrt_blur, bool cull, TileGrid tg, const int* __restrict__ tile_count,
-                   const int* __restrict__ tile_offset, const int* __restrict__ pairs,
-                   long long* __restrict__ out_p2f, float* __restrict__ out_z,
-                   float* __restrict__ out_bary, float* __restrict__ out_d) {
-  constexpr int TX = 1 << LTX, TY = 1 << LTY, NT = TX * TY;
-  __shared__ float4 s_bb[NT];  // xmin, xmax, ymin, ymax (blur inflated; empty when undrawable)
-  __shared__ float4 s_va[NT];  // x0 y0 z0 x1
-  __shared__ float4 s_vb[NT];  // y1 z1 x2 y2
-  __shared__ float s_vc[NT];   // z2
-  __shared__ int s_id[NT];
-  extern __shared__ unsigned char s_dyn[];  // K>1: float kz[K][NT]; int kf[K][NT]
-  float* kz = reinterpret_cast<float*>(s_dyn);
-  int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)(K1 ? 0 : K) * NT;
-
-  const int n = blockIdx.z;
-  const trb_view vd = views[n];
-  const int tid = threadIdx.x;
-  const int xi = blockIdx.x * TX + (tid & (TX - 1));
-  const int yi = blockIdx.y * TY + (tid >> LTX);
-  const bool live = (xi < W) && (yi < H);
-  const float px = pix_to_ndc(W - 1 - xi, W, H);
-  const float py = pix_to_ndc(H - 1 - yi, H, W);
-
-  const int t = (n * tg.tiles_y + blockIdx.y) * tg.tiles_x + blockIdx.x;
-  int nlist = tile_count[t];
-  const int off = tile_offset[t];
-  const bool overflow = (nlist > 0) && (off < 0);
-  if (overflow) nlist = vd.face_count;
-
-  int cnt = 0;
-  float best_z = 0.0f; int best_f = -1; Sample best_s = {0, 0, 0, 0, 0};
-
-  for (int base = 0; base < nlist; base += NT) {
-    const int j = base + tid;
-    float4 bb = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
-    if (j < nlist) {
-      const int lf = overflow ? j : pairs[off + j];
-      const FaceXYZ v = load_face(verts, faces, vd, lf);
-      const bool ok = overflow ? face_is_drawable(v, cull) : true;
-      if (ok) {
-        bb.x = fsub(min3f(v.x0, v.x1, v.x2), sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), sqrt_blur);
-        bb.z = fsub(min3f(v.y0, v.y1, v.y2), sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), sqrt_blur);
-      }
-      s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
-      s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
-      s_vc[tid] = v.z2;
-      s_id[tid] = lf;
-    }
-    s_bb[tid] = bb;
-    __syncthreads();
-    const int m = min(NT, nlist - base);
-    if (live) {
-      for (int q = 0; q < m; ++q) {
-        const float4 b = s_bb[q];
-        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
-        const float4 a = s_va[q], c = s_vb[q];
-        FaceXYZ v;
-        v.x0 = a.x; v.y0 = a.y; v.z0 = a.z; v.x1 = a.w;
-        v.y1 = c.x; v.z1 = c.y; v.x2 = c.z; v.y2 = c.w; v.z2 = s_vc[q];
-        Sample s;
-        if (!eval_pixel_face<PERSP, CLIP>(v, px, py, blur_radius, s)) continue;
-        const int f = s_id[q];
-        if (K1) {
-          if (best_f < 0 || cand_less(s.z, f, best_z, best_f)) { best_z = s.z; best_f = f; best_s = s; }
-        } else {
-          if (cnt == K && !cand_less(s.z, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
-          int pos = cnt < K ? cnt : K - 1;
-          while (pos > 0 && cand_less(s.z, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
-            kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
-            kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
-            --pos;
-          }
-          kz[pos * NT + tid] = s.z; kf[pos * NT + tid] = f;
-          if (cnt < K) ++cnt;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (!live) return;
-
-  const size_t pix = ((size_t)n * H + yi) * W + xi;
-  if (K1) {
-    const bool hit = best_f >= 0;
-    st_cs(out_p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
-    st_cs(out_z + pix, hit ? best_s.z : -1.0f);
-    st_cs(out_d + pix, hit ? best_s.d : -1.0f);
-    st_cs(out_bary + pix * 3 + 0, hit ? best_s.c0 : -1.0f);
-    st_cs(out_bary + pix * 3 + 1, hit ? best_s.c1 : -1.0f);
-    st_cs(out_bary + pix * 3 + 2, hit ? best_s.c2 : -1.0f);
-  } else {
-    const size_t o = pix * K;
-    for (int k = 0; k < K; ++k) {
-      Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
-      long long pf = -1;
-      if (k < cnt) {
-        const int f = kf[k * NT + tid];
-        const FaceXYZ v = load_face(verts, faces, vd, f);
-        eval_pixel_face<PERSP, CLIP>(v, px, py, blur_radius, s);
-        pf = (long long)vd.p2f_base + f;
-      }
-      st_cs(out_p2f + o + k, pf);
-      st_cs(out_z + o + k, s.z);
-      st_cs(out_d + o + k, s.d);
-      st_cs(out_bary + (o + k) * 3 + 0, s.c0);
-      st_cs(out_bary + (o + k) * 3 + 1, s.c1);
-      st_cs(out_bary + (o + k) * 3 + 2, s.c2);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -283,7 +190,7 @@ int run_binning(const float* verts_ndc, const int* faces, const trb_view* views,
   int* tile_count = (int*)(wsb + ws.count);
   int* tile_fill = (int*)(wsb + ws.fill);
   int* tile_offset = (int*)(wsb + ws.offset);
-  int* pairs = (int*)(wsb + ws.pairs);
+  int2* pairs = (int2*)(wsb + ws.pairs);
   const int ntiles = N * tg.tiles_x * tg.tiles_y;
   // header, tile_count and tile_fill are contiguous: one memset
   TRB_CUDA_TRY(cudaMemsetAsync(wsb, 0, ws.offset, st));
@@ -299,31 +206,6 @@ int run_binning(const float* verts_ndc, const int* faces, const trb_view* views,
                                                   tile_count, tile_fill, tile_offset, pairs, z_cull);
     TRB_LAUNCH_CHECK();
   }
-  return TRB_OK;
-}
-
-template <int LTX, int LTY, bool K1>
-static int launch_fine(bool persp, bool clip, dim3 grid, size_t dyn_smem, cudaStream_t st,
-                       const float* verts, const int* faces, const trb_view* views, int H, int W,
-                       int K, float blur, float sqrt_blur, bool cull, TileGrid tg, const int* tc,
-                       const int* to, const int* pairs, long long* p2f, float* z, float* bary,
-                       float* d) {
-  constexpr int NT = (1 << LTX) * (1 << LTY);
-#define TRB_FINE(P, C)                                                                           \
-  do {                                                                                           \
-    auto kern = raster_fine_kernel<LTX, LTY, P, C, K1>;                                          \
-    if (dyn_smem > 0)                                                                            \
-      TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                        (int)dyn_smem));                                         \
-    kern<<<grid, NT, dyn_smem, st>>>(verts, faces, views, H, W, K, blur, sqrt_blur, cull, tg, tc, \
-                                     to, pairs, p2f, z, bary, d);                                \
-  } while (0)
-  if (persp && clip) TRB_FINE(true, true);
-  else if (persp) TRB_FINE(true, false);
-  else if (clip) TRB_FINE(false, true);
-  else TRB_FINE(false, false);
-#undef TRB_FINE
-  TRB_LAUNCH_CHECK();
   return TRB_OK;
 }
 
@@ -361,37 +243,26 @@ extern "C" int trb_raster_forward(const float* verts_ndc, const int32_t* faces, 
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* wsb = (unsigned char*)workspace;
-  int* header = (int*)(wsb + ws.header);
-  int* tile_count = (int*)(wsb + ws.count);
-  int* tile_offset = (int*)(wsb + ws.offset);
-  int* pairs = (int*)(wsb + ws.pairs);
   const float sqrt_blur = sqrtf(blur_radius);
-  const bool cull = flags & TRB_CULL_BACKFACES;
   {
     const int brc = run_binning(verts_ndc, faces, views, N, max_face_count, H, W, tg, ws, workspace, sqrt_blur,
-                                cull, (long long)pair_capacity, st);
+                                flags & TRB_CULL_BACKFACES, (long long)pair_capacity, st);
     if (brc != TRB_OK) return brc;
   }
-  const dim3 grid(tg.tiles_x, tg.tiles_y, N);
-  const bool persp = flags & TRB_PERSPECTIVE_CORRECT, clip = flags & TRB_CLIP_BARYCENTRIC;
-  long long* p2f = (long long*)pix_to_face;
-  int rc;
-  if (K == 1) {
-    rc = launch_fine<4, 4, true>(persp, clip, grid, 0, st, verts_ndc, faces, views, H, W, K, blur_radius,
-                                 sqrt_blur, cull, tg, tile_count, tile_offset, pairs, p2f, zbuf, bary,
-                                 dists);
-  } else if (tg.ltx == 4) {
-    rc = launch_fine<4, 4, false>(persp, clip, grid, (size_t)K * 8 * 256, st, verts_ndc, faces, views, H,
-                                  W, K, blur_radius, sqrt_blur, cull, tg, tile_count, tile_offset, pairs,
-                                  p2f, zbuf, bary, dists);
-  } else {
-    rc = launch_fine<3, 3, false>(persp, clip, grid, (size_t)K * 8 * 64, st, verts_ndc, faces, views, H,
-                                  W, K, blur_radius, sqrt_blur, cull, tg, tile_count, tile_offset, pairs,
-                                  p2f, zbuf, bary, dists);
-  }
+  // the fused fine kernels with the shading epilogue compiled out (TRB_SHADER_NONE)
+  FineArgs a = {};
+  a.verts_ndc = verts_ndc; a.faces = faces; a.views = views;
+  a.H = H; a.W = W; a.K = K; a.blur_radius = blur_radius; a.sqrt_blur = sqrt_blur; a.z_cull = 0.0f;
+  a.flags = flags; a.tg = tg;
+  a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
+  a.pairs = (const int2*)(wsb + ws.pairs);
+  a.ws_header = (const int*)(wsb + ws.header); a.busy_tiles = (const int*)(wsb + ws.busy);
+  a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
+  a.sigma = 1.0f; a.gamma = 1.0f;
+  const int rc = launch_render_fine(TRB_SHADER_NONE, 0, N, st, a);
   if (rc != TRB_OK) return rc;
   if (stats) {
-    write_stats_kernel<<<1, 1, 0, st>>>(header, (long long)pair_capacity, stats);
+    write_stats_kernel<<<1, 1, 0, st>>>((const int*)(wsb + ws.header), (long long)pair_capacity, stats);
     TRB_LAUNCH_CHECK();
   }
   return TRB_OK;

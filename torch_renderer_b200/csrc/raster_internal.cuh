@@ -31,7 +31,7 @@ __host__ inline WsLayout make_ws_layout(int N, const TileGrid& g, int64_t pair_c
   w.offset = w.fill + align(ntiles * 4);
   w.busy = w.offset + align(ntiles * 4);   // compact list of non-empty tiles (header[4] = its length)
   w.pairs = w.busy + align(ntiles * 4);
-  w.total = w.pairs + align((size_t)pair_capacity * 4);
+  w.total = w.pairs + align((size_t)pair_capacity * 8);  // int2 (face, bits of the min vertex z)
   return w;
 }
 

@@ -12,9 +12,7 @@
 // backward (no grad_bary / grad_zbuf / grad_dists tensors exist), scattering with warp-aggregated
 // atomics -> camera-centre backward -> NDC->world backward -> vertex-normal backward (2).  Tiles the
 // forward leaves a compact list of covered pixels (`hit_pixels`); the backward visits only those.
-#include "raster_internal.cuh"
-#include "shade_math.cuh"
-#include "trb_internal.cuh"
+#include "render_internal.cuh"
 
 namespace trb {
 
@@ -67,278 +65,7 @@ __global__ void camera_center_backward_kernel(const float* __restrict__ R, const
   }
 }
 
-// ---- fused fine pass ---------------------------------------------------------------------------
-struct FineArgs {
-  const float* verts_ndc; const int* faces; const trb_view* views;
-  int H, W, K; float blur_radius, sqrt_blur, z_cull; unsigned flags; TileGrid tg;
-  const int* tile_count; const int* tile_offset; const int* pairs;
-  long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
-  const int* ws_header; const int* busy_tiles;
-  const float* view_params; const float* verts_world; const float* normals; const float* colors;
-  float sigma, gamma, bg0, bg1, bg2;
-};
 
-// Appends the linear indices of the pixels of this CTA that got at least one face to the global
-// list the backward pass walks (hit_pixels[0] = count, [1..] = pixel ids, row-major inside a tile so
-// that neighbouring lanes of the backward still see neighbouring pixels).  Must be reached by every
-// thread of the CTA.
-template <int NT>
-__device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int pix) {
-  __shared__ int s_wcnt[NT / 32];
-  __shared__ int s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned ball = __ballot_sync(0xffffffffu, hit);
-  if (lane == 0) s_wcnt[warp] = __popc(ball);
-  __syncthreads();
-  if (tid == 0) {
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
-    s_base = tot > 0 ? atomicAdd(hit_pixels, tot) : 0;
-  }
-  __syncthreads();
-  if (hit) hit_pixels[1 + s_base + s_wcnt[warp] + __popc(ball & ((1u << lane) - 1u))] = pix;
-}
-
-struct ShadeIn {
-  const float* verts_world; const float* normals; const float* colors; const int* faces;
-};
-
-template <int LIGHT>
-__device__ __forceinline__ F3 shade_sample(const ShadeIn& in, const trb_view& vd, const ViewParams& vp,
-                                           int local_face, float b0, float b1, float b2) {
-  const size_t r = (size_t)(vd.face_start + local_face);
-  const int i0 = __ldg(in.faces + 3 * r), i1 = __ldg(in.faces + 3 * r + 1), i2 = __ldg(in.faces + 3 * r + 2);
-  const F3 tex = interp3(b0, b1, b2, ld3(in.colors, i0), ld3(in.colors, i1), ld3(in.colors, i2));
-  if (LIGHT == TRB_LIGHT_AMBIENT) return {vp.amb[0] * tex.x, vp.amb[1] * tex.y, vp.amb[2] * tex.z};
-  const F3 P = interp3(b0, b1, b2, ld3(in.verts_world, i0), ld3(in.verts_world, i1), ld3(in.verts_world, i2));
-  const F3 nr = interp3(b0, b1, b2, ld3(in.normals, i0), ld3(in.normals, i1), ld3(in.normals, i2));
-  Lit lit;
-  return phong_color<LIGHT>(vp, P, nr, tex, lit);
-}
-
-template <int LTX, int LTY, bool K1, int SHADER, int LIGHT>
-__global__ void __launch_bounds__((1 << LTX) * (1 << LTY))
-render_fine_kernel(const FineArgs a) {
-  constexpr int TX = 1 << LTX, TY = 1 << LTY, NT = TX * TY;
-  __shared__ float4 s_bb[NT];   // xmin, xmax, ymin, ymax (blur inflated; empty when undrawable)
-  __shared__ float4 s_va[NT];   // x0 y0 z0 x1
-  __shared__ float4 s_vb[NT];   // y1 z1 x2 y2
-  __shared__ float2 s_vc[NT];   // z2, area (= edge(v2;v0,v1) + kEps)
-  __shared__ float s_zlo[NT];   // lower bound of the depth this face can produce (0: none)
-  __shared__ int s_id[NT];
-  extern __shared__ unsigned char s_dyn[];  // K>1: float kz[K][NT]; int kf[K][NT]
-  const int K = a.K;
-  float* kz = reinterpret_cast<float*>(s_dyn);
-  int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)(K1 ? 0 : K) * NT;
-
-  const int n = blockIdx.z;
-  const trb_view vd = a.views[n];
-  const int tid = threadIdx.x;
-  const int H = a.H, W = a.W;
-  const int xi = blockIdx.x * TX + (tid & (TX - 1));
-  const int yi = blockIdx.y * TY + (tid >> LTX);
-  const bool live = (xi < W) && (yi < H);
-  const float px = pix_to_ndc(W - 1 - xi, W, H);
-  const float py = pix_to_ndc(H - 1 - yi, H, W);
-  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
-  const bool cull = a.flags & TRB_CULL_BACKFACES;
-  const bool hard_edges = a.blur_radius == 0.0f;
-  const float blur = a.blur_radius;
-
-  const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
-  int nlist = a.tile_count[t];
-  const int off = a.tile_offset[t];
-  const bool overflow = (nlist > 0) && (off < 0);
-  if (overflow) nlist = vd.face_count;
-
-  int cnt = 0;
-  float best_z = 0.0f; int best_f = -1;
-  Sample best_s = {0, 0, 0, 0, 0};
-  FaceXYZ best_v = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-
-  for (int base = 0; base < nlist; base += NT) {
-    const int j = base + tid;
-    float4 bb = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
-    if (j < nlist) {
-      const int lf = overflow ? j : a.pairs[off + j];
-      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
-      const bool ok = overflow ? face_is_drawable(v, cull, a.z_cull) : true;
-      if (ok) {
-        bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
-        bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
-      }
-      const float area_e = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
-      s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
-      s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
-      s_vc[tid] = make_float2(v.z2, area_e);
-      s_id[tid] = lf;
-      // Lower bound of the depth any pixel can get from this face (0 = no bound).  With barycentric
-      // clipping the stored weights are a convex combination, so z >= min vertex z up to rounding;
-      // with blur 0 every candidate is strictly inside and the same holds (times area_raw/(area_raw+kEps)
-      // when the weights are not renormalised).  A full top-K list whose K-th depth is already below
-      // this bound cannot change, which skips ~95% of the per-pixel evaluations when K faces are kept
-      // out of hundreds inside the blur band (1M-face mesh, K=8: 1500+ candidates per pixel).
-      const float zmin = min3f(v.z0, v.z1, v.z2);
-      float zlo = 0.0f;
-      if (clip) zlo = (!persp || zmin >= 1e-3f) ? zmin * 0.99999f : 0.0f;
-      else if (hard_edges) {
-        if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
-        else zlo = zmin * 0.99999f * (area_e > 0.0f ? fmaxf(0.0f, (area_e - 2e-8f) / area_e) : 1.0f);
-      }
-      s_zlo[tid] = zlo;
-    }
-    s_bb[tid] = bb;
-    __syncthreads();
-    const int m = min(NT, nlist - base);
-    if (live) {
-      for (int q = 0; q < m; ++q) {
-        const float4 b = s_bb[q];
-        if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
-        if (K1 ? (best_f >= 0 && s_zlo[q] > best_z) : (cnt == K && s_zlo[q] > kz[(K - 1) * NT + tid])) continue;
-        const float4 va = s_va[q], vb = s_vb[q];
-        const float2 vc = s_vc[q];
-        FaceXYZ v;
-        v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
-        v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
-        const float area = vc.y;
-        const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
-        const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
-        const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
-        if (hard_edges) {
-          // blur 0: only strictly-inside samples survive, and w_i = e_i / area keeps the sign of
-          // e_i * area exactly, so a non-positive edge is an exact (not approximate) reject.
-          if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
-                          : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
-            continue;
-        }
-        Sample s;
-        bool inside;
-        if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, s.z, s.c0, s.c1, s.c2, inside)) continue;
-        if (hard_edges) {
-          if (!inside) continue;
-          s.d = 0.0f;  // filled in for the winner(s) only
-        } else {
-          const float dist = triangle_d2(v, px, py);
-          if (!inside && dist >= blur) continue;
-          s.d = inside ? -dist : dist;
-        }
-        const int f = s_id[q];
-        if (K1) {
-          if (best_f < 0 || cand_less(s.z, f, best_z, best_f)) { best_z = s.z; best_f = f; best_s = s; best_v = v; }
-        } else {
-          if (cnt == K && !cand_less(s.z, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
-          int pos = cnt < K ? cnt : K - 1;
-          while (pos > 0 && cand_less(s.z, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
-            kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
-            kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
-            --pos;
-          }
-          kz[pos * NT + tid] = s.z; kf[pos * NT + tid] = f;
-          if (cnt < K) ++cnt;
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  const bool hit = live && (K1 ? best_f >= 0 : cnt > 0);
-  const size_t pix = ((size_t)n * H + yi) * W + xi;
-  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
-  if (!live) return;
-
-  ViewParams vp;
-  ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
-  if (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG) vp = load_view_params(a.view_params, n);
-  const float eps = 1e-10f;
-
-  if (K1) {
-    if (hit && hard_edges) best_s.d = -triangle_d2(best_v, px, py);
-    st_cs(a.p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
-    st_cs(a.zbuf + pix, hit ? best_s.z : -1.0f);
-    st_cs(a.dists + pix, hit ? best_s.d : -1.0f);
-    st_cs(a.bary + pix * 3 + 0, hit ? best_s.c0 : -1.0f);
-    st_cs(a.bary + pix * 3 + 1, hit ? best_s.c1 : -1.0f);
-    st_cs(a.bary + pix * 3 + 2, hit ? best_s.c2 : -1.0f);
-    if (SHADER == TRB_SHADER_NONE) return;
-    float4 out;
-    if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
-      // 1 - (1 - p) is not bit-identical to p; keep the product form of sigmoid_alpha_blend
-      out = make_float4(1.0f, 1.0f, 1.0f, hit ? 1.0f - (1.0f - sigmoidf(-best_s.d / a.sigma)) : 0.0f);
-    } else if (!hit) {
-      out = make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
-    } else {
-      const F3 c = shade_sample<LIGHT>(sin, vd, vp, best_f, best_s.c0, best_s.c1, best_s.c2);
-      if (SHADER == TRB_SHADER_HARD_PHONG) {
-        out = make_float4(c.x, c.y, c.z, 1.0f);
-      } else {
-        const float zrange = vp.zfar - vp.znear;
-        const float zinv = (vp.zfar - best_s.z) / zrange;
-        const float zmax = fmaxf(zinv, eps);
-        const float prob = sigmoidf(-best_s.d / a.sigma);
-        const float w = prob * expf((zinv - zmax) / a.gamma);
-        const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
-        const float inv = 1.0f / (w + delta);
-        out = make_float4((w * c.x + delta * a.bg0) * inv, (w * c.y + delta * a.bg1) * inv,
-                          (w * c.z + delta * a.bg2) * inv, 1.0f - (1.0f - prob));
-      }
-    }
-    st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
-    return;
-  }
-
-  // K > 1: layers are sorted front to back, so the softmax's max z_inv belongs to layer 0
-  const size_t o = pix * K;
-  float alpha = 1.0f, wsum = 0.0f, zmax = eps, zrange = 1.0f;
-  F3 acc = {0, 0, 0};
-  F3 hard_c = {a.bg0, a.bg1, a.bg2};
-  if (SHADER == TRB_SHADER_SOFT_PHONG) {
-    zrange = vp.zfar - vp.znear;
-    if (cnt > 0) zmax = fmaxf(eps, (vp.zfar - kz[tid]) / zrange);
-  }
-  for (int k = 0; k < K; ++k) {
-    Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
-    long long pf = -1;
-    if (k < cnt) {
-      const int f = kf[k * NT + tid];
-      const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
-      eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
-      pf = (long long)vd.p2f_base + f;
-      if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
-        alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
-      } else if (SHADER == TRB_SHADER_HARD_PHONG) {
-        if (k == 0) hard_c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
-      } else if (SHADER == TRB_SHADER_SOFT_PHONG) {
-        const float prob = sigmoidf(-s.d / a.sigma);
-        alpha *= 1.0f - prob;
-        const float zinv = (vp.zfar - s.z) / zrange;
-        const float w = prob * expf((zinv - zmax) / a.gamma);
-        const F3 c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
-        wsum += w;
-        acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
-      }
-    }
-    st_cs(a.p2f + o + k, pf);
-    st_cs(a.zbuf + o + k, s.z);
-    st_cs(a.dists + o + k, s.d);
-    st_cs(a.bary + (o + k) * 3 + 0, s.c0);
-    st_cs(a.bary + (o + k) * 3 + 1, s.c1);
-    st_cs(a.bary + (o + k) * 3 + 2, s.c2);
-  }
-  if (SHADER == TRB_SHADER_NONE) return;
-  float4 out;
-  if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
-    out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
-  } else if (SHADER == TRB_SHADER_HARD_PHONG) {
-    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt > 0 ? 1.0f : 0.0f);
-  } else {
-    const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
-    const float inv = 1.0f / (wsum + delta);
-    out = make_float4((acc.x + delta * a.bg0) * inv, (acc.y + delta * a.bg1) * inv,
-                      (acc.z + delta * a.bg2) * inv, 1.0f - alpha);
-  }
-  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
-}
 
 // ---- fused fine pass, faces_per_pixel == 1 ---------------------------------------------------------
 // The meshes this path sees most (cow at 512^2: ~3.5 px per face, ~200 faces per 16x16 tile) make a
@@ -473,7 +200,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     const int j = base + tid;
     int npx = 0;
     if (j < nlist) {
-      const int lf = overflow ? j : a.pairs[off + j];
+      const int lf = overflow ? j : a.pairs[off + j].x;
       const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
       const bool ok = overflow ? face_is_drawable(v, cull, a.z_cull) : true;
       if (ok) {
@@ -1075,30 +802,6 @@ static inline bool is_phong(int shader) {
   return shader == TRB_SHADER_SOFT_PHONG || shader == TRB_SHADER_HARD_PHONG;
 }
 
-template <int LTX, int LTY, bool K1>
-static int launch_render_fine(int shader, int light, dim3 grid, size_t dyn, cudaStream_t st, const FineArgs& a) {
-  constexpr int NT = (1 << LTX) * (1 << LTY);
-#define TRB_RF(SH, L)                                                                             \
-  do {                                                                                            \
-    auto kern = render_fine_kernel<LTX, LTY, K1, SH, L>;                                          \
-    if (dyn > 0)                                                                                  \
-      TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-    kern<<<grid, NT, dyn, st>>>(a);                                                               \
-  } while (0)
-  if (shader == TRB_SHADER_NONE) TRB_RF(TRB_SHADER_NONE, 0);
-  else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RF(TRB_SHADER_SOFT_SILHOUETTE, 0);
-  else if (shader == TRB_SHADER_SOFT_PHONG) {
-    if (light == 0) TRB_RF(TRB_SHADER_SOFT_PHONG, 0); else if (light == 1) TRB_RF(TRB_SHADER_SOFT_PHONG, 1);
-    else TRB_RF(TRB_SHADER_SOFT_PHONG, 2);
-  } else {
-    if (light == 0) TRB_RF(TRB_SHADER_HARD_PHONG, 0); else if (light == 1) TRB_RF(TRB_SHADER_HARD_PHONG, 1);
-    else TRB_RF(TRB_SHADER_HARD_PHONG, 2);
-  }
-#undef TRB_RF
-  TRB_LAUNCH_CHECK();
-  return TRB_OK;
-}
-
 static int launch_render_fine_k1(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
 #define TRB_RF1(SH, L) render_fine_k1_kernel<SH, L><<<grid, 256, 0, st>>>(a)
   if (shader == TRB_SHADER_NONE) TRB_RF1(TRB_SHADER_NONE, 0);
@@ -1137,6 +840,12 @@ static int launch_render_backward(int shader, int light, dim3 grid, int nt, size
 #undef TRB_RB
   TRB_LAUNCH_CHECK();
   return TRB_OK;
+}
+
+int launch_render_fine(int shader, int light, int N, cudaStream_t st, const FineArgs& a) {
+  if (a.K == 1)
+    return launch_render_fine_k1(shader, light, dim3(ceil_div(a.tg.tiles_x, kStrip), a.tg.tiles_y, N), st, a);
+  return launch_render_fine_kn(shader, light, N, st, a);
 }
 
 static cudaEvent_t g_dbg_events[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1214,19 +923,16 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.H = H; a.W = W; a.K = K; a.blur_radius = cfg->blur_radius; a.sqrt_blur = sqrt_blur; a.z_cull = z_cull;
   a.flags = cfg->raster_flags; a.tg = tg;
   a.tile_count = (const int*)(wsb + ws.count); a.tile_offset = (const int*)(wsb + ws.offset);
-  a.pairs = (const int*)(wsb + ws.pairs);
+  a.pairs = (const int2*)(wsb + ws.pairs);
   a.ws_header = (const int*)(wsb + ws.header); a.busy_tiles = (const int*)(wsb + ws.busy);
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
   a.hit_pixels = tile_hit;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
-  const dim3 grid(tg.tiles_x, tg.tiles_y, N);
   TRB_CUDA_TRY(cudaMemsetAsync(tile_hit, 0, sizeof(int), st));
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
-  if (K == 1) rc = launch_render_fine_k1(sc.shader, sc.light_kind, dim3(ceil_div(tg.tiles_x, kStrip), tg.tiles_y, N), st, a);
-  else if (tg.ltx == 4) rc = launch_render_fine<4, 4, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 256, st, a);
-  else rc = launch_render_fine<3, 3, false>(sc.shader, sc.light_kind, grid, (size_t)K * 8 * 64, st, a);
+  rc = launch_render_fine(sc.shader, sc.light_kind, N, st, a);
   if (rc != TRB_OK) return rc;
   if (g_dbg_events[1]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[1], st));
   if (stats) {

@@ -1,0 +1,65 @@
+// Declarations shared by the fused forward kernels (render.cu: faces_per_pixel == 1; render_kn.cu:
+// faces_per_pixel > 1): kernel arguments, the covered-pixel list, the per-sample shading call.
+#pragma once
+#include "raster_internal.cuh"
+#include "shade_math.cuh"
+#include "trb_internal.cuh"
+
+namespace trb {
+
+struct FineArgs {
+  const float* verts_ndc; const int* faces; const trb_view* views;
+  int H, W, K; float blur_radius, sqrt_blur, z_cull; unsigned flags; TileGrid tg;
+  const int* tile_count; const int* tile_offset; const int2* pairs;  // (face, bits of min vertex z)
+  long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
+  const int* ws_header; const int* busy_tiles;
+  const float* view_params; const float* verts_world; const float* normals; const float* colors;
+  float sigma, gamma, bg0, bg1, bg2;
+};
+
+// Appends the linear indices of the pixels of this CTA that got at least one face to the global
+// list the backward pass walks (hit_pixels[0] = count, [1..] = pixel ids, row-major inside a tile so
+// that neighbouring lanes of the backward still see neighbouring pixels).  Must be reached by every
+// thread of the CTA.
+template <int NT>
+__device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int pix) {
+  __shared__ int s_wcnt[NT / 32];
+  __shared__ int s_base;
+  if (hit_pixels == nullptr) return;  // stand-alone rasteriser: no fused backward follows
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ball = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) s_wcnt[warp] = __popc(ball);
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+    s_base = tot > 0 ? atomicAdd(hit_pixels, tot) : 0;
+  }
+  __syncthreads();
+  if (hit) hit_pixels[1 + s_base + s_wcnt[warp] + __popc(ball & ((1u << lane) - 1u))] = pix;
+}
+
+struct ShadeIn {
+  const float* verts_world; const float* normals; const float* colors; const int* faces;
+};
+
+template <int LIGHT>
+__device__ __forceinline__ F3 shade_sample(const ShadeIn& in, const trb_view& vd, const ViewParams& vp,
+                                           int local_face, float b0, float b1, float b2) {
+  const size_t r = (size_t)(vd.face_start + local_face);
+  const int i0 = __ldg(in.faces + 3 * r), i1 = __ldg(in.faces + 3 * r + 1), i2 = __ldg(in.faces + 3 * r + 2);
+  const F3 tex = interp3(b0, b1, b2, ld3(in.colors, i0), ld3(in.colors, i1), ld3(in.colors, i2));
+  if (LIGHT == TRB_LIGHT_AMBIENT) return {vp.amb[0] * tex.x, vp.amb[1] * tex.y, vp.amb[2] * tex.z};
+  const F3 P = interp3(b0, b1, b2, ld3(in.verts_world, i0), ld3(in.verts_world, i1), ld3(in.verts_world, i2));
+  const F3 nr = interp3(b0, b1, b2, ld3(in.normals, i0), ld3(in.normals, i1), ld3(in.normals, i2));
+  Lit lit;
+  return phong_color<LIGHT>(vp, P, nr, tex, lit);
+}
+
+// Fine pass of one batch: the K == 1 strip kernel (render.cu) or the K > 1 kernel (render_kn.cu).
+int launch_render_fine(int shader, int light, int N, cudaStream_t st, const FineArgs& a);
+// faces_per_pixel > 1 (render_kn.cu)
+int launch_render_fine_kn(int shader, int light, int N, cudaStream_t st, const FineArgs& a);
+
+}  // namespace trb

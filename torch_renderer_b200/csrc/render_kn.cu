@@ -1,0 +1,428 @@
+// Fused fine pass for faces_per_pixel > 1 (sm_100a): per-pixel top-K rasterisation of one tile per CTA
+// with the shading + blending epilogue (reference call sites: camera_pose_optimizer.py:116-121 --
+// SoftSilhouette K=50 --, mesh_deformer.py:135-145, BASELINE config 5 -- 1M faces, K=8; semantics SURVEY
+// A3-A8).  What differs from a plain "every pixel walks the tile's face list":
+//
+//  * DEPTH-ORDERED LISTS.  The binning pass stores (face, min vertex depth) pairs.  A tile whose list is
+//    longer than one staging chunk is bucket-sorted by that depth in shared memory (256 buckets between the
+//    list's min and max, histogram + scan + scatter with shared-memory atomics; exact per-bucket minima).
+//    Faces are then staged front to back, every pixel's top-K fills with near faces first, the existing
+//    exact early reject (a face whose depth lower bound is behind the pixel's K-th layer cannot enter) starts
+//    to fire after a few faces, and the CTA stops as soon as every pixel's K-th layer is nearer than the
+//    lower bound of everything not yet staged.  On the 1M-face sphere at 1024^2 (4,400 candidates per
+//    16x16 tile, 1,500 inside each pixel's blur disc) this walks ~2 chunks instead of ~17.
+//  * COALESCED FRAGMENT STORES.  Layer k of pixel p lives at (p*K + k): a thread-per-pixel store touches
+//    one 4-byte word in each of 32 different sectors (ncu: 468 MB written + 150 MB read-modify-write for
+//    367 MB of output, every warp stalled behind the LSU).  Here the epilogue parks KG layers of the whole
+//    tile in shared memory (bank-conflict-free slot rotation) and the CTA writes them out as contiguous
+//    runs: K*TX consecutive words per tile row.
+//  * Tiles with an empty list stream out the -1 background with the same coalesced pattern.
+#include "render_internal.cuh"
+
+namespace trb {
+
+constexpr int kBuckets = 256;
+
+template <int LT>
+struct KnCfg {
+  static constexpr int TX = 1 << LT, NT = TX * TX;
+  static constexpr int LOGKG = (LT == 4) ? 3 : 4;  // layers parked per output pass: 8 (16x16) / 16 (8x8)
+  static constexpr int KG = 1 << LOGKG;
+  static constexpr int ROT = 5 - LOGKG;             // slot rotation: (kk + (p >> ROT)) & (KG - 1)
+  static constexpr int CAP = (LT == 4) ? 4096 : 2048;  // list entries ordered per super-chunk
+  static constexpr int STAGE_BYTES = NT * 64;       // bb, va, vb (float4) + vc (float2) + zlo + id
+  static constexpr int ORDER_BYTES = CAP * 8;       // face id + depth key
+  static constexpr int OUT_BYTES = NT * KG * 28;    // p2f (8) + zbuf (4) + dists (4) + bary (12)
+  static constexpr int UNION_BYTES =
+      (STAGE_BYTES + ORDER_BYTES > OUT_BYTES) ? STAGE_BYTES + ORDER_BYTES : OUT_BYTES;
+};
+
+// -1 background of one tile, written as contiguous runs (cols*K words per tile row).
+template <int LT, int SHADER>
+__device__ __forceinline__ void fill_tile_kn(const FineArgs& a, int n, int x0, int y0) {
+  constexpr int TX = 1 << LT, NT = TX * TX;
+  const int tid = threadIdx.x;
+  const int K = a.K, H = a.H, W = a.W;
+  const int rows = min(TX, H - y0), cols = min(TX, W - x0);
+  const int run = cols * K;
+  const size_t row_stride = (size_t)W * K;
+  const size_t base0 = ((size_t)(n * H + y0) * W + x0) * K;
+  if ((K & 3) == 0) {
+    // 16-byte stores: every run starts 16-byte aligned and is a multiple of 16 bytes (K % 4 == 0)
+    const int run4 = run >> 2, run2 = run >> 1;
+    const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    for (int idx = tid; idx < rows * run4; idx += NT) {
+      const int ly = idx / run4, i = idx - ly * run4;
+      const size_t g = base0 + ly * row_stride;
+      st_cs(reinterpret_cast<float4*>(a.zbuf + g) + i, m4);
+      st_cs(reinterpret_cast<float4*>(a.dists + g) + i, m4);
+    }
+    for (int idx = tid; idx < rows * run2; idx += NT) {
+      const int ly = idx / run2, i = idx - ly * run2;
+      const size_t g = base0 + ly * row_stride;
+      __stcs(reinterpret_cast<longlong2*>(a.p2f + g) + i, make_longlong2(-1ll, -1ll));
+    }
+    for (int idx = tid; idx < rows * run4 * 3; idx += NT) {
+      const int ly = idx / (run4 * 3), i = idx - ly * (run4 * 3);
+      const size_t g = base0 + ly * row_stride;
+      st_cs(reinterpret_cast<float4*>(a.bary + 3 * g) + i, m4);
+    }
+  } else {
+    for (int idx = tid; idx < rows * run; idx += NT) {
+      const int ly = idx / run, i = idx - ly * run;
+      const size_t g = base0 + ly * row_stride + i;
+      st_cs(a.p2f + g, -1ll);
+      st_cs(a.zbuf + g, -1.0f);
+      st_cs(a.dists + g, -1.0f);
+    }
+    for (int idx = tid; idx < rows * run * 3; idx += NT) {
+      const int ly = idx / (run * 3), i = idx - ly * (run * 3);
+      st_cs(a.bary + 3 * (base0 + ly * row_stride) + i, -1.0f);
+    }
+  }
+  if (SHADER == TRB_SHADER_NONE) return;
+  const int lx = tid & (TX - 1), ly = tid >> LT;
+  if (lx < cols && ly < rows) {
+    const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                              : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+    st_cs(reinterpret_cast<float4*>(a.images) + ((size_t)(n * H + y0 + ly) * W + x0 + lx), bgv);
+  }
+}
+
+template <int LT, int SHADER, int LIGHT>
+__global__ void __launch_bounds__((1 << LT) * (1 << LT))
+render_fine_kn_kernel(const FineArgs a) {
+  using C = KnCfg<LT>;
+  constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT, CAP = C::CAP;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int K = a.K;
+  float* kz = reinterpret_cast<float*>(s_dyn);   // [K][NT] depth of the pixel's k-th nearest candidate
+  int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)K * NT;  // [K][NT] its face
+  unsigned char* s_un = s_dyn + (size_t)K * NT * 8;
+  // (a) list walk: staged faces + the depth-ordered list
+  float4* s_bb = reinterpret_cast<float4*>(s_un);  // xmin, xmax, ymin, ymax (blur inflated; empty if undrawable)
+  float4* s_va = s_bb + NT;                        // x0 y0 z0 x1
+  float4* s_vb = s_va + NT;                        // y1 z1 x2 y2
+  float2* s_vc = reinterpret_cast<float2*>(s_vb + NT);  // z2, area (= edge(v2;v0,v1) + kEps)
+  float* s_zlo = reinterpret_cast<float*>(s_vc + NT);   // lower bound of the depth this face can produce
+  int* s_id = reinterpret_cast<int*>(s_zlo + NT);
+  int* ord_id = reinterpret_cast<int*>(s_un + C::STAGE_BYTES);
+  float* ord_z = reinterpret_cast<float*>(ord_id + CAP);
+  // (b) epilogue: KG layers of the tile parked for the coalesced write-out
+  long long* o_p2f = reinterpret_cast<long long*>(s_un);  // [NT][KG]
+  float* o_z = reinterpret_cast<float*>(o_p2f + NT * KG);
+  float* o_d = o_z + NT * KG;
+  float* o_b = o_d + NT * KG;                              // [NT][KG][3]
+  __shared__ int s_hist[kBuckets];
+  __shared__ unsigned s_bmin[kBuckets];
+  __shared__ float s_bound[kBuckets];  // min depth key over this bucket and every later one
+  __shared__ float s_red[2 * (NT / 32)];
+
+  const int n = blockIdx.z;
+  const trb_view vd = a.views[n];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = a.H, W = a.W;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TX;
+  const int xi = x0 + (tid & (TX - 1));
+  const int yi = y0 + (tid >> LT);
+  const bool live = (xi < W) && (yi < H);
+
+  const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
+  int nlist = a.tile_count[t];
+  if (nlist == 0) {
+    fill_tile_kn<LT, SHADER>(a, n, x0, y0);
+    return;
+  }
+  const int off = a.tile_offset[t];
+  const bool overflow = off < 0;
+  if (overflow) nlist = vd.face_count;
+
+  const float px = pix_to_ndc(W - 1 - xi, W, H);
+  const float py = pix_to_ndc(H - 1 - yi, H, W);
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+  const bool cull = a.flags & TRB_CULL_BACKFACES;
+  const bool hard_edges = a.blur_radius == 0.0f;
+  const float blur = a.blur_radius;
+  // The depth lower bound of a face is a monotone function of its min vertex depth in these modes (see
+  // the staging code below), which is what lets the CTA stop once the remaining keys are behind every
+  // pixel's K-th layer.
+  const bool can_bound = clip || (hard_edges && persp);
+
+  int cnt = 0;
+  for (int sbase = 0; sbase < nlist; sbase += CAP) {
+    const int m = min(CAP, nlist - sbase);
+    const bool ordered = !overflow && can_bound && m > NT;
+    float key_lo = 0.0f, key_scale = 0.0f;
+    if (ordered) {
+      const int2* lst = a.pairs + (size_t)off + sbase;
+      // ---- 1. range of the depth keys
+      float lo = 3.0e38f, hi = -3.0e38f;
+      for (int i = tid; i < m; i += NT) {
+        const float z = __int_as_float(__ldg(&lst[i].y));
+        lo = fminf(lo, z); hi = fmaxf(hi, z);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (lane == 0) { s_red[2 * warp] = lo; s_red[2 * warp + 1] = hi; }
+      for (int i = tid; i < kBuckets; i += NT) { s_hist[i] = 0; s_bmin[i] = 0x7f800000u; }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, s_red[2 * w]); hi = fmaxf(hi, s_red[2 * w + 1]); }
+      key_lo = lo;
+      key_scale = (hi > lo) ? (float)kBuckets / (hi - lo) : 0.0f;
+      // ---- 2. histogram + exact minimum of every bucket (keys are positive: uint order == float order)
+      for (int i = tid; i < m; i += NT) {
+        const float z = __int_as_float(__ldg(&lst[i].y));
+        const int b = min(kBuckets - 1, (int)((z - key_lo) * key_scale));
+        atomicAdd(&s_hist[b], 1);
+        atomicMin(&s_bmin[b], __float_as_uint(z));
+      }
+      __syncthreads();
+      // ---- 3. bucket starts (exclusive scan) and suffix minima, by the first warp
+      if (warp == 0) {
+        constexpr int PER = kBuckets / 32;
+        int c[PER], sum = 0;
+        unsigned mn = 0x7f800000u;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { c[q] = s_hist[lane * PER + q]; sum += c[q]; mn = min(mn, s_bmin[lane * PER + q]); }
+        int incl = sum;
+        unsigned smn = mn;  // min over this lane's buckets and all later lanes'
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+          const unsigned d = __shfl_down_sync(0xffffffffu, smn, o);
+          if (lane + o < 32) smn = min(smn, d);
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { s_hist[lane * PER + q] = run; run += c[q]; }
+        unsigned after = __shfl_down_sync(0xffffffffu, smn, 1);  // min over all later lanes
+        if (lane == 31) after = 0x7f800000u;
+#pragma unroll
+        for (int q = PER - 1; q >= 0; --q) {
+          after = min(after, s_bmin[lane * PER + q]);
+          s_bound[lane * PER + q] = __uint_as_float(after);
+        }
+      }
+      __syncthreads();
+      // ---- 4. scatter into bucket order
+      for (int i = tid; i < m; i += NT) {
+        const int2 e = __ldg(&lst[i]);
+        const float z = __int_as_float(e.y);
+        const int b = min(kBuckets - 1, (int)((z - key_lo) * key_scale));
+        const int pos = atomicAdd(&s_hist[b], 1);
+        ord_id[pos] = e.x; ord_z[pos] = z;
+      }
+      __syncthreads();
+    }
+
+    bool stop = false;
+    for (int base = 0; base < m; base += NT) {
+      // ---- stage up to NT faces of the list
+      const int j = base + tid;
+      float4 bb = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
+      if (j < m) {
+        const int lf = ordered ? ord_id[j] : (overflow ? sbase + j : __ldg(&a.pairs[(size_t)off + sbase + j].x));
+        const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
+        const bool ok = overflow ? face_is_drawable(v, cull, a.z_cull) : true;
+        if (ok) {
+          bb.x = fsub(min3f(v.x0, v.x1, v.x2), a.sqrt_blur); bb.y = fadd(max3f(v.x0, v.x1, v.x2), a.sqrt_blur);
+          bb.z = fsub(min3f(v.y0, v.y1, v.y2), a.sqrt_blur); bb.w = fadd(max3f(v.y0, v.y1, v.y2), a.sqrt_blur);
+        }
+        const float area_e = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+        s_va[tid] = make_float4(v.x0, v.y0, v.z0, v.x1);
+        s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
+        s_vc[tid] = make_float2(v.z2, area_e);
+        s_id[tid] = lf;
+        // Lower bound of the depth any pixel can get from this face (0 = no bound).  With barycentric
+        // clipping the stored weights are a convex combination, so z >= min vertex z up to rounding;
+        // with blur 0 every candidate is strictly inside and the same holds (times area_raw/(area_raw+kEps)
+        // when the weights are not renormalised).  A full top-K list whose K-th depth is already below
+        // this bound cannot change.
+        const float zmin = min3f(v.z0, v.z1, v.z2);
+        float zlo = 0.0f;
+        if (clip) zlo = (!persp || zmin >= 1e-3f) ? zmin * 0.99999f : 0.0f;
+        else if (hard_edges) {
+          if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
+          else zlo = zmin * 0.99999f * (area_e > 0.0f ? fmaxf(0.0f, (area_e - 2e-8f) / area_e) : 1.0f);
+        }
+        s_zlo[tid] = zlo;
+      }
+      s_bb[tid] = bb;
+      __syncthreads();
+      const int mm = min(NT, m - base);
+      if (live) {
+        for (int q = 0; q < mm; ++q) {
+          const float4 b = s_bb[q];
+          if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
+          if (cnt == K && s_zlo[q] > kz[(K - 1) * NT + tid]) continue;
+          const float4 va = s_va[q], vb = s_vb[q];
+          const float2 vc = s_vc[q];
+          FaceXYZ v;
+          v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
+          v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
+          const float area = vc.y;
+          const float e0 = edge_fn(px, py, v.x1, v.y1, v.x2, v.y2);
+          const float e1 = edge_fn(px, py, v.x2, v.y2, v.x0, v.y0);
+          const float e2 = edge_fn(px, py, v.x0, v.y0, v.x1, v.y1);
+          if (hard_edges) {
+            // blur 0: only strictly-inside samples survive, and w_i = e_i / area keeps the sign of
+            // e_i * area exactly, so a non-positive edge is an exact (not approximate) reject.
+            if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                            : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+              continue;
+          }
+          float pz, c0, c1, c2;
+          bool inside;
+          if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, c0, c1, c2, inside)) continue;
+          if (!inside) {
+            if (hard_edges) continue;
+            if (triangle_d2(v, px, py) >= blur) continue;
+          }
+          const int f = s_id[q];
+          if (cnt == K && !cand_less(pz, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
+          int pos = cnt < K ? cnt : K - 1;
+          while (pos > 0 && cand_less(pz, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
+            kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
+            kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
+            --pos;
+          }
+          kz[pos * NT + tid] = pz; kf[pos * NT + tid] = f;
+          if (cnt < K) ++cnt;
+        }
+      }
+      if (ordered && base + NT < m) {
+        // everything not yet staged has a depth key >= bound; stop when that is behind every K-th layer
+        const float zk = ord_z[base + NT];
+        const float bound = s_bound[min(kBuckets - 1, (int)((zk - key_lo) * key_scale))];
+        const float zl = (persp && bound < 1e-3f) ? 0.0f : bound * 0.99999f;
+        const bool done = !live || (cnt == K && zl > kz[(K - 1) * NT + tid]);
+        if (__syncthreads_and(done)) { stop = true; break; }
+      } else {
+        __syncthreads();
+      }
+    }
+    (void)stop;
+  }
+
+  const bool hit = live && cnt > 0;
+  const size_t pix = ((size_t)n * H + yi) * W + xi;
+  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
+
+  ViewParams vp;
+  const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
+  if (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG) vp = load_view_params(a.view_params, n);
+  const float eps = 1e-10f;
+  // layers are sorted front to back, so the softmax's max z_inv belongs to layer 0
+  float alpha = 1.0f, wsum = 0.0f, zmax = eps, zrange = 1.0f;
+  F3 acc = {0, 0, 0};
+  F3 hard_c = {a.bg0, a.bg1, a.bg2};
+  if (SHADER == TRB_SHADER_SOFT_PHONG) {
+    zrange = vp.zfar - vp.znear;
+    if (cnt > 0) zmax = fmaxf(eps, (vp.zfar - kz[tid]) / zrange);
+  }
+  const int rot = tid >> ROT;
+  for (int k0 = 0; k0 < K; k0 += KG) {
+    const int kg = min(KG, K - k0);
+    for (int kk = 0; kk < kg; ++kk) {
+      const int k = k0 + kk;
+      Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+      long long pf = -1;
+      if (k < cnt) {
+        const int f = kf[k * NT + tid];
+        const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
+        eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
+        pf = (long long)vd.p2f_base + f;
+        if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+          alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
+        } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+          if (k == 0) hard_c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+        } else if (SHADER == TRB_SHADER_SOFT_PHONG) {
+          const float prob = sigmoidf(-s.d / a.sigma);
+          alpha *= 1.0f - prob;
+          const float zinv = (vp.zfar - s.z) / zrange;
+          const float w = prob * expf((zinv - zmax) / a.gamma);
+          const F3 c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+          wsum += w;
+          acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
+        }
+      }
+      const int slot = tid * KG + ((kk + rot) & (KG - 1));
+      o_p2f[slot] = pf; o_z[slot] = s.z; o_d[slot] = s.d;
+      o_b[3 * slot] = s.c0; o_b[3 * slot + 1] = s.c1; o_b[3 * slot + 2] = s.c2;
+    }
+    __syncthreads();
+    // ---- the CTA writes the parked layers out as contiguous runs
+    for (int idx = tid; idx < NT * KG; idx += NT) {
+      const int p = idx >> LOGKG;
+      const int kk = ((idx & (KG - 1)) - (p >> ROT)) & (KG - 1);
+      const int gx = x0 + (p & (TX - 1)), gy = y0 + (p >> LT);
+      if (kk < kg && gx < W && gy < H) {
+        const size_t g = ((size_t)(n * H + gy) * W + gx) * K + k0 + kk;
+        st_cs(a.p2f + g, o_p2f[idx]);
+        st_cs(a.zbuf + g, o_z[idx]);
+        st_cs(a.dists + g, o_d[idx]);
+      }
+    }
+    for (int idx = tid; idx < NT * KG * 3; idx += NT) {
+      const int e = idx / 3, c = idx - 3 * e;
+      const int p = e >> LOGKG;
+      const int kk = ((e & (KG - 1)) - (p >> ROT)) & (KG - 1);
+      const int gx = x0 + (p & (TX - 1)), gy = y0 + (p >> LT);
+      if (kk < kg && gx < W && gy < H) {
+        const size_t g = ((size_t)(n * H + gy) * W + gx) * K + k0 + kk;
+        st_cs(a.bary + 3 * g + c, o_b[idx]);
+      }
+    }
+    __syncthreads();
+  }
+  if (SHADER == TRB_SHADER_NONE || !live) return;
+  float4 out;
+  if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+    out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
+  } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt > 0 ? 1.0f : 0.0f);
+  } else {
+    const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+    const float inv = 1.0f / (wsum + delta);
+    out = make_float4((acc.x + delta * a.bg0) * inv, (acc.y + delta * a.bg1) * inv,
+                      (acc.z + delta * a.bg2) * inv, 1.0f - alpha);
+  }
+  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+}
+
+template <int LT>
+static int launch_kn(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
+  using C = KnCfg<LT>;
+  const size_t dyn = (size_t)a.K * C::NT * 8 + C::UNION_BYTES;
+#define TRB_RKN(SH, L)                                                                              \
+  do {                                                                                              \
+    auto kern = render_fine_kn_kernel<LT, SH, L>;                                                   \
+    TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    kern<<<grid, C::NT, dyn, st>>>(a);                                                              \
+  } while (0)
+  if (shader == TRB_SHADER_NONE) TRB_RKN(TRB_SHADER_NONE, 0);
+  else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RKN(TRB_SHADER_SOFT_SILHOUETTE, 0);
+  else if (shader == TRB_SHADER_SOFT_PHONG) {
+    if (light == 0) TRB_RKN(TRB_SHADER_SOFT_PHONG, 0); else if (light == 1) TRB_RKN(TRB_SHADER_SOFT_PHONG, 1);
+    else TRB_RKN(TRB_SHADER_SOFT_PHONG, 2);
+  } else {
+    if (light == 0) TRB_RKN(TRB_SHADER_HARD_PHONG, 0); else if (light == 1) TRB_RKN(TRB_SHADER_HARD_PHONG, 1);
+    else TRB_RKN(TRB_SHADER_HARD_PHONG, 2);
+  }
+#undef TRB_RKN
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
+int launch_render_fine_kn(int shader, int light, int N, cudaStream_t st, const FineArgs& a) {
+  const dim3 grid(a.tg.tiles_x, a.tg.tiles_y, N);
+  if (a.tg.ltx == 4) return launch_kn<4>(shader, light, grid, st, a);
+  return launch_kn<3>(shader, light, grid, st, a);
+}
+
+}  // namespace trb

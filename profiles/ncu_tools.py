@@ -54,8 +54,37 @@ def hot(rep, kernel, launch=0, top=40):
         print(f"{s:7d} {100 * s / max(tot, 1):5.1f}%  ex={ex:9d}  #{k:5d}  {src[:100]}")
 
 
+def lines(rep, kernel, launch=0, top=40):
+    """Stall samples and executed warp instructions aggregated per CUDA source line (file:line)."""
+    out = run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kernel}",
+               "--launch-skip", str(launch), "--launch-count", "1"])
+    agg, fname, hdr = {}, None, None
+    for r in csv.reader(io.StringIO(out)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]; continue
+        if r[0] == "Line No":
+            hdr = r; i_s = hdr.index('Warp Stall Sampling (All Samples)'); i_ex = hdr.index('Instructions Executed'); continue
+        if hdr is None or r[0] == "Function Name":
+            continue
+        try:
+            key = (fname, int(r[0]))
+            s, ex = int(r[i_s] or 0), int(r[i_ex] or 0)
+        except (ValueError, IndexError):
+            continue
+        a = agg.setdefault(key, [0, 0, r[1].strip()])
+        a[0] += s; a[1] += ex
+    tot_s = sum(a[0] for a in agg.values()); tot_ex = sum(a[1] for a in agg.values())
+    print(f"# {kernel}: {tot_s} stall samples, {tot_ex} warp instructions")
+    for (f, ln), (s, ex, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{s:7d} {100 * s / max(tot_s, 1):5.1f}%  ex={ex:11d} {100 * ex / max(tot_ex, 1):5.1f}%  {f}:{ln}  {src[:90]}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "summary":
         summary(sys.argv[2])
+    elif sys.argv[1] == "lines":
+        lines(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
     else:
         hot(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)

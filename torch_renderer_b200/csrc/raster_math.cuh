@@ -16,6 +16,10 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// a / b for a clipped (>= 0) numerator and a positive finite b.  A zero numerator -- one or two of the
+// three clipped barycentrics of every sample outside its face -- sends div.rn.f32 down its ~100-instruction
+// slow path (ncu: 35% of all instructions of the K=8 fine pass); 0 / b is 0 either way.
+__device__ __forceinline__ float div_or_zero(float a, float b) { return a == 0.0f ? 0.0f : __fdiv_rn(a, b); }
 
 // A3: NDC coordinate of pixel-centre i along an axis of S1 pixels (other axis S2).
 __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ bool eval_pixel_face(const FaceXYZ& v, float px, floa
   if (CLIP) {
     c0 = fmaxf(b0, 0.0f); c1 = fmaxf(b1, 0.0f); c2 = fmaxf(b2, 0.0f);
     const float s = fmaxf(fadd(fadd(c0, c1), c2), 1e-5f);
-    c0 = fdiv(c0, s); c1 = fdiv(c1, s); c2 = fdiv(c2, s);
+    c0 = div_or_zero(c0, s); c1 = div_or_zero(c1, s); c2 = div_or_zero(c2, s);
   }
   const float pz = fadd(fadd(fmul(c0, v.z0), fmul(c1, v.z1)), fmul(c2, v.z2));
   if (pz < 0.0f) return false;
@@ -128,7 +132,7 @@ __device__ __forceinline__ bool eval_from_edges(const FaceXYZ& v, float area, fl
   if (clip) {
     c0 = fmaxf(b0, 0.0f); c1 = fmaxf(b1, 0.0f); c2 = fmaxf(b2, 0.0f);
     const float s = fmaxf(fadd(fadd(c0, c1), c2), 1e-5f);
-    c0 = fdiv(c0, s); c1 = fdiv(c1, s); c2 = fdiv(c2, s);
+    c0 = div_or_zero(c0, s); c1 = div_or_zero(c1, s); c2 = div_or_zero(c2, s);
   }
   pz = fadd(fadd(fmul(c0, v.z0), fmul(c1, v.z1)), fmul(c2, v.z2));
   inside = (b0 > 0.0f) && (b1 > 0.0f) && (b2 > 0.0f);
@@ -212,7 +216,7 @@ __device__ __forceinline__ void sample_backward_rt(const FaceXYZ& v, float px, f
     m0 = fmaxf(b0, 0.0f); m1 = fmaxf(b1, 0.0f); m2 = fmaxf(b2, 0.0f);
     ssum = fadd(fadd(m0, m1), m2);
     s = fmaxf(ssum, 1e-5f);
-    c0 = fdiv(m0, s); c1 = fdiv(m1, s); c2 = fdiv(m2, s);
+    c0 = div_or_zero(m0, s); c1 = div_or_zero(m1, s); c2 = div_or_zero(m2, s);
   }
   const bool inside = (b0 > 0.0f) && (b1 > 0.0f) && (b2 > 0.0f);
 #pragma unroll

@@ -738,7 +738,8 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
         i0 = 3 * (int)r; i1 = i0 + 1; i2 = i0 + 2;
       }
       const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
-      sample_backward_rt(v, px, py, persp, clip, gz, gb0, gb1, gb2, gd, gv);
+      // the saved distance is negative (or -0) exactly when the forward found the sample inside
+      sample_backward_fast(v, px, py, persp, clip, signbit(a.dists[s]), gz, gb0, gb1, gb2, gd, gv);
       key = (int)f;
     }
     {

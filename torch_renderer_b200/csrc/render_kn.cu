@@ -276,15 +276,28 @@ render_fine_kn_kernel(const FineArgs a) {
                             : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
               continue;
           }
+          if (clip && cnt == K && s_zlo[q] > 0.0f) {
+            // Sharper, per-pixel form of the bound above: the clipped weights are zero for every vertex
+            // whose edge function has the opposite sign of the area, so the depth is a convex combination
+            // of the remaining vertices only (one or two of them for a sample outside its face -- nearly all
+            // candidates inside a wide blur band).
+            const bool up = area > 0.0f;
+            float zb = 3.0e38f;
+            if (up ? e0 > 0.0f : e0 < 0.0f) zb = v.z0;
+            if (up ? e1 > 0.0f : e1 < 0.0f) zb = fminf(zb, v.z1);
+            if (up ? e2 > 0.0f : e2 < 0.0f) zb = fminf(zb, v.z2);
+            if (zb < 3.0e38f && zb * 0.99999f > kz[(K - 1) * NT + tid]) continue;
+          }
           float pz, c0, c1, c2;
           bool inside;
           if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, c0, c1, c2, inside)) continue;
+          const int f = s_id[q];
+          // the depth is known before the (three more divisions of the) distance: losers leave here
+          if (cnt == K && !cand_less(pz, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
           if (!inside) {
             if (hard_edges) continue;
             if (triangle_d2(v, px, py) >= blur) continue;
           }
-          const int f = s_id[q];
-          if (cnt == K && !cand_less(pz, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
           int pos = cnt < K ? cnt : K - 1;
           while (pos > 0 && cand_less(pz, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
             kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];

@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     headers.append(os.path.join(_ROOT, "include", "trb.h"))
     headers.append(os.path.abspath(__file__))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
-    flags = [f for f in NVCC_FLAGS if not f.endswith("_placeholder")]
+    flags = list(NVCC_FLAGS) + os.environ.get("TRB_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DTRB_KN_STATS (diagnostics)
     if ptxas_info:
         flags += ["-Xptxas", "-v"]
 

@@ -23,18 +23,31 @@ namespace trb {
 
 constexpr int kBuckets = 256;
 
+// Diagnostic counters of the K > 1 walk (build with TRB_EXTRA_NVCC_FLAGS=-DTRB_KN_STATS; read with
+// trb_debug_kn_stats).  Not compiled into the product library.
+#ifdef TRB_KN_STATS
+__device__ unsigned long long g_kn_stats[16];
+#define KN_STAT(i, v) (kn_st[i] += (v))
+#else
+#define KN_STAT(i, v) ((void)0)
+#endif
+
 template <int LT>
 struct KnCfg {
   static constexpr int TX = 1 << LT, NT = TX * TX;
   static constexpr int LOGKG = (LT == 4) ? 3 : 4;  // layers parked per output pass: 8 (16x16) / 16 (8x8)
   static constexpr int KG = 1 << LOGKG;
   static constexpr int ROT = 5 - LOGKG;             // slot rotation: (kk + (p >> ROT)) & (KG - 1)
-  static constexpr int CAP = (LT == 4) ? 4096 : 2048;  // list entries ordered per super-chunk
   static constexpr int STAGE_BYTES = NT * 64;       // bb, va, vb (float4) + vc (float2) + zlo + id
-  static constexpr int ORDER_BYTES = CAP * 8;       // face id + depth key
   static constexpr int OUT_BYTES = NT * KG * 28;    // p2f (8) + zbuf (4) + dists (4) + bary (12)
-  static constexpr int UNION_BYTES =
-      (STAGE_BYTES + ORDER_BYTES > OUT_BYTES) ? STAGE_BYTES + ORDER_BYTES : OUT_BYTES;
+  // list entries ordered per super-chunk (face id + depth key, 8 B each): as many as fit without lowering
+  // the CTAs per SM below what the registers (2 x 256 threads, or 8 x 64) allow anyway
+  __host__ __device__ static constexpr int cap(int K) {
+    return (LT == 4) ? (K <= 12 ? 8192 : (K <= 16 ? 6144 : 4096)) : 2048;
+  }
+  __host__ __device__ static constexpr int union_bytes(int K) {
+    return (STAGE_BYTES + cap(K) * 8 > OUT_BYTES) ? STAGE_BYTES + cap(K) * 8 : OUT_BYTES;
+  }
 };
 
 // -1 background of one tile, written as contiguous runs (cols*K words per tile row).
@@ -93,9 +106,10 @@ template <int LT, int SHADER, int LIGHT>
 __global__ void __launch_bounds__((1 << LT) * (1 << LT))
 render_fine_kn_kernel(const FineArgs a) {
   using C = KnCfg<LT>;
-  constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT, CAP = C::CAP;
+  constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int K = a.K;
+  const int CAP = C::cap(K);
   float* kz = reinterpret_cast<float*>(s_dyn);   // [K][NT] depth of the pixel's k-th nearest candidate
   int* kf = reinterpret_cast<int*>(s_dyn) + (size_t)K * NT;  // [K][NT] its face
   unsigned char* s_un = s_dyn + (size_t)K * NT * 8;
@@ -148,7 +162,12 @@ render_fine_kn_kernel(const FineArgs a) {
   // pixel's K-th layer.
   const bool can_bound = clip || (hard_edges && persp);
 
+#ifdef TRB_KN_STATS
+  unsigned kn_st[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (tid == 0) { KN_STAT(0, 1); KN_STAT(1, nlist); }
+#endif
   int cnt = 0;
+  float kth = 3.0e38f;  // depth of the pixel's K-th layer once the list is full (register copy of kz[K-1])
   for (int sbase = 0; sbase < nlist; sbase += CAP) {
     const int m = min(CAP, nlist - sbase);
     const bool ordered = !overflow && can_bound && m > NT;
@@ -255,11 +274,23 @@ render_fine_kn_kernel(const FineArgs a) {
       s_bb[tid] = bb;
       __syncthreads();
       const int mm = min(NT, m - base);
+      if (tid == 0) KN_STAT(2, mm);
       if (live) {
         for (int q = 0; q < mm; ++q) {
+          KN_STAT(3, 1);
+          // cheapest test first: once the K-th layer has settled it rejects ~90% of a depth-ordered list
+          if (s_zlo[q] > kth) continue;
+          KN_STAT(4, 1);
           const float4 b = s_bb[q];
           if ((px > b.y) || (px < b.x) || (py > b.w) || (py < b.z)) continue;
-          if (cnt == K && s_zlo[q] > kz[(K - 1) * NT + tid]) continue;
+          if (!hard_edges) {
+            // the face lies inside its un-inflated box: a pixel farther than the blur radius from that box
+            // (the rounded corners of the inflated one, 21% of it) fails the distance test by a wide margin
+            const float dx = fmaxf(fmaxf(b.x + a.sqrt_blur - px, px - (b.y - a.sqrt_blur)), 0.0f);
+            const float dy = fmaxf(fmaxf(b.z + a.sqrt_blur - py, py - (b.w - a.sqrt_blur)), 0.0f);
+            if (dx * dx + dy * dy > blur * 1.001f) continue;
+          }
+          KN_STAT(5, 1);
           const float4 va = s_va[q], vb = s_vb[q];
           const float2 vc = s_vc[q];
           FaceXYZ v;
@@ -276,36 +307,73 @@ render_fine_kn_kernel(const FineArgs a) {
                             : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
               continue;
           }
-          if (clip && cnt == K && s_zlo[q] > 0.0f) {
-            // Sharper, per-pixel form of the bound above: the clipped weights are zero for every vertex
-            // whose edge function has the opposite sign of the area, so the depth is a convex combination
-            // of the remaining vertices only (one or two of them for a sample outside its face -- nearly all
-            // candidates inside a wide blur band).
-            const bool up = area > 0.0f;
-            float zb = 3.0e38f;
-            if (up ? e0 > 0.0f : e0 < 0.0f) zb = v.z0;
-            if (up ? e1 > 0.0f : e1 < 0.0f) zb = fminf(zb, v.z1);
-            if (up ? e2 > 0.0f : e2 < 0.0f) zb = fminf(zb, v.z2);
-            if (zb < 3.0e38f && zb * 0.99999f > kz[(K - 1) * NT + tid]) continue;
-          }
-          float pz, c0, c1, c2;
-          bool inside;
-          if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, c0, c1, c2, inside)) continue;
           const int f = s_id[q];
+          float pz;
+          bool inside;
+          bool have_pz = false;
+          // s_zlo > 0 <=> the convex-combination argument of the staging code holds for this face: the
+          // perspective / clip renormalisations cannot hit their epsilon clamps, so the area and the
+          // perspective denominator cancel out of the depth.
+          if (s_zlo[q] > 0.0f && (clip || persp)) {
+            // Clipped barycentrics are zero for every vertex whose edge function has the opposite sign of
+            // the area, so the depth is a convex combination of the remaining vertices only -- one or two
+            // of them for a sample outside its face, i.e. nearly every candidate inside a wide blur band.
+            const bool up = area > 0.0f;
+            const bool p0 = up ? e0 > 0.0f : e0 < 0.0f;
+            const bool p1 = up ? e1 > 0.0f : e1 < 0.0f;
+            const bool p2 = up ? e2 > 0.0f : e2 < 0.0f;
+            const int npos = (int)p0 + (int)p1 + (int)p2;
+            if (clip && npos == 1) {
+              // One positive weight w_i >= w_0 + w_1 + w_2 ~ 1: the clip + renormalise step yields
+              // exactly (1, 0, 0) -- b_i / max(b_i + 0 + 0, 1e-5) with b_i >= 1 -- and the depth is exactly
+              // z_i (1 * z_i + 0 + 0): no division is needed to know it.
+              pz = p0 ? v.z0 : (p1 ? v.z1 : v.z2);
+              inside = false;
+              have_pz = true;
+              KN_STAT(6, 1);
+            } else if (cnt == K && (clip || npos == 3)) {
+              // Approximate depth first.  With a_i = e_i for the positive weights (0 for the clipped ones)
+              //   z = z0 z1 z2 (a0+a1+a2) / (a0 z1 z2 + a1 z0 z2 + a2 z0 z1)   (perspective-correct)
+              //   z = (a0 z0 + a1 z1 + a2 z2) / (a0 + a1 + a2)                 (otherwise)
+              // is what the exact IEEE sequence (9 divisions) computes up to ~2e-6 relative: every term has
+              // the same sign, nothing cancels.  A candidate that loses by more than 1e-4 relative is out.
+              const float a0 = p0 ? e0 : 0.0f, a1 = p1 ? e1 : 0.0f, a2 = p2 ? e2 : 0.0f;
+              float num, den;
+              if (persp) {
+                const float z12 = v.z1 * v.z2, z02 = v.z0 * v.z2, z01 = v.z0 * v.z1;
+                num = v.z0 * z12 * (a0 + a1 + a2);
+                den = a0 * z12 + a1 * z02 + a2 * z01;
+              } else {
+                num = a0 * v.z0 + a1 * v.z1 + a2 * v.z2;
+                den = a0 + a1 + a2;
+              }
+              if (__fdividef(num, den) * 0.9999f > kth) continue;
+              KN_STAT(7, 1);
+            }
+          }
+          if (!have_pz) {
+            KN_STAT(8, 1);
+            float c0, c1, c2;
+            if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, c0, c1, c2, inside)) continue;
+          }
           // the depth is known before the (three more divisions of the) distance: losers leave here
-          if (cnt == K && !cand_less(pz, f, kz[(K - 1) * NT + tid], kf[(K - 1) * NT + tid])) continue;
+          if (cnt == K && !cand_less(pz, f, kth, kf[(K - 1) * NT + tid])) continue;
+          KN_STAT(9, 1);
           if (!inside) {
             if (hard_edges) continue;
             if (triangle_d2(v, px, py) >= blur) continue;
           }
+          KN_STAT(10, 1);
           int pos = cnt < K ? cnt : K - 1;
           while (pos > 0 && cand_less(pz, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
             kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
             kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
             --pos;
+            KN_STAT(11, 1);
           }
           kz[pos * NT + tid] = pz; kf[pos * NT + tid] = f;
           if (cnt < K) ++cnt;
+          if (cnt == K) kth = kz[(K - 1) * NT + tid];
         }
       }
       if (ordered && base + NT < m) {
@@ -313,8 +381,8 @@ render_fine_kn_kernel(const FineArgs a) {
         const float zk = ord_z[base + NT];
         const float bound = s_bound[min(kBuckets - 1, (int)((zk - key_lo) * key_scale))];
         const float zl = (persp && bound < 1e-3f) ? 0.0f : bound * 0.99999f;
-        const bool done = !live || (cnt == K && zl > kz[(K - 1) * NT + tid]);
-        if (__syncthreads_and(done)) { stop = true; break; }
+        const bool done = !live || zl > kth;
+        if (__syncthreads_and(done)) { stop = true; if (tid == 0) KN_STAT(12, 1); break; }
       } else {
         __syncthreads();
       }
@@ -322,6 +390,15 @@ render_fine_kn_kernel(const FineArgs a) {
     (void)stop;
   }
 
+#ifdef TRB_KN_STATS
+  if (live && cnt < K) KN_STAT(13, 1);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    unsigned v = kn_st[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(&g_kn_stats[i], (unsigned long long)v);
+  }
+#endif
   const bool hit = live && cnt > 0;
   const size_t pix = ((size_t)n * H + yi) * W + xi;
   append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
@@ -411,7 +488,7 @@ render_fine_kn_kernel(const FineArgs a) {
 template <int LT>
 static int launch_kn(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
   using C = KnCfg<LT>;
-  const size_t dyn = (size_t)a.K * C::NT * 8 + C::UNION_BYTES;
+  const size_t dyn = (size_t)a.K * C::NT * 8 + C::union_bytes(a.K);
 #define TRB_RKN(SH, L)                                                                              \
   do {                                                                                              \
     auto kern = render_fine_kn_kernel<LT, SH, L>;                                                   \
@@ -439,3 +516,13 @@ int launch_render_fine_kn(int shader, int light, int N, cudaStream_t st, const F
 }
 
 }  // namespace trb
+
+#ifdef TRB_KN_STATS
+// Copies the 16 walk counters to `host_out` and clears them (diagnostic builds only; synchronises).
+extern "C" int trb_debug_kn_stats(unsigned long long* host_out) {
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(host_out, trb::g_kn_stats, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  if (cudaMemcpyToSymbol(trb::g_kn_stats, zero, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  return TRB_OK;
+}
+#endif

@@ -212,3 +212,23 @@ def test_c5_scaled_down_exact_and_full_size_properties():
     assert torch.isfinite(images).all() and images.min() >= 0 and images[..., :3].max() <= 1.0 + 1e-4
     (images ** 2).mean().backward()
     assert torch.isfinite(vd.grad).all() and vd.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("nlat,nlon,size,K", [(101, 200, 64, 50), (246, 245, 96, 8)])
+def test_dense_tile_lists_ordered_in_super_chunks(nlat, nlon, size, K):
+    """Tile lists longer than one ordered super-chunk of the K > 1 fine kernel (2,048 entries for 8x8 tiles,
+    8,192 for 16x16): 40k faces on a 64^2 image at K=50 and 120k faces on a 96^2 image at K=8, soft blur with
+    clipped, perspective-correct barycentrics.  Every early-exit path (depth-bucket order, CTA stop, one-positive-
+    weight shortcut, approximate-depth pre-reject) must leave the result bit-identical to the oracle's full walk."""
+    trb = _trb()
+    v, f = _grid_sphere(nlat, nlon, seed=4)
+    eye = 2.7 * torch.nn.functional.normalize(torch.tensor([[0.5, -0.4, -0.7]]), dim=1)
+    R, T = trb.look_at_view_transform(eye=eye)
+    mesh = trb.Meshes([v.to(DEV)], [f.to(DEV)])
+    cams = trb.FoVPerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV))
+    rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=size, blur_radius=BLUR, faces_per_pixel=K))
+    frag = rast(mesh)
+    ndc = rast.transform(mesh).cpu().reshape(1, -1, 3)
+    want = oracle_rasterize(ndc, f, (size, size), BLUR, K, True, True)
+    _check_fragments(frag, want)
+    assert (want[0][..., K - 1] >= 0).sum() > 500

@@ -40,13 +40,12 @@ struct KnCfg {
   static constexpr int ROT = 5 - LOGKG;             // slot rotation: (kk + (p >> ROT)) & (KG - 1)
   static constexpr int STAGE_BYTES = NT * 64;       // bb, va, vb (float4) + vc (float2) + zlo + id
   static constexpr int OUT_BYTES = NT * KG * 28;    // p2f (8) + zbuf (4) + dists (4) + bary (12)
-  // list entries ordered per super-chunk (face id + depth key, 8 B each): as many as fit without lowering
-  // the CTAs per SM below what the registers (2 x 256 threads, or 8 x 64) allow anyway
+  // list entries ordered per super-chunk (face ids, 4 B each)
   __host__ __device__ static constexpr int cap(int K) {
-    return (LT == 4) ? (K <= 12 ? 8192 : (K <= 16 ? 6144 : 4096)) : 2048;
+    return (LT == 4) ? (K <= 12 ? 8192 : 4096) : 2048;
   }
   __host__ __device__ static constexpr int union_bytes(int K) {
-    return (STAGE_BYTES + cap(K) * 8 > OUT_BYTES) ? STAGE_BYTES + cap(K) * 8 : OUT_BYTES;
+    return (STAGE_BYTES + cap(K) * 4 > OUT_BYTES) ? STAGE_BYTES + cap(K) * 4 : OUT_BYTES;
   }
 };
 
@@ -103,7 +102,7 @@ __device__ __forceinline__ void fill_tile_kn(const FineArgs& a, int n, int x0, i
 }
 
 template <int LT, int SHADER, int LIGHT>
-__global__ void __launch_bounds__((1 << LT) * (1 << LT))
+__global__ void __launch_bounds__((1 << LT) * (1 << LT), LT == 4 ? 3 : 8)
 render_fine_kn_kernel(const FineArgs a) {
   using C = KnCfg<LT>;
   constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
@@ -120,8 +119,7 @@ render_fine_kn_kernel(const FineArgs a) {
   float2* s_vc = reinterpret_cast<float2*>(s_vb + NT);  // z2, area (= edge(v2;v0,v1) + kEps)
   float* s_zlo = reinterpret_cast<float*>(s_vc + NT);   // lower bound of the depth this face can produce
   int* s_id = reinterpret_cast<int*>(s_zlo + NT);
-  int* ord_id = reinterpret_cast<int*>(s_un + C::STAGE_BYTES);
-  float* ord_z = reinterpret_cast<float*>(ord_id + CAP);
+  int* ord_id = reinterpret_cast<int*>(s_un + C::STAGE_BYTES);  // [CAP] face ids in depth-bucket order
   // (b) epilogue: KG layers of the tile parked for the coalesced write-out
   long long* o_p2f = reinterpret_cast<long long*>(s_un);  // [NT][KG]
   float* o_z = reinterpret_cast<float*>(o_p2f + NT * KG);
@@ -131,6 +129,7 @@ render_fine_kn_kernel(const FineArgs a) {
   __shared__ unsigned s_bmin[kBuckets];
   __shared__ float s_bound[kBuckets];  // min depth key over this bucket and every later one
   __shared__ float s_red[2 * (NT / 32)];
+  __shared__ unsigned char s_chunk_bucket[8192 / NT + 1];  // bucket of the first entry of every staging chunk
 
   const int n = blockIdx.z;
   const trb_view vd = a.views[n];
@@ -171,8 +170,8 @@ render_fine_kn_kernel(const FineArgs a) {
   for (int sbase = 0; sbase < nlist; sbase += CAP) {
     const int m = min(CAP, nlist - sbase);
     const bool ordered = !overflow && can_bound && m > NT;
-    float key_lo = 0.0f, key_scale = 0.0f;
     if (ordered) {
+      float key_lo, key_scale;
       const int2* lst = a.pairs + (size_t)off + sbase;
       // ---- 1. range of the depth keys
       float lo = 3.0e38f, hi = -3.0e38f;
@@ -234,7 +233,8 @@ render_fine_kn_kernel(const FineArgs a) {
         const float z = __int_as_float(e.y);
         const int b = min(kBuckets - 1, (int)((z - key_lo) * key_scale));
         const int pos = atomicAdd(&s_hist[b], 1);
-        ord_id[pos] = e.x; ord_z[pos] = z;
+        ord_id[pos] = e.x;
+        if ((pos & (NT - 1)) == 0) s_chunk_bucket[pos / NT] = (unsigned char)b;
       }
       __syncthreads();
     }
@@ -378,8 +378,7 @@ render_fine_kn_kernel(const FineArgs a) {
       }
       if (ordered && base + NT < m) {
         // everything not yet staged has a depth key >= bound; stop when that is behind every K-th layer
-        const float zk = ord_z[base + NT];
-        const float bound = s_bound[min(kBuckets - 1, (int)((zk - key_lo) * key_scale))];
+        const float bound = s_bound[s_chunk_bucket[base / NT + 1]];
         const float zl = (persp && bound < 1e-3f) ? 0.0f : bound * 0.99999f;
         const bool done = !live || zl > kth;
         if (__syncthreads_and(done)) { stop = true; if (tid == 0) KN_STAT(12, 1); break; }

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 1
+#define TRB_ABI_VERSION 2
 #define TRB_MAX_FACES_PER_PIXEL 150
 
 typedef void* trb_stream_t; /* cudaStream_t */
@@ -222,6 +222,9 @@ typedef struct trb_render_config {
   int64_t num_faces;             /* rows of faces */
   int64_t num_ndc_verts;         /* rows of verts_ndc = sum_n vert_count */
   int64_t pair_capacity;
+  int32_t scratch_is_zeroed;     /* backward: the caller already zeroed `scratch` (e.g. it lives in the same
+                                    zero-filled allocation as the gradient outputs): skip the memset */
+  int32_t reserved;
 } trb_render_config;
 
 /* workspace_bytes: scratch for the forward; hit_pixels_len: length of hit_pixels (int32: a count
@@ -241,7 +244,7 @@ int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        trb_stream_t stream);
 /* grad_images may be NULL (shader NONE); grad_zbuf / grad_bary / grad_dists are optional extra
  * upstream gradients on the Fragments.  Every grad_* output is ACCUMULATED into (caller zeroes;
- * any may be NULL); `scratch` is zeroed by the call. */
+ * any may be NULL); `scratch` is zeroed by the call unless cfg->scratch_is_zeroed. */
 int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views,
                         const float* verts_world, const int32_t* faces, const float* vert_colors,
                         const float* R, const float* T, const float* proj, const float* view_params,

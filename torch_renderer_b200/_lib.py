@@ -38,7 +38,8 @@ class RenderConfig(ctypes.Structure):
                 ("max_vert_count", _c.c_int32), ("camera_center_from_rt", _c.c_int32),
                 ("want_light_grad", _c.c_int32), ("z_clip_value", _f),
                 ("num_world_verts", _c.c_int64), ("num_faces", _c.c_int64),
-                ("num_ndc_verts", _c.c_int64), ("pair_capacity", _c.c_int64)]
+                ("num_ndc_verts", _c.c_int64), ("pair_capacity", _c.c_int64),
+                ("scratch_is_zeroed", _c.c_int32), ("reserved", _c.c_int32)]
 
 
 # name -> argtypes; every function returns int (trb_status) unless noted
@@ -93,7 +94,7 @@ def lib() -> ctypes.CDLL:
             fn.restype = _c.c_int
         handle.trb_status_string.argtypes = [_i]
         handle.trb_status_string.restype = _c.c_char_p
-        if handle.trb_abi_version() != 1:
+        if handle.trb_abi_version() != 2:
             raise TrbLibraryError("libtrb.so ABI version mismatch; rebuild it")
         for which, (name, size) in enumerate((("trb_view", 32), ("trb_shade_config", _c.sizeof(ShadeConfig)),
                                               ("trb_render_config", _c.sizeof(RenderConfig)))):

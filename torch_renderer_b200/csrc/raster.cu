@@ -12,16 +12,12 @@
 //    shared memory otherwise -- and barycentrics/distances are recomputed for the K survivors;
 //  * ties are broken by (z, face index), so the result does not depend on list order.
 #include "render_internal.cuh"
+#include "stages.cuh"
 
 namespace trb {
 
 // ------------------------------------------------------------------------------------------
-// Binning.  One thread per (view, face): count (FILL=false) or write (FILL=true) the face into
-// every tile its blur-inflated bounding box can touch.  Neighbouring faces of a mesh mostly land in
-// the same tiles, so the lanes of a warp that address the same tile in the same step are grouped with
-// match.any and issue ONE atomic per group (the same-address atomics of the naive version serialised
-// in the L2: 2.2 ms for 4 x 1M faces).  A pair is (face, bits of the face's min vertex depth); the
-// K > 1 fine pass orders its tile lists by that depth.
+// Binning (bodies in stages.cuh): count -> allocate -> fill.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
@@ -30,88 +26,14 @@ bin_faces_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
                  const int* __restrict__ tile_offset, int2* __restrict__ pairs, float z_cull) {
   const int n = blockIdx.y;
   const trb_view vd = views[n];
-  const int lf = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int tx0 = 0, ty0 = 0, nx = 0, ny = 0;
-  float zmin = 0.0f;
-  if (lf < vd.face_count) {
-    const FaceXYZ v = load_face(verts, faces, vd, lf);
-    if (face_is_drawable(v, cull, z_cull)) {
-      const float xmin = min3f(v.x0, v.x1, v.x2) - sqrt_blur, xmax = max3f(v.x0, v.x1, v.x2) + sqrt_blur;
-      const float ymin = min3f(v.y0, v.y1, v.y2) - sqrt_blur, ymax = max3f(v.y0, v.y1, v.y2) + sqrt_blur;
-      int px0, px1, py0, py1;
-      pixel_range(xmin, xmax, W, H, px0, px1);
-      pixel_range(ymin, ymax, H, W, py0, py1);
-      if (px0 <= px1 && py0 <= py1) {
-        tx0 = px0 >> tg.ltx; ty0 = py0 >> tg.lty;
-        nx = (px1 >> tg.ltx) - tx0 + 1; ny = (py1 >> tg.lty) - ty0 + 1;
-        zmin = min3f(v.z0, v.z1, v.z2);
-      }
-    }
-  }
-  const int cnt = nx * ny;
-  const int steps = __reduce_max_sync(0xffffffffu, cnt);  // warp-uniform trip count
-  const int tbase = n * tg.tiles_x * tg.tiles_y;
-  int ix = 0, iy = 0;
-  for (int i = 0; i < steps; ++i) {
-    const bool have = i < cnt;
-    // lanes without a tile in this step get distinct negative keys: singleton groups, skipped
-    const int t = have ? tbase + (ty0 + iy) * tg.tiles_x + tx0 + ix : -1 - lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, t);
-    if (have) {
-      const int leader = __ffs(peers) - 1;
-      const int npeers = __popc(peers);
-      if (!FILL) {
-        if (lane == leader) atomicAdd(tile_count + t, npeers);
-      } else {
-        const int off = tile_offset[t];
-        int base = 0;
-        if (lane == leader && off >= 0) base = atomicAdd(tile_fill + t, npeers);
-        base = __shfl_sync(peers, base, leader);
-        if (off >= 0)
-          pairs[(size_t)off + base + __popc(peers & ((1u << lane) - 1u))] = make_int2(lf, __float_as_int(zmin));
-      }
-      if (++ix == nx) { ix = 0; ++iy; }
-    }
-  }
+  bin_face<FILL>(verts, faces, vd, n, blockIdx.x * blockDim.x + threadIdx.x, H, W, tg, sqrt_blur, cull, tile_count,
+                 tile_fill, tile_offset, pairs, z_cull);
 }
 
-// Hands every non-empty tile a contiguous slice of `pairs` (order between tiles is irrelevant).
 __global__ void __launch_bounds__(256)
 alloc_tiles_kernel(const int* __restrict__ tile_count, int* __restrict__ tile_offset, int ntiles,
                    int* __restrict__ header, long long pair_capacity, int* __restrict__ busy_list) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = t < ntiles ? tile_count[t] : 0;
-  // warp-aggregated reservation
-  const int lane = threadIdx.x & 31;
-  int incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += u;
-  }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  int base = 0;
-  if (lane == 31 && warp_total > 0) {
-    // header[0..1] is a 64-bit cursor so that the needed total is exact even past capacity
-    base = (int)min((unsigned long long)0x7fffffff,
-                    atomicAdd((unsigned long long*)header, (unsigned long long)warp_total));
-  }
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (t < ntiles) {
-    const long long off = (long long)base + (incl - c);
-    const bool fits = off + c <= pair_capacity;
-    tile_offset[t] = (c == 0) ? 0 : (fits ? (int)off : -1);
-    if (c > 0 && !fits) atomicAdd(header + 2, 1);
-  }
-  // compact list of non-empty tiles: the fused fine pass spreads them over its CTAs
-  const unsigned busy = __ballot_sync(0xffffffffu, c > 0);
-  if (busy) {
-    int bbase = 0;
-    if (lane == 0) bbase = atomicAdd(header + 4, __popc(busy));
-    bbase = __shfl_sync(0xffffffffu, bbase, 0);
-    if (c > 0) busy_list[bbase + __popc(busy & ((1u << lane) - 1u))] = t;
-  }
+  alloc_tile(tile_count, tile_offset, ntiles, header, pair_capacity, busy_list, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void write_stats_kernel(const int* __restrict__ header, long long pair_capacity,

@@ -13,59 +13,9 @@
 // atomics -> camera-centre backward -> NDC->world backward -> vertex-normal backward (2).  Tiles the
 // forward leaves a compact list of covered pixels (`hit_pixels`); the backward visits only those.
 #include "render_internal.cuh"
+#include "stages.cuh"
 
 namespace trb {
-
-// ---- 3x3 inverse (adjugate) ------------------------------------------------------------------
-__device__ __forceinline__ void inv3(const float* r, float a[9]) {
-  const float c00 = r[4] * r[8] - r[5] * r[7], c01 = r[5] * r[6] - r[3] * r[8], c02 = r[3] * r[7] - r[4] * r[6];
-  const float det = r[0] * c00 + r[1] * c01 + r[2] * c02;
-  const float id = 1.0f / det;
-  a[0] = c00 * id; a[1] = (r[2] * r[7] - r[1] * r[8]) * id; a[2] = (r[1] * r[5] - r[2] * r[4]) * id;
-  a[3] = c01 * id; a[4] = (r[0] * r[8] - r[2] * r[6]) * id; a[5] = (r[2] * r[3] - r[0] * r[5]) * id;
-  a[6] = c02 * id; a[7] = (r[1] * r[6] - r[0] * r[7]) * id; a[8] = (r[0] * r[4] - r[1] * r[3]) * id;
-}
-
-// camera centre C = -T * inv(R)  (row vectors)
-__global__ void camera_center_kernel(const float* __restrict__ R, const float* __restrict__ T,
-                                     float* __restrict__ vp, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float a[9];
-  inv3(R + 9 * (size_t)n, a);
-  const float* t = T + 3 * (size_t)n;
-  float* o = vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
-  o[0] = -(t[0] * a[0] + t[1] * a[3] + t[2] * a[6]);
-  o[1] = -(t[0] * a[1] + t[1] * a[4] + t[2] * a[7]);
-  o[2] = -(t[0] * a[2] + t[1] * a[5] + t[2] * a[8]);
-}
-
-// dC = -dT A - C dR A   =>   gT_i = -sum_k gC_k A_ik ;  gR_ij = -C_i * sum_k A_jk gC_k
-__global__ void camera_center_backward_kernel(const float* __restrict__ R, const float* __restrict__ vp,
-                                              const float* __restrict__ g_vp, float* __restrict__ gR,
-                                              float* __restrict__ gT, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float a[9];
-  inv3(R + 9 * (size_t)n, a);
-  const float* c = vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
-  const float* g = g_vp + (size_t)n * TRB_VIEW_PARAM_STRIDE + 13;
-  float ag[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) ag[j] = a[3 * j] * g[0] + a[3 * j + 1] * g[1] + a[3 * j + 2] * g[2];
-  if (gT) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) gT[3 * (size_t)n + i] -= ag[i];
-  }
-  if (gR) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) gR[9 * (size_t)n + 3 * i + j] -= c[i] * ag[j];
-  }
-}
-
-
 
 // ---- fused fine pass, faces_per_pixel == 1 ---------------------------------------------------------
 // The meshes this path sees most (cow at 512^2: ~3.5 px per face, ~200 faces per 16x16 tile) make a
@@ -121,6 +71,7 @@ constexpr int kStrip = 8;
 template <int SHADER, int LIGHT>
 __global__ void __launch_bounds__(256)
 render_fine_k1_kernel(const FineArgs a) {
+  pdl_wait();
   const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * kStrip;
   const int* counts = a.tile_count + (size_t)(n * a.tg.tiles_y + tby) * a.tg.tiles_x;
   int cnt[kStrip];
@@ -389,6 +340,7 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
 template <bool K1, int SHADER, int LIGHT>
 __global__ void __launch_bounds__(128, K1 ? 4 : 1)
 render_backward_kernel(const BwdArgs a) {
+  pdl_wait();
   extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
   const int count = a.hit_pixels[0];
   const int count_up = (count + 31) & ~31;
@@ -749,39 +701,6 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   }
 }
 
-// Per-vertex epilogue of the fused backward: unpacks the float4 accumulators.  grad_verts += pixel-
-// coordinate path, grad_colors += colour path, and the gradient of the unit vertex normals is pushed
-// through the normalisation (raw / max(|raw|, 1e-6)) into g_raw for the per-face scatter that follows.
-__global__ void __launch_bounds__(256)
-finalize_vertex_grads_kernel(long long V, const float* __restrict__ raw, const float4* __restrict__ g_norm4,
-                             const float4* __restrict__ g_world4, const float4* __restrict__ g_col4,
-                             float* __restrict__ g_raw, float* __restrict__ grad_verts,
-                             float* __restrict__ grad_colors) {
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  if (g_world4 && grad_verts) {
-    const float4 g = g_world4[v];
-    grad_verts[3 * v] += g.x; grad_verts[3 * v + 1] += g.y; grad_verts[3 * v + 2] += g.z;
-  }
-  if (g_col4 && grad_colors) {
-    const float4 g = g_col4[v];
-    grad_colors[3 * v] += g.x; grad_colors[3 * v + 1] += g.y; grad_colors[3 * v + 2] += g.z;
-  }
-  if (g_norm4 && g_raw) {
-    const float4 g = g_norm4[v];
-    const float x = raw[3 * v], y = raw[3 * v + 1], z = raw[3 * v + 2];
-    const float len = sqrtf(x * x + y * y + z * z);
-    if (len > 1e-6f) {
-      const float inv = 1.0f / len;
-      const float ux = x * inv, uy = y * inv, uz = z * inv;
-      const float d = ux * g.x + uy * g.y + uz * g.z;
-      g_raw[3 * v] = (g.x - ux * d) * inv; g_raw[3 * v + 1] = (g.y - uy * d) * inv; g_raw[3 * v + 2] = (g.z - uz * d) * inv;
-    } else {
-      g_raw[3 * v] = g.x * 1e6f; g_raw[3 * v + 1] = g.y * 1e6f; g_raw[3 * v + 2] = g.z * 1e6f;
-    }
-  }
-}
-
 // ---- host side ----------------------------------------------------------------------------------
 static int check_render_cfg(const trb_render_config* c) {
   if (!c) return TRB_ERR_BAD_ARG;
@@ -804,7 +723,7 @@ static inline bool is_phong(int shader) {
 }
 
 static int launch_render_fine_k1(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
-#define TRB_RF1(SH, L) render_fine_k1_kernel<SH, L><<<grid, 256, 0, st>>>(a)
+#define TRB_RF1(SH, L) TRB_CUDA_TRY(launch_pdl(render_fine_k1_kernel<SH, L>, grid, dim3(256), 0, st, a))
   if (shader == TRB_SHADER_NONE) TRB_RF1(TRB_SHADER_NONE, 0);
   else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RF1(TRB_SHADER_SOFT_SILHOUETTE, 0);
   else if (shader == TRB_SHADER_SOFT_PHONG) {
@@ -827,7 +746,7 @@ static int launch_render_backward(int shader, int light, dim3 grid, int nt, size
     auto kern = render_backward_kernel<K1, SH, L>;                                                \
     if (dyn > 0)                                                                                  \
       TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-    kern<<<grid, nt, dyn, st>>>(a);                                                               \
+    TRB_CUDA_TRY(launch_pdl(kern, grid, dim3(nt), dyn, st, a));                                   \
   } while (0)
   if (shader == TRB_SHADER_NONE) TRB_RB(TRB_SHADER_NONE, 0);
   else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RB(TRB_SHADER_SOFT_SILHOUETTE, 0);
@@ -900,23 +819,12 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (is_phong(sc.shader) && sc.light_kind != TRB_LIGHT_AMBIENT) {
-    rc = trb_vertex_normals_forward(verts_world, faces, cfg->num_world_verts, cfg->num_faces, normals_raw,
-                                    normals, device, stream);
-    if (rc != TRB_OK) return rc;
-    if (cfg->camera_center_from_rt) {
-      camera_center_kernel<<<ceil_div(N, 128), 128, 0, st>>>(R, T, view_params, N);
-      TRB_LAUNCH_CHECK();
-    }
-  }
-  rc = trb_transform_forward(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective,
-                             verts_ndc, device, stream);
+  const bool lit = is_phong(sc.shader) && sc.light_kind != TRB_LIGHT_AMBIENT;
+  rc = run_forward_stages(cfg, views, verts_world, faces, R, T, proj, view_params, verts_ndc, normals_raw, normals,
+                          tile_hit, workspace, tg, ws, lit, st);
   if (rc != TRB_OK) return rc;
   const float sqrt_blur = sqrtf(cfg->blur_radius);
   const float z_cull = fmaxf(cfg->z_clip_value, 0.0f);
-  rc = run_binning(verts_ndc, faces, views, N, cfg->max_face_count, H, W, tg, ws, workspace, sqrt_blur,
-                   cfg->raster_flags & TRB_CULL_BACKFACES, (long long)cfg->pair_capacity, st, z_cull);
-  if (rc != TRB_OK) return rc;
 
   unsigned char* wsb = (unsigned char*)workspace;
   FineArgs a;
@@ -931,7 +839,6 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
-  TRB_CUDA_TRY(cudaMemsetAsync(tile_hit, 0, sizeof(int), st));
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
   rc = launch_render_fine(sc.shader, sc.light_kind, N, st, a);
   if (rc != TRB_OK) return rc;
@@ -969,12 +876,11 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_ndc = (size_t)cfg->num_ndc_verts, V = (size_t)cfg->num_world_verts;
-  TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (4 * n_ndc + 15 * V) * sizeof(float), st));
+  if (!cfg->scratch_is_zeroed) TRB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (4 * n_ndc + 15 * V) * sizeof(float), st));
   float4* g_ndc4 = reinterpret_cast<float4*>(scratch);
   float4* g_world4 = g_ndc4 + n_ndc;
   float4* g_col4 = g_world4 + V;
   float4* g_norm4 = g_col4 + V;
-  float* g_raw = reinterpret_cast<float*>(g_norm4 + V);
   const bool geom = grad_verts_world || grad_R || grad_T || grad_proj;
   // the camera centre (when derived from R, T) feeds grad_R / grad_T through grad_view_params
   float* g_vp = grad_view_params;
@@ -1006,26 +912,11 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   if (rc != TRB_OK) return rc;
   if (g_dbg_events[3]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[3], st));
 
-  if (cam_chain) {
-    camera_center_backward_kernel<<<ceil_div(N, 128), 128, 0, st>>>(R, view_params, g_vp, grad_R, grad_T, N);
-    TRB_LAUNCH_CHECK();
-  }
-  if (geom) {
-    rc = transform_backward_strided(verts_world, R, T, proj, views, N, cfg->max_vert_count, cfg->perspective,
-                                    reinterpret_cast<const float*>(g_ndc4), 4, grad_verts_world, grad_R, grad_T,
-                                    grad_proj, device, stream);
-    if (rc != TRB_OK) return rc;
-  }
   const bool normals_chain = lit && grad_verts_world;
-  if (a.g_verts_world || a.g_colors || normals_chain) {
-    finalize_vertex_grads_kernel<<<(unsigned)ceil_div64((long long)V, 256), 256, 0, st>>>(
-        (long long)V, normals_raw, normals_chain ? g_norm4 : nullptr, a.g_verts_world ? g_world4 : nullptr,
-        a.g_colors ? g_col4 : nullptr, g_raw, grad_verts_world, grad_vert_colors);
-    TRB_LAUNCH_CHECK();
-  }
-  if (normals_chain) {
-    rc = face_normals_backward(verts_world, faces, cfg->num_faces, g_raw, grad_verts_world, st);
-    if (rc != TRB_OK) return rc;
-  }
+  rc = run_backward_post(cfg, views, verts_world, faces, R, T, proj, view_params, g_vp, normals_raw, g_ndc4,
+                         a.g_verts_world ? g_world4 : nullptr, a.g_colors ? g_col4 : nullptr,
+                         normals_chain ? g_norm4 : nullptr, grad_verts_world, grad_vert_colors, grad_R, grad_T,
+                         grad_proj, geom, cam_chain, normals_chain, st);
+  if (rc != TRB_OK) return rc;
   return TRB_OK;
 }

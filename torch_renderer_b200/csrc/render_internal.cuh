@@ -57,6 +57,19 @@ __device__ __forceinline__ F3 shade_sample(const ShadeIn& in, const trb_view& vd
   return phong_color<LIGHT>(vp, P, nr, tex, lit);
 }
 
+// The small stages around the fine pass, packed by block role (render_stages.cu).
+int run_forward_stages(const trb_render_config* cfg, const trb_view* views, const float* verts_world,
+                       const int32_t* faces, const float* R, const float* T, const float* proj,
+                       float* view_params, float* verts_ndc, float* normals_raw, float* normals,
+                       int32_t* hit_pixels, void* workspace, const TileGrid& tg, const WsLayout& ws, bool lit,
+                       cudaStream_t st);
+int run_backward_post(const trb_render_config* cfg, const trb_view* views, const float* verts_world,
+                      const int32_t* faces, const float* R, const float* T, const float* proj,
+                      const float* view_params, const float* g_view_params, const float* normals_raw,
+                      const float4* g_ndc4, const float4* g_world4, const float4* g_col4, const float4* g_norm4,
+                      float* grad_verts, float* grad_colors, float* grad_R, float* grad_T, float* grad_proj,
+                      bool geom, bool cam_chain, bool normals_chain, cudaStream_t st);
+
 // Fine pass of one batch: the K == 1 strip kernel (render.cu) or the K > 1 kernel (render_kn.cu).
 int launch_render_fine(int shader, int light, int N, cudaStream_t st, const FineArgs& a);
 // faces_per_pixel > 1 (render_kn.cu)

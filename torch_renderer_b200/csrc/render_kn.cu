@@ -18,6 +18,7 @@
 //    runs: K*TX consecutive words per tile row.
 //  * Tiles with an empty list stream out the -1 background with the same coalesced pattern.
 #include "render_internal.cuh"
+#include "stages.cuh"
 
 namespace trb {
 
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__((1 << LT) * (1 << LT), LT == 4 ? 3 : 8)
 render_fine_kn_kernel(const FineArgs a) {
   using C = KnCfg<LT>;
   constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int K = a.K;
   const int CAP = C::cap(K);
@@ -492,7 +494,7 @@ static int launch_kn(int shader, int light, dim3 grid, cudaStream_t st, const Fi
   do {                                                                                              \
     auto kern = render_fine_kn_kernel<LT, SH, L>;                                                   \
     TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-    kern<<<grid, C::NT, dyn, st>>>(a);                                                              \
+    TRB_CUDA_TRY(launch_pdl(kern, grid, dim3(C::NT), dyn, st, a));                                  \
   } while (0)
   if (shader == TRB_SHADER_NONE) TRB_RKN(TRB_SHADER_NONE, 0);
   else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RKN(TRB_SHADER_SOFT_SILHOUETTE, 0);

@@ -11,8 +11,19 @@ int transform_backward_strided(const float* verts_world, const float* R, const f
                                const float* grad_verts_ndc, int grad_stride, float* grad_verts_world,
                                float* grad_R, float* grad_T, float* grad_proj, int device, trb_stream_t stream);
 
-// Second half of trb_vertex_normals_backward: grad of the raw (un-normalised) normals -> grad_verts.
-int face_normals_backward(const float* verts, const int32_t* faces, int64_t F, const float* grad_raw,
-                          float* grad_verts, cudaStream_t st);
+// Launch with the programmatic-serialisation attribute (programmatic dependent launch): the kernel may be
+// scheduled while its predecessor in the stream drains; it must begin with pdl_wait() (stages.cuh).  Captured
+// into a CUDA graph this becomes a programmatic edge.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 }  // namespace trb

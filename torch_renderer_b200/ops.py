@@ -459,8 +459,7 @@ class _RenderFn(torch.autograd.Function):
                 _ptr(proj), _ptr(vp), _ptr(verts_ndc), _ptr(normals_raw), _ptr(normals), _ptr(p2f), _ptr(zbuf),
                 _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), _ptr(tile_hit),
                 _ptr(ws), ws_bytes.value, _ptr(stats), dev.index, _stream(dev)), "render")
-        lit = phong and spec["light_kind"] != _lib.LIGHT_AMBIENT
-        _bump(7 + (3 if lit else 0))
+        _bump(5 + (1 if want_stats else 0))  # prep, count, alloc, fill, fine (+ stats)
         if want_stats:
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
             host_stats.copy_(stats, non_blocking=True)
@@ -486,11 +485,13 @@ class _RenderFn(torch.autograd.Function):
         if shader != _lib.SHADER_NONE and g_images is None:
             g_images = torch.zeros((N, cfg.shade.H, cfg.shade.W, 4), dtype=torch.float32, device=dev)
         # one zero-filled buffer for every accumulated gradient
-        sizes = [V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE]
+        # ... and for the kernel's float4 accumulators (16-byte aligned: the scratch block comes first)
+        n_scratch = (max(ctx.n_scratch, 1) + 3) // 4 * 4
+        sizes = [n_scratch, V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE]
         flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
         parts = list(flat.split(sizes))
-        g_verts, g_cols, g_R, g_T, g_proj, g_vp = parts
-        scratch = torch.empty((max(ctx.n_scratch, 1),), dtype=torch.float32, device=dev)
+        scratch, g_verts, g_cols, g_R, g_T, g_proj, g_vp = parts
+        cfg.scratch_is_zeroed = 1
         f32 = lambda t: None if t is None else _f32c(t)
         want_vp = vp is not None
         with _timed("render_backward", dev):
@@ -502,7 +503,7 @@ class _RenderFn(torch.autograd.Function):
                 _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
                 _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),
                 _ptr(g_vp if want_vp else None), _ptr(scratch), dev.index, _stream(dev)), "render backward")
-        _bump(7)
+        _bump(2)  # fused backward, post
         return (g_verts.view(V, 3) if need[0] else None,
                 g_cols.view(V, 3) if (need[1] and colors is not None) else None,
                 g_R.view(N, 3, 3) if need[2] else None, g_T.view(N, 3) if need[3] else None,

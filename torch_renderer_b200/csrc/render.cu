@@ -56,6 +56,69 @@ __device__ __forceinline__ void fill_empty_tile(const FineArgs& a, int n, int tb
   st_cs(reinterpret_cast<float4*>(a.images) + pix, bgv);
 }
 
+// The same for a tile that lies entirely inside an image whose rows keep 16-byte alignment (W % 4 == 0):
+// 16-byte stores only -- 2.75 per thread instead of 7, and every store instruction covers whole sectors
+// (the stride-3 barycentric stores above touch 12 sectors for 4 sectors' worth of data).
+template <int SHADER>
+__device__ __forceinline__ void fill_empty_tile_v4(const FineArgs& a, int n, int tbx, int tby) {
+  const int tid = threadIdx.x;
+  const size_t pix0 = ((size_t)n * a.H + tby * 16) * a.W + tbx * 16;  // top-left pixel of the tile
+  const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+  const size_t W = a.W;
+  if (tid < 64) {          // zbuf: 16 rows x 4
+    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (tid >> 2) * W) + (tid & 3), m4);
+  } else if (tid < 128) {  // dists
+    const int i = tid - 64;
+    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i >> 2) * W) + (i & 3), m4);
+  } else {                 // pix_to_face: 16 rows x 8 (two int64 per store)
+    const int i = tid - 128;
+    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i >> 3) * W) + (i & 7), make_longlong2(-1ll, -1ll));
+  }
+  if (tid < 192) {         // barycentrics: 16 rows x 12
+    const int r = tid / 12, c = tid - r * 12;
+    st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+  }
+  if (SHADER == TRB_SHADER_NONE) return;
+  const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                            : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+  st_cs(reinterpret_cast<float4*>(a.images) + pix0 + (tid >> 4) * W + (tid & 15), bgv);
+}
+
+// A whole strip of kStrip empty tiles inside the image: row-contiguous 16-byte stores, every warp
+// instruction writes 512 consecutive bytes.
+template <int SHADER>
+__device__ __forceinline__ void fill_empty_strip_v4(const FineArgs& a, int n, int tbx0, int tby) {
+  const int tid = threadIdx.x;
+  const size_t W = a.W;
+  const size_t pix0 = ((size_t)n * a.H + tby * 16) * W + tbx0 * 16;
+  const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {   // zbuf, dists: 16 rows x 32
+    const int i = tid + 256 * j;
+    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (i >> 5) * W) + (i & 31), m4);
+    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i >> 5) * W) + (i & 31), m4);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {   // pix_to_face: 16 rows x 64
+    const int i = tid + 256 * j;
+    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i >> 6) * W) + (i & 63), make_longlong2(-1ll, -1ll));
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {   // barycentrics: 16 rows x 96
+    const int i = tid + 256 * j;
+    const int r = i / 96, c = i - r * 96;
+    st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+  }
+  if (SHADER == TRB_SHADER_NONE) return;
+  const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                            : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // RGBA: 16 rows x 128
+    const int i = tid + 256 * j;
+    st_cs(reinterpret_cast<float4*>(a.images) + pix0 + (i >> 7) * W + (i & 127), bgv);
+  }
+}
+
 template <int SHADER, int LIGHT>
 __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 
@@ -69,7 +132,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 constexpr int kStrip = 8;
 
 template <int SHADER, int LIGHT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 render_fine_k1_kernel(const FineArgs a) {
   pdl_wait();
   const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * kStrip;
@@ -78,9 +141,20 @@ render_fine_k1_kernel(const FineArgs a) {
 #pragma unroll
   for (int s = 0; s < kStrip; ++s) cnt[s] = (tbx0 + s < a.tg.tiles_x) ? __ldg(counts + tbx0 + s) : -1;
   const int nbusy = __ldg(a.ws_header + 4);
+  const bool rows_inside = (tby + 1) * 16 <= a.H && (a.W & 3) == 0;
+  bool all_empty = true;
 #pragma unroll
-  for (int s = 0; s < kStrip; ++s)
-    if (cnt[s] == 0) fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
+  for (int s = 0; s < kStrip; ++s) all_empty = all_empty && cnt[s] == 0;
+  if (all_empty && rows_inside && (tbx0 + kStrip) * 16 <= a.W) {
+    fill_empty_strip_v4<SHADER>(a, n, tbx0, tby);
+  } else {
+#pragma unroll
+    for (int s = 0; s < kStrip; ++s)
+      if (cnt[s] == 0) {
+        if (rows_inside && (tbx0 + s + 1) * 16 <= a.W) fill_empty_tile_v4<SHADER>(a, n, tbx0 + s, tby);
+        else fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
+      }
+  }
   // deal the non-empty tiles out evenly over the grid (32-bit arithmetic only)
   const unsigned ncta = gridDim.x * gridDim.y * gridDim.z;
   const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;

@@ -151,6 +151,9 @@ def run_ours(args):
     work_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(work_stream)
 
+    # every step rasterises: no reuse of Fragments between identical renders (the inputs of the device-resident
+    # leg do not change from step to step)
+    trb.set_fragment_cache(False)
     v, f, colors, R, T = _scene(dev)
     V, F, N = v.shape[0], f.shape[0], VIEWS_PER_GPU
     # weak scaling: every rank renders its own 64 views of the orbit (rotated per rank), mesh replicated

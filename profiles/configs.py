@@ -11,6 +11,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch_renderer_b200 as trb  # noqa: E402
 from helpers import load_mesh, normalize_mesh  # noqa: E402
 
+trb.set_fragment_cache(False)  # timings are of the kernels, not of the reuse of Fragments between equal renders
 SIGMA = 1e-4
 BLUR = math.log(1.0 / 1e-4 - 1.0) * SIGMA
 
@@ -119,7 +120,40 @@ def c5(dev, nv=4, nlat=501, nlon=1000, size=1024, K=8):
                       verts=int(v.shape[0]))
 
 
+def pose_step(dev, cache):
+    """One step of camera_pose_optimizer.Model.forward (:237-254) with the script's ACTIVE settings (:123-128):
+    cow, 512^2, K=1, blur 0; rasterizer -> zbuf, silhouette renderer, Phong renderer on the same R, T; pose =
+    (T, quaternion) requires grad.  `cache` switches the reuse of Fragments between the three calls."""
+    trb.set_fragment_cache(cache)
+    v, f = load_mesh("cow")
+    cols = torch.rand(1, v.shape[0], 3)
+    mesh = trb.Meshes([v.to(dev)], [f.to(dev)], textures=trb.TexturesVertex(cols.to(dev)))
+    cams = trb.FoVPerspectiveCameras(device=dev)
+    settings = trb.RasterizationSettings(image_size=512, blur_radius=0.0, faces_per_pixel=1)
+    blend = trb.BlendParams(SIGMA, 1e-4, (0, 0, 0))
+    rast = trb.MeshRasterizer(cams, settings)
+    sil = trb.MeshRenderer(trb.MeshRasterizer(cams, settings), trb.SoftSilhouetteShader(blend))
+    phong = trb.MeshRenderer(trb.MeshRasterizer(cams, settings),
+                             trb.SoftPhongShader(device=dev, cameras=cams, blend_params=blend,
+                                                 lights=trb.PointLights(device=dev, location=[[0.0, 0.0, -3.0]])))
+    R, T = trb.look_at_view_transform(0.7, 30, 60)
+    pose = torch.cat([T, trb.transforms.matrix_to_quaternion(R)], -1).to(dev).requires_grad_(True)
+    tgt_d = torch.rand(1, 512, 512, device=dev); tgt_a = torch.rand(1, 512, 512, device=dev)
+    tgt_c = torch.rand(1, 512, 512, 3, device=dev)
+
+    def step():
+        pose.grad = None
+        Rm = trb.transforms.quaternion_to_matrix(pose[:, 3:]); Tm = pose[:, :3]
+        depth = torch.relu(rast(meshes_world=mesh, R=Rm, T=Tm).zbuf[..., 0])
+        alpha = sil(mesh, R=Rm, T=Tm)[..., 3]
+        rgb = phong(mesh, R=Rm, T=Tm)[..., :3]
+        ((depth - tgt_d).abs().mean() + (alpha - tgt_a).abs().mean() + ((rgb - tgt_c) ** 2).mean()).backward()
+    return step, dict(views=1, bytes=3 * bview(1, 512, 512, v.shape[0], f.shape[0]))
+
+
 BUILDERS = {
+    "pose_step": lambda dev: pose_step(dev, False),
+    "pose_step_cached": lambda dev: pose_step(dev, True),
     "C1": c1,
     "C3": c3,
     "C3cow": lambda dev: c3(dev, "cow"),

@@ -20,3 +20,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _no_fragment_cache():
+    """Every test exercises the kernel it names: Fragments are not reused between back-to-back identical renders
+    unless a test switches the cache on (tests/test_gpu_parity.py::test_fragment_cache_*)."""
+    try:
+        from torch_renderer_b200.rasterizer import set_fragment_cache
+    except Exception:
+        yield
+        return
+    set_fragment_cache(False)
+    yield
+    set_fragment_cache(False)

@@ -581,3 +581,61 @@ def test_z_clip_culls_faces_entirely_nearer_than_the_plane():
     frag0 = trb.MeshRasterizer(trb.PerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV), focal_length=1.7320508),
                                trb.RasterizationSettings(image_size=96, faces_per_pixel=2))(mesh)
     assert (frag0.pix_to_face != frag.pix_to_face).any()
+
+
+def test_fragment_cache_reference_step_pattern():
+    """camera_pose_optimizer.py:237-254: rasterizer(meshes, R=R, T=T).zbuf, then the silhouette renderer, then the
+    Phong renderer on the same meshes / R / T / settings.  With the Fragments cache the scene is rasterised once
+    per step; values and pose gradients must equal the uncached run, and nothing may leak into the next step."""
+    trb = _trb()
+    from torch_renderer_b200.rasterizer import _fragment_cache, set_fragment_cache
+    v, f = _scene("teapot")
+    cols = torch.rand(1, v.shape[0], 3, generator=torch.Generator().manual_seed(1))
+    mesh = trb.Meshes([v.to(DEV)], [f.to(DEV)], textures=trb.TexturesVertex(cols.to(DEV)))
+    cams = trb.FoVPerspectiveCameras(device=DEV)
+    settings = trb.RasterizationSettings(image_size=128, blur_radius=0.0, faces_per_pixel=1)
+    blend = trb.BlendParams(1e-4, 1e-4, (0, 0, 0))
+    rast = trb.MeshRasterizer(cams, settings)
+    sil = trb.MeshRenderer(trb.MeshRasterizer(cams, settings), trb.SoftSilhouetteShader(blend))
+    phong = trb.MeshRenderer(trb.MeshRasterizer(cams, settings),
+                             trb.SoftPhongShader(device=DEV, cameras=cams, blend_params=blend,
+                                                 lights=trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]])))
+    R0, T0 = trb.look_at_view_transform(2.7, 30, 60)
+    q0 = torch.cat([T0, trb.transforms.matrix_to_quaternion(R0)], -1).to(DEV)
+
+    def step(pose):
+        R = trb.transforms.quaternion_to_matrix(pose[:, 3:]); T = pose[:, :3]
+        depth = torch.relu(rast(meshes_world=mesh, R=R, T=T).zbuf[..., 0])
+        alpha = sil(mesh, R=R, T=T)[..., 3]
+        rgb = phong(mesh, R=R, T=T)[..., :3]
+        loss = depth.mean() + alpha.mean() + (rgb ** 2).mean()
+        loss.backward()
+        return depth.detach(), alpha.detach(), rgb.detach(), pose.grad.clone()
+
+    set_fragment_cache(False)
+    want = step(q0.clone().requires_grad_(True))
+    set_fragment_cache(True)
+    pose = q0.clone().requires_grad_(True)
+    h0 = _fragment_cache.hits
+    got = step(pose)
+    assert _fragment_cache.hits - h0 == 2          # silhouette + Phong reused the rasteriser's Fragments
+    for a, b in zip(got[:3], want[:3]):
+        assert torch.allclose(a, b, atol=1e-4, rtol=0)
+    assert rel_l2(got[3].cpu(), want[3].cpu()) < 1e-3
+    # next step, same tensors: the stored graph is spent, so the scene is rasterised again (no stale reuse)
+    pose.grad = None
+    h1 = _fragment_cache.hits
+    got2 = step(pose)
+    assert _fragment_cache.hits - h1 == 2
+    assert rel_l2(got2[3].cpu(), want[3].cpu()) < 1e-3
+    # an in-place update of an input is a different scene
+    with torch.no_grad():
+        frag_a = rast(mesh, R=R0.to(DEV), T=T0.to(DEV))
+        Rm, Tm = R0.to(DEV), T0.to(DEV)
+        fa = rast(mesh, R=Rm, T=Tm)
+        fb = rast(mesh, R=Rm, T=Tm)
+        assert fb.zbuf is fa.zbuf                   # identical inputs: reused
+        Tm.add_(0.2)
+        fc = rast(mesh, R=Rm, T=Tm)
+        assert fc.zbuf is not fa.zbuf and not torch.equal(fc.zbuf, fa.zbuf)
+    set_fragment_cache(False)

@@ -80,7 +80,8 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
 
 
 def _stream(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    # the raw cudaStream_t of torch's current stream (torch.cuda.current_stream() builds a Stream object: 13 us)
+    return torch._C._cuda_getCurrentRawStream(device.index)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -439,45 +440,60 @@ class _RenderFn(torch.autograd.Function):
         check(L.trb_render_sizes(ctypes.byref(cfg), ctypes.byref(ws_bytes), ctypes.byref(n_tiles),
                                  ctypes.byref(n_scratch)), "render")
         phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
-        ws = torch.empty((ws_bytes.value,), dtype=torch.uint8, device=dev)
-        verts_ndc = torch.empty((table.total_ndc_verts, 3), dtype=torch.float32, device=dev)
-        normals_raw = torch.empty_like(verts) if phong else None
-        normals = torch.empty_like(verts) if phong else None
+        # One allocation for everything the caller never sees -- workspace, NDC vertices, vertex normals, the
+        # covered-pixel list, bin statistics -- addressed by offset (each torch.empty costs ~4 us of host time).
+        want_stats = table._pending is None and not torch.cuda.is_current_stream_capturing()
+        V3 = verts.shape[0] * 12
+        sizes = (ws_bytes.value, table.total_ndc_verts * 12, V3 if phong else 0, V3 if phong else 0,
+                 max(n_tiles.value, 1) * 4, 16 if want_stats else 0)
+        offs, total = [], 0
+        for nb in sizes:
+            offs.append(total)
+            total += (nb + 255) & ~255
+        aux = torch.empty((max(total, 256),), dtype=torch.uint8, device=dev)
+        base = aux.data_ptr()
+        p_ws, p_ndc, p_nraw, p_nrm, p_hit, p_stats = (base + o for o in offs)
+        if not phong:
+            p_nraw = p_nrm = 0
+        if not want_stats:
+            p_stats = 0
         p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
         zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         images = (torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if shader != _lib.SHADER_NONE
                   else torch.empty((0,), dtype=torch.float32, device=dev))
-        tile_hit = torch.empty((max(n_tiles.value, 1),), dtype=torch.int32, device=dev)
-        # bin statistics are only fetched when no earlier read-back is still pending
-        want_stats = table._pending is None and not torch.cuda.is_current_stream_capturing()
-        stats = torch.empty((4,), dtype=torch.int32, device=dev) if want_stats else None
         with _timed("render_forward", dev):
             check(L.trb_render_forward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
-                _ptr(proj), _ptr(vp), _ptr(verts_ndc), _ptr(normals_raw), _ptr(normals), _ptr(p2f), _ptr(zbuf),
-                _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), _ptr(tile_hit),
-                _ptr(ws), ws_bytes.value, _ptr(stats), dev.index, _stream(dev)), "render")
+                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, _ptr(p2f), _ptr(zbuf),
+                _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), p_hit,
+                p_ws, ws_bytes.value, p_stats, dev.index, _stream(dev)), "render")
         _bump(5 + (1 if want_stats else 0))  # prep, count, alloc, fill, fine (+ stats)
         if want_stats:
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
-            host_stats.copy_(stats, non_blocking=True)
+            host_stats.copy_(aux[offs[5]:offs[5] + 16].view(torch.int32), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             table._pending = (host_stats, ev)
-        ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, verts_ndc, normals_raw, normals, p2f, zbuf,
-                              bary, dists, tile_hit)
+        ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists)
+        ctx.aux_offsets = (offs[1], offs[2], offs[3], offs[4], phong)
         ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch.value
-        ctx.mark_non_differentiable(p2f, verts_ndc)
+        ctx.token = spec.get("_token")   # Fragments cache: set once a backward has consumed this graph
+        ctx.mark_non_differentiable(p2f)
         ctx.set_materialize_grads(False)
-        return images, p2f, zbuf, bary, dists, verts_ndc
+        return images, p2f, zbuf, bary, dists
 
     @staticmethod
-    def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists, g_ndc_ext):
-        (verts, colors, R, T, proj, vp, faces, verts_ndc, normals_raw, normals, p2f, zbuf, bary, dists,
-         tile_hit) = ctx.saved_tensors
+    def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists):
+        verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists = ctx.saved_tensors
+        o_ndc, o_nraw, o_nrm, o_hit, phong = ctx.aux_offsets
+        base = aux.data_ptr()
+        p_ndc, p_hit = base + o_ndc, base + o_hit
+        p_nraw, p_nrm = (base + o_nraw, base + o_nrm) if phong else (0, 0)
         table, cfg = ctx.table, ctx.cfg
+        if ctx.token is not None:
+            ctx.token["consumed"] = True
         dev = verts.device
         need = ctx.needs_input_grad  # verts, colors, R, T, proj, view_params
         N, V = table.N, verts.shape[0]
@@ -497,8 +513,8 @@ class _RenderFn(torch.autograd.Function):
         with _timed("render_backward", dev):
             check(_lib.lib().trb_render_backward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
-                _ptr(proj), _ptr(vp), _ptr(verts_ndc), _ptr(normals_raw), _ptr(normals), _ptr(p2f), _ptr(zbuf),
-                _ptr(bary), _ptr(dists), _ptr(tile_hit), _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
+                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, _ptr(p2f), _ptr(zbuf),
+                _ptr(bary), _ptr(dists), p_hit, _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
                 _ptr(f32(g_zbuf)), _ptr(f32(g_bary)), _ptr(f32(g_dists)),
                 _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
                 _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),
@@ -512,7 +528,7 @@ class _RenderFn(torch.autograd.Function):
 
 
 def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
-    """Returns (images [N,H,W,4] or empty, pix_to_face, zbuf, bary, dists, verts_ndc)."""
+    """Returns (images [N,H,W,4] or empty, pix_to_face, zbuf, bary, dists)."""
     if spec["K"] > _lib.MAX_FACES_PER_PIXEL:
         raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
     return _RenderFn.apply(verts, colors, R, T, proj, view_params, faces, table, spec)

@@ -131,6 +131,71 @@ def _cached_half_znear(cameras):
     return cache[1]
 
 
+class _FragmentCache:
+    """The Fragments of the most recent rasterisation, keyed on the identity + version of every input tensor
+    and on the raster settings.  The reference rasterises the same scene two or three times
+    per step -- ``rasterizer(meshes, R=R, T=T).zbuf``, then the silhouette renderer, then the Phong renderer
+    with the same meshes, R, T and settings (camera_pose_optimizer.py:244-250, torch_renderer.py:113-120,
+    deform_mesh_with_color.py:373-381); with the cache the second and third call only run the shading kernel
+    on the stored Fragments, and the backward rasterises once (autograd sums the three gradient streams).
+
+    One entry; entries above ``max_bytes`` are not kept (a chunk of a 1024-view job must not stay alive past
+    its iteration); nothing is stored while a CUDA graph is being captured."""
+
+    def __init__(self):
+        self.enabled = True
+        self.max_bytes = 2 << 30
+        self.key = None
+        self.refs = ()
+        self.value = None
+        self.token = None
+        self.hits = 0
+
+    def clear(self):
+        self.key, self.refs, self.value, self.token = None, (), None, None
+
+    @staticmethod
+    def make_key(tensors, spec, table):
+        ids = tuple((id(t), t._version) for t in tensors)
+        raster = (spec["image_size"], spec["K"], spec["blur_radius"], spec["flags"], spec["z_clip"],
+                  spec["perspective"])
+        return (ids, raster, id(table), torch.is_grad_enabled())
+
+    def lookup(self, key, tensors):
+        if not self.enabled or self.key != key or self.value is None:
+            return None
+        # a backward pass has already run through the stored Fragments: their autograd graph is spent
+        if self.token is not None and self.token.get("consumed"):
+            return None
+        # ids are only unique among live objects: every input must still be the tensor the entry was made from
+        if len(self.refs) != len(tensors) or any(r() is not t for r, t in zip(self.refs, tensors)):
+            return None
+        self.hits += 1
+        return self.value
+
+    def store(self, key, tensors, fragments, token=None):
+        if not self.enabled or torch.cuda.is_current_stream_capturing():
+            return
+        nbytes = sum(t.numel() * t.element_size() for t in fragments if t is not None)
+        if nbytes > self.max_bytes:
+            self.clear()
+            return
+        import weakref
+        self.key, self.refs, self.value = key, tuple(weakref.ref(t) for t in tensors), fragments
+        self.token = token
+
+
+_fragment_cache = _FragmentCache()
+
+
+def set_fragment_cache(enabled: bool = True, max_bytes: Optional[int] = None) -> None:
+    """Switches the reuse of Fragments between back-to-back renders of identical inputs on or off."""
+    _fragment_cache.enabled = bool(enabled)
+    if max_bytes is not None:
+        _fragment_cache.max_bytes = int(max_bytes)
+    _fragment_cache.clear()
+
+
 def _expand_views(t: torch.Tensor, N: int, what: str) -> torch.Tensor:
     if t.shape[0] == N:
         return t
@@ -166,10 +231,11 @@ class MeshRasterizer(nn.Module):
         T = cameras.T if T is None else T
         # PyTorch3D's get_world_to_view_transform stores per-call overrides on the camera object;
         # the shaders' specular term (get_camera_center() without kwargs) relies on it.
-        cameras.R, cameras.T = R, T
+        cameras.__dict__["R"], cameras.__dict__["T"] = R, T   # plain attributes (nn.Module.__setattr__ is slow)
         proj_kwargs = {k: v for k, v in kwargs.items()
                        if k not in ("R", "T", "cameras", "lights", "materials", "blend_params", "raster_settings")}
         proj, perspective = _cached_projection(cameras, proj_kwargs)
+        self.__dict__["_identity"] = (R, T, proj)   # the caller's tensor objects (expand() below makes new ones per call)
         R = _expand_views(R.to(dev), N, "R")
         T = _expand_views(T.to(dev), N, "T")
         proj = _expand_views(proj.to(dev), N, "projection")
@@ -213,8 +279,21 @@ class MeshRasterizer(nn.Module):
         return ops.transform_verts(meshes_world._unique_verts(), R, T, proj, meshes_world.view_table(),
                                    perspective)
 
+    def _cache_key(self, meshes_world: Meshes, spec):
+        """(key, tensors) of this call for the Fragments cache; valid right after ``_resolve``."""
+        tensors = (meshes_world._unique_verts(), meshes_world.faces_packed_i32()) + tuple(self._identity)
+        return _fragment_cache.make_key(tensors, spec, meshes_world.view_table()), tensors
+
     def forward(self, meshes_world: Meshes, **kwargs) -> Fragments:
         _, R, T, proj, spec = self._resolve(meshes_world, kwargs)
-        _, p2f, zbuf, bary, dists, _ = ops.render(meshes_world._unique_verts(), None, R, T, proj, None,
+        key, tensors = self._cache_key(meshes_world, spec)
+        cached = _fragment_cache.lookup(key, tensors)
+        if cached is not None:
+            return cached
+        token = {"consumed": False}
+        spec["_token"] = token
+        _, p2f, zbuf, bary, dists = ops.render(meshes_world._unique_verts(), None, R, T, proj, None,
                                                   meshes_world.faces_packed_i32(), meshes_world.view_table(), spec)
-        return Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+        fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+        _fragment_cache.store(key, tensors, fragments, token)
+        return fragments

@@ -7,7 +7,8 @@ from .cameras import (  # noqa: F401
     SfMPerspectiveCameras, camera_position_from_spherical_angles, get_world_to_view_transform,
     look_at_rotation, look_at_view_transform)
 from .lighting import AmbientLights, DirectionalLights, Materials, PointLights  # noqa: F401
-from .rasterizer import Fragments, MeshRasterizer, RasterizationSettings, rasterize_meshes  # noqa: F401
+from .rasterizer import (  # noqa: F401
+    Fragments, MeshRasterizer, RasterizationSettings, rasterize_meshes, set_fragment_cache)
 from .shader import (  # noqa: F401
     HardPhongShader, MeshRenderer, MeshRendererWithFragments, SoftPhongShader, SoftSilhouetteShader,
     TexturedSoftPhongShader)

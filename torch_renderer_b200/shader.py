@@ -248,13 +248,23 @@ class MeshRenderer(nn.Module):
             znear = kwargs.get("znear", getattr(shader_cameras, "znear", 1.0))
             zfar = kwargs.get("zfar", getattr(shader_cameras, "zfar", 100.0))
             vp = _cached_view_params(shader, N, dev, lights, materials, shader_cameras, znear, zfar, not from_rt)
+        # the same scene was just rasterised with the same settings (the reference does that 2-3 times per
+        # step): shade the stored Fragments instead of rasterising again
+        from .rasterizer import _fragment_cache
+        key, tensors = rast._cache_key(meshes_world, spec)
+        cached = _fragment_cache.lookup(key, tensors)
+        if cached is not None:
+            return shader(cached, meshes_world, **kwargs), cached
         bg = blend_params.background_color
         bg = tuple(float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg))
-        spec.update(shader=kind, light_kind=light_kind, sigma=float(blend_params.sigma),
+        token = {"consumed": False}
+        spec.update(_token=token, shader=kind, light_kind=light_kind, sigma=float(blend_params.sigma),
                     gamma=float(blend_params.gamma), background=bg, camera_center_from_rt=from_rt)
-        images, p2f, zbuf, bary, dists, _ = ops.render(
+        images, p2f, zbuf, bary, dists = ops.render(
             meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec)
-        return images, Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+        fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+        _fragment_cache.store(key, tensors, fragments, token)
+        return images, fragments
 
     def forward(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
         fused = self._render_fused(meshes_world, kwargs)

@@ -15,18 +15,39 @@ import torch
 import torch.nn.functional as F
 
 
+_Q2M = {}
+
+
+def _q2m_table(dtype, device):
+    """[16, 9] constant: column c holds the +-1 weights of the products q_a q_b (row 4a+b) in entry c of the
+    rotation matrix divided by two_s (the diagonal's leading 1 is added separately)."""
+    key = (dtype, str(device))
+    t = _Q2M.get(key)
+    if t is None:
+        c = torch.zeros(16, 9, dtype=dtype)
+        r, i, j, k = 0, 1, 2, 3
+        for col, terms in enumerate((
+                ((j, j, -1), (k, k, -1)), ((i, j, 1), (k, r, -1)), ((i, k, 1), (j, r, 1)),
+                ((i, j, 1), (k, r, 1)), ((i, i, -1), (k, k, -1)), ((j, k, 1), (i, r, -1)),
+                ((i, k, 1), (j, r, -1)), ((j, k, 1), (i, r, 1)), ((i, i, -1), (j, j, -1)))):
+            for a, b, sgn in terms:
+                c[4 * a + b, col] = sgn
+        eye = torch.eye(3, dtype=dtype).reshape(9)
+        t = (c.to(device), eye.to(device))
+        _Q2M[key] = t
+    return t
+
+
 def quaternion_to_matrix(quaternions: torch.Tensor) -> torch.Tensor:
-    """(..., 4) real-first quaternions -> (..., 3, 3) rotation matrices (need not be unit)."""
-    r, i, j, k = torch.unbind(quaternions, -1)
-    two_s = 2.0 / (quaternions * quaternions).sum(-1)
-    o = torch.stack(
-        (
-            1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
-            two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
-            two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j),
-        ),
-        -1,
-    )
+    """(..., 4) real-first quaternions -> (..., 3, 3) rotation matrices (need not be unit).
+
+    Same polynomial as ``pytorch3d.transforms.quaternion_to_matrix`` (R = I + two_s * L(q q^T)), written as one
+    outer product and one [16, 9] contraction: 7 small kernels forward instead of ~40 (and ~80 fewer in the
+    backward) -- the pose -> matrix conversion was 60% of the host time of a camera_pose_optimizer.py step."""
+    table, eye = _q2m_table(quaternions.dtype, quaternions.device)
+    two_s = 2.0 / (quaternions * quaternions).sum(-1, keepdim=True)
+    qq = (quaternions[..., :, None] * quaternions[..., None, :]).reshape(quaternions.shape[:-1] + (16,))
+    o = eye + two_s * (qq @ table)
     return o.reshape(quaternions.shape[:-1] + (3, 3))
 
 

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 2
+#define TRB_ABI_VERSION 3
 #define TRB_MAX_FACES_PER_PIXEL 150
 
 typedef void* trb_stream_t; /* cudaStream_t */
@@ -78,7 +78,7 @@ typedef struct trb_view {
 int trb_abi_version(void);
 const char* trb_status_string(int status);
 int trb_last_cuda_error(void);
-/* sizeof(trb_view | trb_shade_config | trb_render_config) for which = 0 | 1 | 2 as compiled into the
+/* sizeof(trb_view | trb_shade_config | trb_render_config | trb_uv_texture) for which = 0 | 1 | 2 | 3 as compiled into the
  * library: bindings compare it with their own layout and refuse a stale build. */
 int trb_abi_struct_size(int which);
 
@@ -157,7 +157,8 @@ int trb_vertex_normals_backward(const float* verts, const int32_t* faces, int64_
 #define TRB_LIGHT_POINT 1
 #define TRB_LIGHT_DIRECTIONAL 2
 #define TRB_TEX_VERTEX 0 /* per-vertex RGB interpolated in the kernel (TexturesVertex) */
-#define TRB_TEX_TEXELS 1 /* caller supplies texels f32[N,H,W,K,3] (e.g. TexturesUV)    */
+#define TRB_TEX_TEXELS 1 /* caller supplies texels f32[N,H,W,K,3] (trb_shade_* only)      */
+#define TRB_TEX_UV 2     /* TexturesUV sampled inside the fused kernels (trb_render_* only) */
 #define TRB_VIEW_PARAM_STRIDE 20
 /* view_params f32[N,20]: [0:3] light location/direction, [3:6] ambient (material*light),
  * [6:9] diffuse (material*light), [9:12] specular (material*light), [12] shininess,
@@ -201,7 +202,8 @@ int trb_shade_backward(const trb_shade_config* host_cfg, const trb_view* views,
  * forward and read once in the backward; nothing else of size N*H*W*K touches HBM.
  *
  * shade.shader may be TRB_SHADER_NONE: rasterise only (MeshRasterizer.forward).  Textures are
- * per-vertex colours (TexturesVertex); other textures go through trb_shade_forward with texels.
+ * per-vertex colours (TexturesVertex, texture_mode TRB_TEX_VERTEX) or one UV map (TRB_TEX_UV, host_uv);
+ * anything else goes through trb_shade_forward with texels.
  */
 #define TRB_SHADER_NONE (-1)
 
@@ -230,6 +232,18 @@ typedef struct trb_render_config {
 /* workspace_bytes: scratch for the forward; hit_pixels_len: length of hit_pixels (int32: a count
  * followed by the linear ids of the pixels that got at least one face -- the backward visits only
  * those); backward_scratch_floats: length of the f32 scratch the backward needs. */
+/* TexturesUV for the fused pipeline (replaces TexturesUV.sample_textures: interp_face_attrs on the UVs +
+ * grid_sample(flip(maps), 2uv-1, bilinear, align_corners=True, padding border); reference:
+ * every load_objs_as_meshes() of data/cow_mesh/cow.obj, deform_mesh_with_color.py:266-271,329).
+ * One map shared by all views of the batch; host struct holding device pointers. */
+typedef struct trb_uv_texture {
+  const float* map;         /* f32 [map_h, map_w, 3] */
+  const float* verts_uvs;   /* f32 [Vt, 2] */
+  const int32_t* faces_uvs; /* i32 [F, 3], row r belongs to row r of `faces` */
+  float* grad_map;          /* backward only: f32 [map_h, map_w, 3], ACCUMULATED into; may be NULL */
+  int32_t map_h, map_w;
+} trb_uv_texture;
+
 int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* hit_pixels_len,
                      int64_t* backward_scratch_floats);
 /* view_params f32[N,20] is in/out (camera centre filled in when camera_center_from_rt).
@@ -240,8 +254,9 @@ int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        const float* R, const float* T, const float* proj, float* view_params,
                        float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
                        float* zbuf, float* bary, float* dists, float* images, int32_t* hit_pixels,
-                       void* workspace, size_t workspace_bytes, int32_t* stats, int device,
-                       trb_stream_t stream);
+                       void* workspace, size_t workspace_bytes, int32_t* stats,
+                       const trb_uv_texture* host_uv /* NULL unless shade.texture_mode == TRB_TEX_UV */,
+                       int device, trb_stream_t stream);
 /* grad_images may be NULL (shader NONE); grad_zbuf / grad_bary / grad_dists are optional extra
  * upstream gradients on the Fragments.  Every grad_* output is ACCUMULATED into (caller zeroes;
  * any may be NULL); `scratch` is zeroed by the call unless cfg->scratch_is_zeroed. */
@@ -253,8 +268,8 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         const float* dists, const int32_t* hit_pixels, const float* grad_images,
                         const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
                         float* grad_verts_world, float* grad_vert_colors, float* grad_R, float* grad_T,
-                        float* grad_proj, float* grad_view_params, float* scratch, int device,
-                        trb_stream_t stream);
+                        float* grad_proj, float* grad_view_params, float* scratch,
+                        const trb_uv_texture* host_uv, int device, trb_stream_t stream);
 
 /* Measurement hook (bench.py's roofline leg): when non-NULL, the four cudaEvent_t handles are
  * recorded on the call's stream immediately before / after the dominant kernel of

@@ -639,3 +639,49 @@ def test_fragment_cache_reference_step_pattern():
         fc = rast(mesh, R=Rm, T=Tm)
         assert fc.zbuf is not fa.zbuf and not torch.equal(fc.zbuf, fa.zbuf)
     set_fragment_cache(False)
+
+
+@pytest.mark.parametrize("K,blur,lights", [(1, 0.0, "point"), (4, 1e-3, "point"), (1, 0.0, "ambient")])
+def test_textures_uv_fused_in_kernels(K, blur, lights):
+    """TexturesUV sampled inside the fused kernels (the cow asset of camera_pose_optimizer.py /
+    deform_mesh_with_color.py:266-271,329) against the composed path -- rasterise, CUDA UV interpolation,
+    torch grid_sample(flip(map), 2uv-1, bilinear, align_corners=True, border), shade with texels: same images,
+    same gradients w.r.t. the texture map, the vertices and the per-view R / T."""
+    trb = _trb()
+    torch.manual_seed(0)
+    v, f = load_mesh("cow")
+    v = normalize_mesh(v)
+    vt, ft = cow_uvs()
+    tex = torch.rand(1, 48, 80, 3)
+    R, T = _views(2, seed=4)
+
+    def run(fused):
+        texd = tex.to(DEV).requires_grad_(True)
+        vd = v.to(DEV).requires_grad_(True)
+        Rd, Td = R.to(DEV).requires_grad_(True), T.to(DEV).requires_grad_(True)
+        mesh = trb.Meshes(verts=[vd], faces=[f.to(DEV)],
+                          textures=trb.TexturesUV(maps=texd, faces_uvs=[ft.to(DEV)], verts_uvs=[vt.to(DEV)])).extend(2)
+        cameras = trb.FoVPerspectiveCameras(device=DEV, R=Rd, T=Td)
+        lt = (trb.AmbientLights(device=DEV) if lights == "ambient"
+              else trb.PointLights(device=DEV, location=[[0.5, 1.0, -2.5]]))
+        rast = trb.MeshRasterizer(cameras=cameras, raster_settings=trb.RasterizationSettings(
+            image_size=(72, 96), blur_radius=blur, faces_per_pixel=K))
+        shader = trb.SoftPhongShader(device=DEV, cameras=cameras, lights=lt)
+        if fused:
+            from torch_renderer_b200 import ops
+            n0 = ops.launch_count()
+            img = trb.MeshRenderer(rast, shader)(mesh)
+            assert ops.launch_count() - n0 <= 6, "TexturesUV did not take the fused path"
+        else:
+            img = shader(rast(mesh), mesh)
+        w = torch.linspace(0.5, 1.5, 72 * 96 * 4, device=DEV).reshape(1, 72, 96, 4)
+        (img * w).sum().backward()
+        return img.detach(), texd.grad, vd.grad, Rd.grad, Td.grad
+
+    a, b = run(True), run(False)
+    assert (a[0][..., 3] > 0).sum() > 500
+    assert torch.allclose(a[0], b[0], atol=1e-4, rtol=0), (a[0] - b[0]).abs().max()
+    for name, x, y in zip(("texture map", "verts", "R", "T"), a[1:], b[1:]):
+        assert x is not None and y is not None, name
+        assert rel_l2(x.cpu(), y.cpu()) < 1e-3, (name, rel_l2(x.cpu(), y.cpu()))
+    assert a[1].abs().sum() > 0

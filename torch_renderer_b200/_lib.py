@@ -18,7 +18,7 @@ TRB_OK, TRB_ERR_BAD_ARG, TRB_ERR_K_TOO_LARGE, TRB_ERR_WORKSPACE, TRB_ERR_CUDA = 
 PERSPECTIVE_CORRECT, CLIP_BARYCENTRIC, CULL_BACKFACES = 1, 2, 4
 SHADER_NONE, SHADER_SOFT_PHONG, SHADER_HARD_PHONG, SHADER_SOFT_SILHOUETTE = -1, 0, 1, 2
 LIGHT_AMBIENT, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2
-TEX_VERTEX, TEX_TEXELS = 0, 1
+TEX_VERTEX, TEX_TEXELS, TEX_UV = 0, 1, 2
 VIEW_PARAM_STRIDE = 20
 MAX_FACES_PER_PIXEL = 150
 
@@ -42,6 +42,11 @@ class RenderConfig(ctypes.Structure):
                 ("scratch_is_zeroed", _c.c_int32), ("reserved", _c.c_int32)]
 
 
+class UvTexture(ctypes.Structure):
+    _fields_ = [("map", _vp), ("verts_uvs", _vp), ("faces_uvs", _vp), ("grad_map", _vp),
+                ("map_h", _c.c_int32), ("map_w", _c.c_int32)]
+
+
 # name -> argtypes; every function returns int (trb_status) unless noted
 _SIGNATURES = {
     "trb_abi_version": [],
@@ -60,8 +65,8 @@ _SIGNATURES = {
     "trb_shade_forward": [_c.POINTER(ShadeConfig)] + [_vp] * 12 + [_i, _vp],
     "trb_shade_backward": [_c.POINTER(ShadeConfig)] + [_vp] * 20 + [_i, _vp],
     "trb_render_sizes": [_c.POINTER(RenderConfig), _c.POINTER(_sz), _c.POINTER(_i64), _c.POINTER(_i64)],
-    "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _i, _vp],
-    "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_i, _vp],
+    "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _c.POINTER(UvTexture), _i, _vp],
+    "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture), _i, _vp],
     "trb_debug_set_events": [_vp, _vp, _vp, _vp],
 }
 
@@ -94,10 +99,11 @@ def lib() -> ctypes.CDLL:
             fn.restype = _c.c_int
         handle.trb_status_string.argtypes = [_i]
         handle.trb_status_string.restype = _c.c_char_p
-        if handle.trb_abi_version() != 2:
+        if handle.trb_abi_version() != 3:
             raise TrbLibraryError("libtrb.so ABI version mismatch; rebuild it")
         for which, (name, size) in enumerate((("trb_view", 32), ("trb_shade_config", _c.sizeof(ShadeConfig)),
-                                              ("trb_render_config", _c.sizeof(RenderConfig)))):
+                                              ("trb_render_config", _c.sizeof(RenderConfig)),
+                                              ("trb_uv_texture", _c.sizeof(UvTexture)))):
             if handle.trb_abi_struct_size(which) != size:
                 raise TrbLibraryError(f"libtrb.so is stale: sizeof({name}) is {handle.trb_abi_struct_size(which)} in "
                                       f"the library but {size} in the binding; run python -m torch_renderer_b200.build")

@@ -15,6 +15,7 @@ extern "C" int trb_abi_struct_size(int which) {
     case 0: return (int)sizeof(trb_view);
     case 1: return (int)sizeof(trb_shade_config);
     case 2: return (int)sizeof(trb_render_config);
+    case 3: return (int)sizeof(trb_uv_texture);
     default: return -1;
   }
 }

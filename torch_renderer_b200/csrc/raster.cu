@@ -181,6 +181,7 @@ extern "C" int trb_raster_forward(const float* verts_ndc, const int32_t* faces, 
   a.ws_header = (const int*)(wsb + ws.header); a.busy_tiles = (const int*)(wsb + ws.busy);
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
   a.sigma = 1.0f; a.gamma = 1.0f;
+  a.uv = {nullptr, nullptr, nullptr, 0, 0};
   const int rc = launch_render_fine(TRB_SHADER_NONE, 0, N, st, a);
   if (rc != TRB_OK) return rc;
   if (stats) {

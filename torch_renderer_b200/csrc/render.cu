@@ -367,7 +367,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     out = make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
   } else {
     const ViewParams vp = load_view_params(a.view_params, n);
-    const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
+    const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces, a.uv};
     const F3 c = shade_sample<LIGHT>(sin, vd, vp, best_f, s.c0, s.c1, s.c2);
     if (SHADER == TRB_SHADER_HARD_PHONG) {
       out = make_float4(c.x, c.y, c.z, 1.0f);
@@ -397,6 +397,7 @@ struct BwdArgs {
   float4* g_verts_ndc; float4* g_verts_world; float4* g_normals; float4* g_colors;  // xyz_ accumulators
   float* g_view_params; int want_light_grad, want_cam_grad;
   float sigma, gamma, bg0, bg1, bg2;
+  UvTex uv; float* g_tex_map;  // TexturesUV: texture lookup instead of vertex colours; gradient of the map
 };
 
 __device__ __forceinline__ void scatter9(int key, float b0, float b1, float b2, F3 g, float4* base, int i0,
@@ -472,14 +473,27 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
     if (PHONG) {
       ViewParams vp = load_view_params(a.view_params, n);
       F3 C0 = {0, 0, 0}, C1 = C0, C2 = C0, X0 = C0, X1 = C0, X2 = C0, N0 = C0, N1 = C0, N2 = C0;
+      const bool use_uv = a.uv.map != nullptr;
+      F2 t0 = {0, 0}, t1 = t0, t2 = t0;
       if (on) {
-        C0 = ld3(a.colors, w0i); C1 = ld3(a.colors, w1i); C2 = ld3(a.colors, w2i);
+        if (use_uv) {
+          t0 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r)); t1 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r + 1));
+          t2 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r + 2));
+        } else {
+          C0 = ld3(a.colors, w0i); C1 = ld3(a.colors, w1i); C2 = ld3(a.colors, w2i);
+        }
         if (LIT) {
           X0 = ld3(a.verts_world, w0i); X1 = ld3(a.verts_world, w1i); X2 = ld3(a.verts_world, w2i);
           N0 = ld3(a.normals, w0i); N1 = ld3(a.normals, w1i); N2 = ld3(a.normals, w2i);
         }
       }
-      const F3 tex = interp3(b0, b1, b2, C0, C1, C2);
+      F3 tex = interp3(b0, b1, b2, C0, C1, C2);
+      UvTap tap = {};
+      F3 dtu = {0, 0, 0}, dtv = {0, 0, 0};
+      if (use_uv && on) {
+        tap = uv_tap(a.uv, b0 * t0.x + b1 * t1.x + b2 * t2.x, b0 * t0.y + b1 * t1.y + b2 * t2.y);
+        tex = uv_sample(a.uv, tap, &dtu, &dtv);
+      }
       const F3 P = interp3(b0, b1, b2, X0, X1, X2);
       const F3 nr = interp3(b0, b1, b2, N0, N1, N2);
       Lit lit;
@@ -512,7 +526,13 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
       const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
       F3 gT, gP, gN, g_lv, g_cam;
       phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
-      gb0 += dot3(gT, C0); gb1 += dot3(gT, C1); gb2 += dot3(gT, C2);
+      if (use_uv) {
+        const float gu = dot3(gT, dtu), gvv = dot3(gT, dtv);
+        gb0 += gu * t0.x + gvv * t0.y; gb1 += gu * t1.x + gvv * t1.y; gb2 += gu * t2.x + gvv * t2.y;
+        if (a.g_tex_map && on) uv_scatter(a.g_tex_map, tap, gT);
+      } else {
+        gb0 += dot3(gT, C0); gb1 += dot3(gT, C1); gb2 += dot3(gT, C2);
+      }
       if (LIT) {
         gb0 += dot3(gP, X0) + dot3(gN, N0); gb1 += dot3(gP, X1) + dot3(gN, N1); gb2 += dot3(gP, X2) + dot3(gN, N2);
       }
@@ -521,7 +541,7 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
                             b2 * gv.x, b2 * gv.y, b2 * gv.z};
         warp_groups_add_xyz3(wg, key, v, base, w0i, w1i, w2i);
       };
-      if (a.g_colors) scatter(a.g_colors, gT);
+      if (a.g_colors && !use_uv) scatter(a.g_colors, gT);
       if (LIT) {
         if (a.g_verts_world) scatter(a.g_verts_world, gP);
         if (a.g_normals) scatter(a.g_normals, gN);
@@ -642,8 +662,19 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
         const size_t r = (size_t)(vd.face_start + (int)(f - vd.p2f_base));
         i0 = __ldg(a.faces + 3 * r); i1 = __ldg(a.faces + 3 * r + 1); i2 = __ldg(a.faces + 3 * r + 2);
         b0 = a.bary[s * 3]; b1 = a.bary[s * 3 + 1]; b2 = a.bary[s * 3 + 2];
-        const F3 C0 = ld3(a.colors, i0), C1 = ld3(a.colors, i1), C2 = ld3(a.colors, i2);
-        const F3 tex = interp3(b0, b1, b2, C0, C1, C2);
+        const bool use_uv = a.uv.map != nullptr;
+        F3 C0 = {0, 0, 0}, C1 = C0, C2 = C0, tex, dtu = C0, dtv = C0;
+        F2 t0 = {0, 0}, t1 = t0, t2 = t0;
+        UvTap tap = {};
+        if (use_uv) {
+          t0 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r)); t1 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r + 1));
+          t2 = ld2(a.uv.verts_uvs, __ldg(a.uv.faces_uvs + 3 * r + 2));
+          tap = uv_tap(a.uv, b0 * t0.x + b1 * t1.x + b2 * t2.x, b0 * t0.y + b1 * t1.y + b2 * t2.y);
+          tex = uv_sample(a.uv, tap, &dtu, &dtv);
+        } else {
+          C0 = ld3(a.colors, i0); C1 = ld3(a.colors, i1); C2 = ld3(a.colors, i2);
+          tex = interp3(b0, b1, b2, C0, C1, C2);
+        }
         F3 X0 = {0, 0, 0}, X1 = X0, X2 = X0, N0 = X0, N1 = X0, N2 = X0, P = X0, nr = X0;
         if (LIGHT != TRB_LIGHT_AMBIENT) {
           X0 = ld3(a.verts_world, i0); X1 = ld3(a.verts_world, i1); X2 = ld3(a.verts_world, i2);
@@ -667,14 +698,21 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
         phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
         g_lv_acc.x += g_lv.x; g_lv_acc.y += g_lv.y; g_lv_acc.z += g_lv.z;
         g_cam_acc.x += g_cam.x; g_cam_acc.y += g_cam.y; g_cam_acc.z += g_cam.z;
-        float gb0 = dot3(gT, C0), gb1 = dot3(gT, C1), gb2 = dot3(gT, C2);
+        float gb0, gb1, gb2;
+        if (use_uv) {
+          const float gu = dot3(gT, dtu), gvv = dot3(gT, dtv);
+          gb0 = gu * t0.x + gvv * t0.y; gb1 = gu * t1.x + gvv * t1.y; gb2 = gu * t2.x + gvv * t2.y;
+          if (a.g_tex_map) uv_scatter(a.g_tex_map, tap, gT);
+        } else {
+          gb0 = dot3(gT, C0); gb1 = dot3(gT, C1); gb2 = dot3(gT, C2);
+        }
         if (LIGHT != TRB_LIGHT_AMBIENT) {
           gb0 += dot3(gP, X0) + dot3(gN, N0); gb1 += dot3(gP, X1) + dot3(gN, N1); gb2 += dot3(gP, X2) + dot3(gN, N2);
         }
         const float4 pk = make_float4(gb0, gb1, gb2, gdotc);
         if (K1) park1 = pk; else s_park[k * NT + tid] = pk;
       }
-      if (a.g_colors) scatter9(key, b0, b1, b2, gT, a.g_colors, i0, i1, i2);
+      if (a.g_colors && a.uv.map == nullptr) scatter9(key, b0, b1, b2, gT, a.g_colors, i0, i1, i2);
       if (LIGHT != TRB_LIGHT_AMBIENT) {
         if (a.g_verts_world) scatter9(key, b0, b1, b2, gP, a.g_verts_world, i0, i1, i2);
         if (a.g_normals) scatter9(key, b0, b1, b2, gN, a.g_normals, i0, i1, i2);
@@ -784,7 +822,8 @@ static int check_render_cfg(const trb_render_config* c) {
   if (s.N > 65535 || (int64_t)s.N * s.H * s.W >= 2147483647ll) return TRB_ERR_BAD_ARG;
   if (s.shader < -1 || s.shader > 2 || s.light_kind < 0 || s.light_kind > 2) return TRB_ERR_BAD_ARG;
   if (s.shader != TRB_SHADER_NONE && (!(s.sigma > 0.0f) || !(s.gamma > 0.0f))) return TRB_ERR_BAD_ARG;
-  if (s.shader >= 0 && s.shader != TRB_SHADER_SOFT_SILHOUETTE && s.texture_mode != TRB_TEX_VERTEX)
+  if (s.shader >= 0 && s.shader != TRB_SHADER_SOFT_SILHOUETTE && s.texture_mode != TRB_TEX_VERTEX &&
+      s.texture_mode != TRB_TEX_UV)
     return TRB_ERR_BAD_ARG;
   if (!(c->blur_radius >= 0.0f) || !(c->z_clip_value == c->z_clip_value) || c->max_face_count < 0 || c->max_vert_count < 0 || c->pair_capacity < 0 ||
       c->num_world_verts < 0 || c->num_faces < 0 || c->num_ndc_verts < 0)
@@ -874,8 +913,8 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
                                   const float* R, const float* T, const float* proj, float* view_params,
                                   float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
                                   float* zbuf, float* bary, float* dists, float* images, int32_t* tile_hit,
-                                  void* workspace, size_t workspace_bytes, int32_t* stats, int device,
-                                  trb_stream_t stream) {
+                                  void* workspace, size_t workspace_bytes, int32_t* stats,
+                                  const trb_uv_texture* uv, int device, trb_stream_t stream) {
   int rc = check_render_cfg(cfg);
   if (rc != TRB_OK) return rc;
   const trb_shade_config& sc = cfg->shade;
@@ -886,7 +925,11 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
     return TRB_ERR_BAD_ARG;
   if (cfg->max_face_count > 0 && (!verts_world || !faces)) return TRB_ERR_BAD_ARG;
   if (sc.shader != TRB_SHADER_NONE && !images) return TRB_ERR_BAD_ARG;
-  if (is_phong(sc.shader) && (!view_params || !vert_colors || !normals_raw || !normals)) return TRB_ERR_BAD_ARG;
+  const bool use_uv = is_phong(sc.shader) && sc.texture_mode == TRB_TEX_UV;
+  if (use_uv && (!uv || !uv->map || !uv->verts_uvs || !uv->faces_uvs || uv->map_h < 1 || uv->map_w < 1))
+    return TRB_ERR_BAD_ARG;
+  if (is_phong(sc.shader) && (!view_params || (!vert_colors && !use_uv) || !normals_raw || !normals))
+    return TRB_ERR_BAD_ARG;
   const TileGrid tg = make_tile_grid(H, W, K);
   const WsLayout ws = make_ws_layout(N, tg, cfg->pair_capacity);
   if (workspace_bytes < ws.total) return TRB_ERR_WORKSPACE;
@@ -913,6 +956,8 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
+  a.uv = {nullptr, nullptr, nullptr, 0, 0};
+  if (use_uv) a.uv = {uv->map, uv->verts_uvs, uv->faces_uvs, uv->map_h, uv->map_w};
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
   rc = launch_render_fine(sc.shader, sc.light_kind, N, st, a);
   if (rc != TRB_OK) return rc;
@@ -933,7 +978,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
                                    const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
                                    float* grad_verts_world, float* grad_vert_colors, float* grad_R,
                                    float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
-                                   int device, trb_stream_t stream) {
+                                   const trb_uv_texture* uv, int device, trb_stream_t stream) {
   int rc = check_render_cfg(cfg);
   if (rc != TRB_OK) return rc;
   const trb_shade_config& sc = cfg->shade;
@@ -945,7 +990,10 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   if (sc.shader != TRB_SHADER_NONE && !grad_images) return TRB_ERR_BAD_ARG;
   const bool phong = is_phong(sc.shader);
   const bool lit = phong && sc.light_kind != TRB_LIGHT_AMBIENT;
-  if (phong && (!view_params || !vert_colors)) return TRB_ERR_BAD_ARG;
+  const bool use_uv = phong && sc.texture_mode == TRB_TEX_UV;
+  if (use_uv && (!uv || !uv->map || !uv->verts_uvs || !uv->faces_uvs || uv->map_h < 1 || uv->map_w < 1))
+    return TRB_ERR_BAD_ARG;
+  if (phong && (!view_params || (!vert_colors && !use_uv))) return TRB_ERR_BAD_ARG;
   if (lit && (!normals_raw || !normals)) return TRB_ERR_BAD_ARG;
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -970,7 +1018,10 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   a.g_verts_ndc = geom ? g_ndc4 : nullptr;
   a.g_verts_world = (lit && grad_verts_world) ? g_world4 : nullptr;
   a.g_normals = (lit && grad_verts_world) ? g_norm4 : nullptr;
-  a.g_colors = (phong && grad_vert_colors) ? g_col4 : nullptr;
+  a.g_colors = (phong && grad_vert_colors && !use_uv) ? g_col4 : nullptr;
+  a.uv = {nullptr, nullptr, nullptr, 0, 0};
+  a.g_tex_map = nullptr;
+  if (use_uv) { a.uv = {uv->map, uv->verts_uvs, uv->faces_uvs, uv->map_h, uv->map_w}; a.g_tex_map = uv->grad_map; }
   a.g_view_params = lit ? g_vp : nullptr;
   a.want_light_grad = (lit && g_vp && cfg->want_light_grad) ? 1 : 0;
   a.want_cam_grad = (lit && g_vp && (cam_chain || cfg->want_light_grad)) ? 1 : 0;

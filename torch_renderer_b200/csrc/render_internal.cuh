@@ -15,6 +15,7 @@ struct FineArgs {
   const int* ws_header; const int* busy_tiles;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   float sigma, gamma, bg0, bg1, bg2;
+  UvTex uv;  // uv.map != nullptr: TexturesUV instead of per-vertex colours
 };
 
 // Appends the linear indices of the pixels of this CTA that got at least one face to the global
@@ -41,7 +42,7 @@ __device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int
 }
 
 struct ShadeIn {
-  const float* verts_world; const float* normals; const float* colors; const int* faces;
+  const float* verts_world; const float* normals; const float* colors; const int* faces; UvTex uv;
 };
 
 template <int LIGHT>
@@ -49,7 +50,15 @@ __device__ __forceinline__ F3 shade_sample(const ShadeIn& in, const trb_view& vd
                                            int local_face, float b0, float b1, float b2) {
   const size_t r = (size_t)(vd.face_start + local_face);
   const int i0 = __ldg(in.faces + 3 * r), i1 = __ldg(in.faces + 3 * r + 1), i2 = __ldg(in.faces + 3 * r + 2);
-  const F3 tex = interp3(b0, b1, b2, ld3(in.colors, i0), ld3(in.colors, i1), ld3(in.colors, i2));
+  F3 tex;
+  if (in.uv.map != nullptr) {
+    const F2 t0 = ld2(in.uv.verts_uvs, __ldg(in.uv.faces_uvs + 3 * r)), t1 = ld2(in.uv.verts_uvs, __ldg(in.uv.faces_uvs + 3 * r + 1)),
+             t2 = ld2(in.uv.verts_uvs, __ldg(in.uv.faces_uvs + 3 * r + 2));
+    const UvTap k = uv_tap(in.uv, b0 * t0.x + b1 * t1.x + b2 * t2.x, b0 * t0.y + b1 * t1.y + b2 * t2.y);
+    tex = uv_sample(in.uv, k, nullptr, nullptr);
+  } else {
+    tex = interp3(b0, b1, b2, ld3(in.colors, i0), ld3(in.colors, i1), ld3(in.colors, i2));
+  }
   if (LIGHT == TRB_LIGHT_AMBIENT) return {vp.amb[0] * tex.x, vp.amb[1] * tex.y, vp.amb[2] * tex.z};
   const F3 P = interp3(b0, b1, b2, ld3(in.verts_world, i0), ld3(in.verts_world, i1), ld3(in.verts_world, i2));
   const F3 nr = interp3(b0, b1, b2, ld3(in.normals, i0), ld3(in.normals, i1), ld3(in.normals, i2));

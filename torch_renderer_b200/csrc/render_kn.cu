@@ -405,7 +405,7 @@ render_fine_kn_kernel(const FineArgs a) {
   append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
 
   ViewParams vp;
-  const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces};
+  const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces, a.uv};
   if (SHADER == TRB_SHADER_SOFT_PHONG || SHADER == TRB_SHADER_HARD_PHONG) vp = load_view_params(a.view_params, n);
   const float eps = 1e-10f;
   // layers are sorted front to back, so the softmax's max z_inv belongs to layer 0

@@ -113,6 +113,88 @@ __device__ __forceinline__ void phong_color_bwd(const ViewParams& vp, F3 tex, co
   g_cam = g_vd;
 }
 
+// ---- TexturesUV (A7): bilinear lookup, align_corners=True, border padding, y-flipped map ---------------
+// What PyTorch3D expresses as grid_sample(flip(maps, H), 2*uv - 1, align_corners=True, padding_mode="border"):
+// column = u (Wt-1), row of the FLIPPED map = v (Ht-1), both clamped to the map; a clamped coordinate
+// has zero gradient.
+struct UvTex {
+  const float* map;        // f32 [Ht, Wt, 3]; nullptr = per-vertex colours
+  const float* verts_uvs;  // f32 [Vt, 2]
+  const int* faces_uvs;    // i32 [F, 3]
+  int h, w;
+};
+
+struct UvTap {
+  int o00, o01, o10, o11;      // element offsets of the four texels (x3 channels), -1 = outside the map
+  float w00, w01, w10, w11;
+  float wx, wy, du, dv;        // fractions; d(column)/du and d(flipped row)/dv (0 when clamped)
+};
+
+__device__ __forceinline__ UvTap uv_tap(const UvTex& t, float u, float v) {
+  UvTap k;
+  const float xmax = (float)(t.w - 1), ymax = (float)(t.h - 1);
+  float ix = u * xmax, iy = v * ymax;
+  k.du = (ix > 0.0f && ix < xmax) ? xmax : 0.0f;
+  k.dv = (iy > 0.0f && iy < ymax) ? ymax : 0.0f;
+  ix = fminf(fmaxf(ix, 0.0f), xmax);
+  iy = fminf(fmaxf(iy, 0.0f), ymax);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  k.wx = ix - fx; k.wy = iy - fy;
+  k.w00 = (1.0f - k.wx) * (1.0f - k.wy); k.w01 = k.wx * (1.0f - k.wy);
+  k.w10 = (1.0f - k.wx) * k.wy; k.w11 = k.wx * k.wy;
+  const bool xin = x1 < t.w, yin = y1 < t.h;
+  const int r0 = t.h - 1 - y0, r1 = t.h - 1 - y1;  // rows of the stored (un-flipped) map
+  k.o00 = 3 * (r0 * t.w + x0);
+  k.o01 = xin ? 3 * (r0 * t.w + x1) : -1;
+  k.o10 = yin ? 3 * (r1 * t.w + x0) : -1;
+  k.o11 = (xin && yin) ? 3 * (r1 * t.w + x1) : -1;
+  return k;
+}
+
+__device__ __forceinline__ F3 uv_ld(const float* __restrict__ m, int o) {
+  if (o < 0) return {0.0f, 0.0f, 0.0f};
+  return {__ldg(m + o), __ldg(m + o + 1), __ldg(m + o + 2)};
+}
+
+// texel = sum_ij w_ij M_ij; optionally d texel / du and d texel / dv
+__device__ __forceinline__ F3 uv_sample(const UvTex& t, const UvTap& k, F3* d_du, F3* d_dv) {
+  const F3 a = uv_ld(t.map, k.o00), b = uv_ld(t.map, k.o01), c = uv_ld(t.map, k.o10), d = uv_ld(t.map, k.o11);
+  if (d_du) {
+    const float s = k.du, q = 1.0f - k.wy;
+    *d_du = {s * (q * (b.x - a.x) + k.wy * (d.x - c.x)), s * (q * (b.y - a.y) + k.wy * (d.y - c.y)),
+             s * (q * (b.z - a.z) + k.wy * (d.z - c.z))};
+  }
+  if (d_dv) {
+    const float s = k.dv, q = 1.0f - k.wx;
+    *d_dv = {s * (q * (c.x - a.x) + k.wx * (d.x - b.x)), s * (q * (c.y - a.y) + k.wx * (d.y - b.y)),
+             s * (q * (c.z - a.z) + k.wx * (d.z - b.z))};
+  }
+  return {k.w00 * a.x + k.w01 * b.x + k.w10 * c.x + k.w11 * d.x,
+          k.w00 * a.y + k.w01 * b.y + k.w10 * c.y + k.w11 * d.y,
+          k.w00 * a.z + k.w01 * b.z + k.w10 * c.z + k.w11 * d.z};
+}
+
+// scatter of d loss / d texel into the gradient of the map
+__device__ __forceinline__ void uv_scatter(float* __restrict__ g_map, const UvTap& k, F3 g) {
+  const int o[4] = {k.o00, k.o01, k.o10, k.o11};
+  const float w[4] = {k.w00, k.w01, k.w10, k.w11};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (o[i] < 0 || w[i] == 0.0f) continue;
+    atomicAdd(g_map + o[i], w[i] * g.x); atomicAdd(g_map + o[i] + 1, w[i] * g.y);
+    atomicAdd(g_map + o[i] + 2, w[i] * g.z);
+  }
+}
+
+struct F2 {
+  float x, y;
+};
+__device__ __forceinline__ F2 ld2(const float* __restrict__ p, int i) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p) + i);
+  return {v.x, v.y};
+}
+
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 struct FaceIds {

@@ -410,12 +410,13 @@ class _RenderFn(torch.autograd.Function):
     rasterisation + shading epilogue) and one backward.  ``spec`` carries the static configuration."""
 
     @staticmethod
-    def forward(ctx, verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
+    def forward(ctx, verts, colors, tex_map, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
         _require_cuda(verts, "render")
         dev = verts.device
         L = _lib.lib()
         verts, R, T, proj = _f32c(verts), _f32c(R), _f32c(T), _f32c(proj)
         colors = None if colors is None else _f32c(colors)
+        tex_map = None if tex_map is None else _f32c(tex_map)
         # the kernel may write the camera centres into the block: never alias a cached tensor
         vp = None if view_params is None else _f32c(view_params).clone()
         N, (H, W), K = table.N, spec["image_size"], spec["K"]
@@ -423,7 +424,13 @@ class _RenderFn(torch.autograd.Function):
         cfg = _lib.RenderConfig()
         sc = cfg.shade
         sc.N, sc.H, sc.W, sc.K = N, H, W, K
-        sc.shader, sc.light_kind, sc.texture_mode = shader, spec["light_kind"], _lib.TEX_VERTEX
+        sc.shader, sc.light_kind = shader, spec["light_kind"]
+        sc.texture_mode = _lib.TEX_UV if tex_map is not None else _lib.TEX_VERTEX
+        uv = None
+        if tex_map is not None:
+            verts_uvs, faces_uvs = spec["uv"]
+            uv = _lib.UvTexture(tex_map.data_ptr(), verts_uvs.data_ptr(), faces_uvs.data_ptr(), 0,
+                                tex_map.shape[0], tex_map.shape[1])
         sc.sigma, sc.gamma = spec["sigma"], spec["gamma"]
         sc.background[0], sc.background[1], sc.background[2] = spec["background"]
         cfg.blur_radius, cfg.raster_flags = spec["blur_radius"], spec["flags"]
@@ -468,7 +475,8 @@ class _RenderFn(torch.autograd.Function):
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
                 _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, _ptr(p2f), _ptr(zbuf),
                 _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), p_hit,
-                p_ws, ws_bytes.value, p_stats, dev.index, _stream(dev)), "render")
+                p_ws, ws_bytes.value, p_stats, None if uv is None else ctypes.byref(uv), dev.index,
+                _stream(dev)), "render")
         _bump(5 + (1 if want_stats else 0))  # prep, count, alloc, fill, fine (+ stats)
         if want_stats:
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
@@ -476,7 +484,8 @@ class _RenderFn(torch.autograd.Function):
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             table._pending = (host_stats, ev)
-        ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists)
+        ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists, tex_map,
+                              *(spec["uv"] if tex_map is not None else ()))
         ctx.aux_offsets = (offs[1], offs[2], offs[3], offs[4], phong)
         ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch.value
         ctx.token = spec.get("_token")   # Fragments cache: set once a backward has consumed this graph
@@ -486,7 +495,7 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists):
-        verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists = ctx.saved_tensors
+        verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists, tex_map = ctx.saved_tensors[:13]
         o_ndc, o_nraw, o_nrm, o_hit, phong = ctx.aux_offsets
         base = aux.data_ptr()
         p_ndc, p_hit = base + o_ndc, base + o_hit
@@ -495,7 +504,8 @@ class _RenderFn(torch.autograd.Function):
         if ctx.token is not None:
             ctx.token["consumed"] = True
         dev = verts.device
-        need = ctx.needs_input_grad  # verts, colors, R, T, proj, view_params
+        need = list(ctx.needs_input_grad)  # verts, colors, tex_map, R, T, proj, view_params
+        need_tex = need.pop(2)
         N, V = table.N, verts.shape[0]
         shader = cfg.shade.shader
         if shader != _lib.SHADER_NONE and g_images is None:
@@ -503,11 +513,17 @@ class _RenderFn(torch.autograd.Function):
         # one zero-filled buffer for every accumulated gradient
         # ... and for the kernel's float4 accumulators (16-byte aligned: the scratch block comes first)
         n_scratch = (max(ctx.n_scratch, 1) + 3) // 4 * 4
-        sizes = [n_scratch, V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE]
+        n_tex = tex_map.numel() if (tex_map is not None and need_tex) else 0
+        sizes = [n_scratch, V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE, n_tex]
         flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
         parts = list(flat.split(sizes))
-        scratch, g_verts, g_cols, g_R, g_T, g_proj, g_vp = parts
+        scratch, g_verts, g_cols, g_R, g_T, g_proj, g_vp, g_tex = parts
         cfg.scratch_is_zeroed = 1
+        uv = None
+        if tex_map is not None:
+            verts_uvs, faces_uvs = ctx.saved_tensors[13:15]
+            uv = _lib.UvTexture(tex_map.data_ptr(), verts_uvs.data_ptr(), faces_uvs.data_ptr(),
+                                g_tex.data_ptr() if n_tex else 0, tex_map.shape[0], tex_map.shape[1])
         f32 = lambda t: None if t is None else _f32c(t)
         want_vp = vp is not None
         with _timed("render_backward", dev):
@@ -518,17 +534,20 @@ class _RenderFn(torch.autograd.Function):
                 _ptr(f32(g_zbuf)), _ptr(f32(g_bary)), _ptr(f32(g_dists)),
                 _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
                 _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),
-                _ptr(g_vp if want_vp else None), _ptr(scratch), dev.index, _stream(dev)), "render backward")
+                _ptr(g_vp if want_vp else None), _ptr(scratch), None if uv is None else ctypes.byref(uv),
+                dev.index, _stream(dev)), "render backward")
         _bump(2)  # fused backward, post
         return (g_verts.view(V, 3) if need[0] else None,
                 g_cols.view(V, 3) if (need[1] and colors is not None) else None,
+                g_tex.view(tex_map.shape) if n_tex else None,
                 g_R.view(N, 3, 3) if need[2] else None, g_T.view(N, 3) if need[3] else None,
                 g_proj.view(N, 4) if need[4] else None,
                 g_vp.view(N, _lib.VIEW_PARAM_STRIDE) if (need[5] and want_vp) else None, None, None, None)
 
 
-def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict):
-    """Returns (images [N,H,W,4] or empty, pix_to_face, zbuf, bary, dists)."""
+def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict, tex_map=None):
+    """Returns (images [N,H,W,4] or empty, pix_to_face, zbuf, bary, dists).  With ``tex_map`` (f32 [Ht,Wt,3])
+    the texture is a UV map sampled in the kernels; ``spec["uv"]`` = (verts_uvs f32 [Vt,2], faces_uvs i32 [F,3])."""
     if spec["K"] > _lib.MAX_FACES_PER_PIXEL:
         raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
-    return _RenderFn.apply(verts, colors, R, T, proj, view_params, faces, table, spec)
+    return _RenderFn.apply(verts, colors, tex_map, R, T, proj, view_params, faces, table, spec)

@@ -223,16 +223,23 @@ class MeshRenderer(nn.Module):
         blend_params = kwargs.get("blend_params", shader.blend_params)
         from_rt = False
         phong = kind != _lib.SHADER_SOFT_SILHOUETTE
+        tex_map = uv = None
         if phong:
             textures = meshes_world.textures
-            if not isinstance(textures, TexturesVertex):
-                return None
-            shared = table.shared_mesh and textures._replicas == table.N
-            if table.shared_mesh and not shared:
-                return None
-            colors = textures._unique_features(shared)
-            if colors.shape[-1] != 3 or colors.shape[0] != meshes_world._unique_verts().shape[0]:
-                return None
+            if isinstance(textures, TexturesVertex):
+                shared = table.shared_mesh and textures._replicas == table.N
+                if table.shared_mesh and not shared:
+                    return None
+                colors = textures._unique_features(shared)
+                if colors.shape[-1] != 3 or colors.shape[0] != meshes_world._unique_verts().shape[0]:
+                    return None
+            else:
+                # TexturesUV sampled inside the kernels: one mesh (or one mesh extended to N views) with ONE map
+                fused_uv = getattr(textures, "_fused_inputs", None)
+                got = None if fused_uv is None else fused_uv(table, meshes_world.faces_packed_i32())
+                if got is None:
+                    return None
+                tex_map, uv = got
         cameras, R, T, proj, spec = rast._resolve(meshes_world, kwargs)   # also stores R, T on `cameras`
         if phong:
             shader_cameras = shader._get_cameras(**kwargs)
@@ -258,10 +265,13 @@ class MeshRenderer(nn.Module):
         bg = blend_params.background_color
         bg = tuple(float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg))
         token = {"consumed": False}
+        if uv is not None:
+            spec["uv"] = uv
         spec.update(_token=token, shader=kind, light_kind=light_kind, sigma=float(blend_params.sigma),
                     gamma=float(blend_params.gamma), background=bg, camera_center_from_rt=from_rt)
         images, p2f, zbuf, bary, dists = ops.render(
-            meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec)
+            meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec,
+            tex_map=tex_map)
         fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
         _fragment_cache.store(key, tensors, fragments, token)
         return images, fragments

@@ -172,6 +172,32 @@ class TexturesUV:
             maps += t._maps; fu += t._faces_uvs; vu += t._verts_uvs
         return self._clone_with(maps, fu, vu)
 
+    def _fused_inputs(self, table, faces_i32):
+        """(map f32 [Ht,Wt,3], (verts_uvs f32 [Vt,2], faces_uvs i32 [F,3])) when the fused kernels can sample this
+        texture themselves -- one mesh, or one mesh extended to N views, with a single RGB map, bilinear /
+        align_corners / border (the defaults the reference uses) -- else None (-> sample_textures + texels)."""
+        if (self.sampling_mode != "bilinear" or not self.align_corners or self.padding_mode != "border"
+                or self._N == 0):
+            return None
+        m0, f0, v0 = self._maps[0], self._faces_uvs[0], self._verts_uvs[0]
+        if self._N > 1 and not (table.shared_mesh and all(m is m0 for m in self._maps)
+                                and all(f is f0 for f in self._faces_uvs) and all(v is v0 for v in self._verts_uvs)):
+            return None
+        if self._N != table.N and self._N != 1:
+            return None
+        if self._N == 1 and table.N != 1:
+            return None
+        if m0.dim() != 3 or m0.shape[-1] != 3 or not m0.is_cuda or f0.shape[0] != faces_i32.shape[0]:
+            return None
+        cache = self.__dict__.get("_fused_cache")
+        key = (id(f0), id(v0), v0._version)
+        if cache is None or cache[0] != key:
+            cache = (key, f0.to(torch.int32).contiguous(), v0.detach().float().contiguous())
+            self.__dict__["_fused_cache"] = cache
+        if v0.requires_grad:
+            return None   # gradients w.r.t. the UV coordinates go through the composed path
+        return m0, (cache[2], cache[1])
+
     def sample_textures(self, fragments, faces_packed=None) -> torch.Tensor:
         """(N,H,W,K,C): interpolate UVs (CUDA kernel), then bilinear lookup in the y-flipped map
         with ``align_corners=True`` and border padding (A7)."""

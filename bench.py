@@ -317,6 +317,12 @@ def run_ours(args):
     h2d = sum(h.numel() * 4 for h in host)
     d2h = 4 + sum(h.numel() * 4 for h in host_out)
 
+    from torch_renderer_b200 import parallel as _par
+    peer = [v for v in _par._peer_allreduce.values() if v not in (None, False)]
+    for v in peer:
+        v.check()   # no rank missed a flag barrier
+    collective = "none" if world == 1 else ("peer-memory one-shot kernel (csrc/allreduce.cu)" if peer else "nccl all-reduce")
+
     cpu = cpu_baseline(sample_views=args.cpu_views) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
@@ -327,6 +333,7 @@ def run_ours(args):
             "(tests/golden/meshes.npz), random vertex colours, seed 0",
             "config": {"workload": WORKLOAD, "views_per_gpu": N, "image": [H, W], "faces_per_pixel": K,
                        "parallelism": f"view-sharded x{world}, mesh replicated, 1 fused allreduce of shared grads",
+                       "collective": collective,
                        "l2_policy": "inputs larger than L2: Fragments + images + their grads = 1.2 GB per step vs 126 MB L2",
                        "launch_mode": mode_device, "e2e_launch_mode": mode_e2e},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -271,6 +271,20 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         float* grad_proj, float* grad_view_params, float* scratch,
                         const trb_uv_texture* host_uv, int device, trb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: one-shot sum all-reduce of the view-shared gradients over peer memory.
+ * The reference has no distributed path (every script pins cuda:0); the view batch is sharded over the GPUs of
+ * one box and this is the step's only exchange.  host_segments[i] / host_counts[i]: up to 4 local f32 buffers,
+ * reduced in place (sum over ranks, rank order).  host_peer_inbox[r] (r < world): this process's mapping of
+ * rank r's inbox, 2 * world * capacity_floats 8-byte words, zero-initialised once with all ranks synchronised
+ * before the first call (e.g. torch symmetric memory).  epochs u32[trb_allreduce_grid(capacity_floats)]
+ * (device, local, zero-initialised once): per-block call counters.  error_flag i32[1] (device) is set when a
+ * peer's data did not arrive within the spin limit.  Every rank must call with the same segment layout. */
+int trb_allreduce_grid(int64_t capacity_floats);
+int trb_allreduce_sum_f32(float* const* host_segments, const int64_t* host_counts, int num_segments,
+                          void* const* host_peer_inbox, int64_t capacity_floats, int rank, int world,
+                          uint32_t* epochs, int32_t* error_flag, int device, trb_stream_t stream);
+
 /* Measurement hook (bench.py's roofline leg): when non-NULL, the four cudaEvent_t handles are
  * recorded on the call's stream immediately before / after the dominant kernel of
  * trb_render_forward (the fused fine pass) and of trb_render_backward (the fused backward).

@@ -3,15 +3,17 @@
 Views are independent in the forward pass, so every rank renders a contiguous slice of the camera
 batch against a replicated mesh with no data-path collective.  The backward needs exactly one
 exchange: parameters shared by all views (vertices, vertex colours / texture map, a shared pose)
-receive per-rank partial gradients that are summed with ONE NCCL all-reduce over a single fused
-fp32 buffer (35 KB for the cow .. 12 MB for a 1M-face mesh -- latency regime on NVLink 5 / NVSwitch,
-so one launch per step instead of one per tensor).  Per-view camera gradients stay local.
+receive per-rank partial gradients that are summed in ONE kernel over NVLink / NVSwitch peer memory
+(``PeerAllReduce`` -> csrc/allreduce.cu: stage, flag barrier, sum the peers' buffers; 35 KB for the cow ..
+12 MB for a 1M-face mesh -- latency regime), with a single fused NCCL all-reduce as the fallback when
+symmetric memory is not available (and on CPU / gloo).  Per-view camera gradients stay local.
 
 The reference has no distributed path at all (every script pins cuda:0); this is the
 B200-native addition BASELINE.json's north_star asks for.
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -42,6 +44,75 @@ def max_views_for_memory(H: int, W: int, K: int, budget_bytes: int, with_grad: b
     return max(1, budget_bytes // per_view)
 
 
+class PeerAllReduce:
+    """One-shot sum all-reduce over NVLink / NVSwitch peer memory (``trb_allreduce_sum_f32``, csrc/allreduce.cu).
+
+    Allocates an inbox in torch symmetric memory (every rank maps every peer's copy) once per (group,
+    capacity); each call is ONE kernel: every rank pushes its values, tagged with the call's epoch, into all
+    peers' inboxes and sums what arrives in its own.  Raises at construction when symmetric memory is
+    unavailable (the caller falls back to NCCL)."""
+
+    MAX_FLOATS = 1 << 16   # 256 KB messages; larger sums are bandwidth- not latency-bound: NCCL
+
+    def __init__(self, capacity_floats: int, device: torch.device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._ctypes, self._lib = ctypes, _lib
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self.capacity = (int(capacity_floats) + 1023) // 1024 * 1024
+        self.buf = symm_mem.empty(2 * self.world * self.capacity * 2, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group=group)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every inbox is zero (epoch 0) before anyone pushes
+        self.peer_inbox = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epochs = torch.zeros(_lib.lib().trb_allreduce_grid(self.capacity), dtype=torch.int32, device=device)
+
+    def __call__(self, grads: Sequence[torch.Tensor]) -> None:
+        ctypes, _lib = self._ctypes, self._lib
+        n = len(grads)
+        if n > 4 or sum(g.numel() for g in grads) > self.capacity:
+            raise ValueError("PeerAllReduce: too many / too large segments for this inbox")
+        if any(g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+            raise ValueError("PeerAllReduce: segments must be contiguous float32")
+        seg = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads])
+        cnt = (ctypes.c_int64 * n)(*[g.numel() for g in grads])
+        _lib.check(_lib.lib().trb_allreduce_sum_f32(
+            seg, cnt, n, self.peer_inbox, self.capacity, self.rank, self.world, self.epochs.data_ptr(),
+            self.error.data_ptr(), self.device.index, torch._C._cuda_getCurrentRawStream(self.device.index)),
+            "peer all-reduce")
+
+    def check(self) -> None:
+        """Raises if a peer's data did not arrive (synchronises; call outside timed regions)."""
+        if int(self.error.item()) != 0:
+            raise RuntimeError("PeerAllReduce: a peer's contribution did not arrive within the spin limit")
+
+
+_peer_allreduce = {}
+
+
+def _get_peer_allreduce(n_floats: int, device: torch.device, group):
+    """The cached PeerAllReduce for this (group, device), grown when needed; None when peer memory is not usable."""
+    key = (id(group), str(device))
+    cur = _peer_allreduce.get(key)
+    if cur is False:
+        return None
+    if n_floats > PeerAllReduce.MAX_FLOATS:
+        return None
+    if cur is None:
+        try:
+            cur = PeerAllReduce(PeerAllReduce.MAX_FLOATS, device, group)
+        except Exception:  # noqa: BLE001 -- no symmetric memory / no P2P: NCCL does it
+            _peer_allreduce[key] = False
+            return None
+        _peer_allreduce[key] = cur
+    return cur
+
+
 def allreduce_shared_grads(tensors: Sequence[Optional[torch.Tensor]], group=None, async_op: bool = False):
     """Sums the gradients of view-shared parameters across ranks with ONE all-reduce.
 
@@ -51,6 +122,14 @@ def allreduce_shared_grads(tensors: Sequence[Optional[torch.Tensor]], group=None
     grads = [t for t in tensors if t is not None]
     if not grads or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
+    # CUDA tensors on an NCCL group: the one-kernel peer-memory path (latency regime: 70 KB .. a few MB)
+    if (not async_op and len(grads) <= 4 and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()
+                                                 for g in grads)
+            and dist.get_backend(group) == "nccl" and not os.environ.get("TRB_NCCL_ALLREDUCE")):
+        peer = _get_peer_allreduce(sum(g.numel() for g in grads), grads[0].device, group)
+        if peer is not None:
+            peer(grads)
+            return None
     flat = torch.cat([g.reshape(-1).float() for g in grads])
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 

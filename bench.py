@@ -188,23 +188,26 @@ def run_ours(args):
         core_device()
         allreduce_shared_grads([verts.grad, cols.grad])
 
-    # pinned host buffers for the end-to-end leg: inputs in, gradients + a scalar metric out
-    host = [t.detach().cpu().pin_memory() for t in params]
-    host_out = [torch.empty_like(h).pin_memory() for h in host]
-    metric_host = torch.empty((), dtype=torch.float32).pin_memory()
+    # pinned host buffers for the end-to-end leg: ONE packed buffer each way (inputs in; gradients + metric out)
+    sizes = [t.numel() for t in params]
+    host_in = torch.cat([t.detach().reshape(-1).cpu() for t in params]).pin_memory()
+    dev_in = torch.empty_like(host_in, device=dev)
+    host_out = torch.empty(sum(sizes) + 1, dtype=torch.float32).pin_memory()
+    dev_out = torch.empty(sum(sizes) + 1, dtype=torch.float32, device=dev)
 
     def core_e2e():             # H2D of this step's inputs + forward + backward + metric
-        for p, h in zip(params, host):
+        dev_in.copy_(host_in, non_blocking=True)
+        for p, chunk in zip(params, dev_in.split(sizes)):
             p.grad = None
-            p.data.copy_(h, non_blocking=True)
+            p.data.copy_(chunk.view_as(p))
         images = renderer(meshes, R=Rd, T=Td)
         images.backward(grad_img)
-        # the step's result read back by the host: mean alpha (silhouette coverage)
-        metric_host.copy_(images.detach()[..., 3].mean(), non_blocking=True)
+        # the step's result read back by the host: mean alpha (silhouette coverage) ...
+        dev_out[-1:].copy_(images.detach()[..., 3].mean().reshape(1))
 
-    def readback_e2e():         # ... and every gradient
-        for p, o in zip(params, host_out):
-            o.copy_(p.grad, non_blocking=True)
+    def readback_e2e():         # ... and every gradient (after the all-reduce of the shared ones)
+        torch.cat([p.grad.reshape(-1) for p in params], out=dev_out[:-1])
+        host_out.copy_(dev_out, non_blocking=True)
 
     def graphed(fn):
         """Captures one step (forward + backward [+ copies]) into a CUDA graph; eager on failure."""
@@ -304,18 +307,26 @@ def run_ours(args):
 
     # end-to-end through the public API with host buffers
     core_e2e_run, mode_e2e = graphed(core_e2e)
+    if world == 1:
+        def whole_e2e():
+            core_e2e()
+            readback_e2e()
+        whole_run, mode_e2e = graphed(whole_e2e)
+        run_e2e = whole_run
+    else:
+        readback_run, _ = graphed(readback_e2e)
 
-    def run_e2e():
-        core_e2e_run()
-        allreduce_shared_grads([verts.grad, cols.grad])
-        readback_e2e()
+        def run_e2e():
+            core_e2e_run()
+            allreduce_shared_grads([verts.grad, cols.grad])
+            readback_run()
 
     for _ in range(max(3, args.warmup)):
         run_e2e()
     ms_e2e = timed(run_e2e, args.steps) / args.steps
     e2e_value = world * N / (ms_e2e / 1e3)
-    h2d = sum(h.numel() * 4 for h in host)
-    d2h = 4 + sum(h.numel() * 4 for h in host_out)
+    h2d = host_in.numel() * 4
+    d2h = host_out.numel() * 4
 
     from torch_renderer_b200 import parallel as _par
     peer = [v for v in _par._peer_allreduce.values() if v not in (None, False)]

@@ -11,7 +11,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtrb.so")
+# TRB_LIB_PATH selects another build of the same ABI (same-box A/B of kernel variants: profiles/ab_run.sh)
+LIB_PATH = os.environ.get("TRB_LIB_PATH") or os.path.join(_PKG, "libtrb.so")
 
 TRB_OK, TRB_ERR_BAD_ARG, TRB_ERR_K_TOO_LARGE, TRB_ERR_WORKSPACE, TRB_ERR_CUDA = range(5)
 

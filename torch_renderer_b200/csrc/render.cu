@@ -130,9 +130,12 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 // (one tile per CTA bound the kernel by CTA turnover x the latency of the list-length load;
 // rasterising the strip's own tiles serialised the 4-8 neighbouring busy tiles of an object in one CTA).
 constexpr int kStrip = 8;
+#ifndef TRB_K1_CTAS
+#define TRB_K1_CTAS 4   // 64 registers: 4 x 256 threads per SM (same-box A/B: 3 -> 4 CTAs: fine 0.160 -> 0.147 ms)
+#endif
 
 template <int SHADER, int LIGHT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, TRB_K1_CTAS)
 render_fine_k1_kernel(const FineArgs a) {
   pdl_wait();
   const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * kStrip;

@@ -36,6 +36,11 @@ __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
   return ((unsigned long long)zb << 32) | (unsigned)f;
 }
 
+#ifndef TRB_K1_STRIP
+#define TRB_K1_STRIP 8
+#endif
+constexpr int kStrip = TRB_K1_STRIP;  // tiles per CTA strip
+
 // Background of one tile whose face list is empty: a pure streaming store of -1 Fragments and
 // the background colour.
 template <int SHADER>
@@ -92,30 +97,32 @@ __device__ __forceinline__ void fill_empty_strip_v4(const FineArgs& a, int n, in
   const size_t W = a.W;
   const size_t pix0 = ((size_t)n * a.H + tby * 16) * W + tbx0 * 16;
   const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+  constexpr int ZW = kStrip * 4, PW = kStrip * 8, BW = kStrip * 12, IW = kStrip * 16;  // 16-byte words per row
+  static_assert(kStrip % 4 == 0, "the strip fill deals whole rounds of 256 stores");
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {   // zbuf, dists: 16 rows x 32
+  for (int j = 0; j < kStrip / 4; ++j) {       // zbuf, dists: 16 rows x ZW
     const int i = tid + 256 * j;
-    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (i >> 5) * W) + (i & 31), m4);
-    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i >> 5) * W) + (i & 31), m4);
+    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (i / ZW) * W) + (i % ZW), m4);
+    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i / ZW) * W) + (i % ZW), m4);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {   // pix_to_face: 16 rows x 64
+  for (int j = 0; j < kStrip / 2; ++j) {       // pix_to_face: 16 rows x PW
     const int i = tid + 256 * j;
-    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i >> 6) * W) + (i & 63), make_longlong2(-1ll, -1ll));
+    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i / PW) * W) + (i % PW), make_longlong2(-1ll, -1ll));
   }
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {   // barycentrics: 16 rows x 96
+  for (int j = 0; j < kStrip * 3 / 4; ++j) {   // barycentrics: 16 rows x BW
     const int i = tid + 256 * j;
-    const int r = i / 96, c = i - r * 96;
+    const int r = i / BW, c = i - r * BW;
     st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
   }
   if (SHADER == TRB_SHADER_NONE) return;
   const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
                                                             : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {   // RGBA: 16 rows x 128
+  for (int j = 0; j < kStrip; ++j) {           // RGBA: 16 rows x IW
     const int i = tid + 256 * j;
-    st_cs(reinterpret_cast<float4*>(a.images) + pix0 + (i >> 7) * W + (i & 127), bgv);
+    st_cs(reinterpret_cast<float4*>(a.images) + pix0 + (i / IW) * W + (i % IW), bgv);
   }
 }
 
@@ -129,7 +136,6 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 // resident CTAs is doing latency-bound raster work while the rest keeps the HBM write stream busy
 // (one tile per CTA bound the kernel by CTA turnover x the latency of the list-length load;
 // rasterising the strip's own tiles serialised the 4-8 neighbouring busy tiles of an object in one CTA).
-constexpr int kStrip = 8;
 #ifndef TRB_K1_CTAS
 #define TRB_K1_CTAS 4   // 64 registers: 4 x 256 threads per SM (same-box A/B: 3 -> 4 CTAs: fine 0.160 -> 0.147 ms)
 #endif
@@ -415,8 +421,11 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
 template <bool K1, int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
 
+#ifndef TRB_BWD_CTAS
+#define TRB_BWD_CTAS 4
+#endif
 template <bool K1, int SHADER, int LIGHT>
-__global__ void __launch_bounds__(128, K1 ? 4 : 1)
+__global__ void __launch_bounds__(128, K1 ? TRB_BWD_CTAS : 1)
 render_backward_kernel(const BwdArgs a) {
   pdl_wait();
   extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
@@ -1033,7 +1042,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   // block size: the K>1 Phong path parks 16 B per (layer, thread) in shared memory
   const int nt = (K == 1 || !phong) ? 128 : (K <= 24 ? 128 : (K <= 100 ? 64 : 32));
   const size_t dyn = (K > 1 && phong) ? (size_t)K * nt * 16 : 0;
-  const dim3 grid(kNumSMs * (512 / nt));
+  const dim3 grid(kNumSMs * (K == 1 ? TRB_BWD_CTAS : 512 / nt));
   if (g_dbg_events[2]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[2], st));
   if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
   else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, dyn, st, a);

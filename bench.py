@@ -369,9 +369,9 @@ def run_ours(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
 # filled in after each profiling pass, None until a capture of that kernel exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r01_ncu_full_v7.txt (ncu --set full, one launch each, 64 views of C2)
-    "render_fine_kernel": 701_876_992,      # 4.52 MB read + 697.35 MB written (algorithmic: 751.7 MB)
-    "render_backward_kernel": 22_633_728,   # only covered pixels (6% of the image) are re-read
+    # profiles/r01_ncu_full_v11.txt (ncu --set full, one launch each, 64 views of C2)
+    "render_fine_kernel": 695_949_824,      # 6.06 MB read + 689.88 MB written (algorithmic: 751.7 MB)
+    "render_backward_kernel": 22_641_152,   # only covered pixels (1.9% of the image) are re-read
 }
 
 

@@ -206,3 +206,28 @@ def test_compat_alias_keeps_reference_import_lines_working():
         "try:\n    Pointclouds()\nexcept NotImplementedError:\n    print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_allreduce_and_uv_entry_points_reject_bad_arguments_without_gpu():
+    """The argument checks of the newer entry points run before any CUDA call."""
+    L = _lib.lib()
+    assert L.trb_allreduce_grid(1) == 1 and L.trb_allreduce_grid(1 << 16) == 64
+    seg = (ctypes.c_void_p * 1)(8)
+    cnt = (ctypes.c_int64 * 1)(4)
+    inbox = (ctypes.c_void_p * 2)(16, 32)
+    ok_tail = (1 << 16, 0, 2, 64, 128, 0, None)
+    assert L.trb_allreduce_sum_f32(seg, cnt, 5, inbox, *ok_tail) == _lib.TRB_ERR_BAD_ARG      # > 4 segments
+    assert L.trb_allreduce_sum_f32(seg, cnt, 1, inbox, 1 << 16, 2, 2, 64, 128, 0, None) == _lib.TRB_ERR_BAD_ARG  # rank >= world
+    assert L.trb_allreduce_sum_f32(seg, cnt, 1, inbox, 2, 0, 2, 64, 128, 0, None) == _lib.TRB_ERR_BAD_ARG  # total > capacity
+    assert L.trb_allreduce_sum_f32(seg, cnt, 1, None, *ok_tail) == _lib.TRB_ERR_BAD_ARG        # no inboxes
+    # fused render with texture_mode UV but no trb_uv_texture
+    cfg = _lib.RenderConfig()
+    cfg.shade.N, cfg.shade.H, cfg.shade.W, cfg.shade.K = 1, 8, 8, 1
+    cfg.shade.shader, cfg.shade.light_kind, cfg.shade.texture_mode = _lib.SHADER_SOFT_PHONG, 1, _lib.TEX_UV
+    cfg.shade.sigma = cfg.shade.gamma = 1e-4
+    cfg.max_face_count = cfg.max_vert_count = 1
+    args = [8] * 18
+    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    cfg.shade.texture_mode = 7
+    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_abi_struct_size(3) == ctypes.sizeof(_lib.UvTexture)

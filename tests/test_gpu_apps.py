@@ -1,0 +1,153 @@
+"""Application-level GPU tests: the optimisation loops the reference scripts run, end to end through the public
+API, judged by whether they converge (camera_pose_optimizer.py:237-330 -- pose from silhouette + depth + colour;
+mesh_deformer.py:181-222 -- per-vertex colours from multi-view images; deform_mesh_from_pcd.py / mesh_deformer.py
+-- vertex offsets from silhouettes).  They exercise forward + backward of every fused kernel together with
+autograd, the Fragments cache, TexturesUV and per-call camera overrides the way a user of the reference would."""
+import math
+
+import pytest
+import torch
+
+from helpers import cow_uvs, load_mesh, normalize_mesh
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+SIGMA = 1e-4
+BLUR = math.log(1.0 / 1e-4 - 1.0) * SIGMA
+
+
+def _trb():
+    import torch_renderer_b200 as trb
+    return trb
+
+
+def test_camera_pose_optimisation_converges():
+    """Pose = (T, quaternion) optimised against silhouette + depth + colour references of the UV-textured cow."""
+    trb = _trb()
+    trb.set_fragment_cache(True)   # the three renders of a step share one rasterisation, as in the reference
+    torch.manual_seed(0)
+    v, f = load_mesh("cow")
+    v = normalize_mesh(v)
+    vt, ft = cow_uvs()
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 64), torch.linspace(0, 1, 64), indexing="ij")
+    tex = torch.stack([xx, yy, 0.5 + 0.5 * torch.sin(12 * xx) * torch.cos(9 * yy)], -1)[None]
+    mesh = trb.Meshes([v.to(DEV)], [f.to(DEV)],
+                      textures=trb.TexturesUV(maps=tex.to(DEV), faces_uvs=[ft.to(DEV)], verts_uvs=[vt.to(DEV)]))
+    cams = trb.FoVPerspectiveCameras(device=DEV)
+    blend = trb.BlendParams(SIGMA, 1e-4, (0.0, 0.0, 0.0))
+    soft = trb.RasterizationSettings(image_size=128, blur_radius=BLUR, faces_per_pixel=20)
+    hard = trb.RasterizationSettings(image_size=128, blur_radius=0.0, faces_per_pixel=1)
+    sil = trb.MeshRenderer(trb.MeshRasterizer(cams, soft), trb.SoftSilhouetteShader(blend))
+    rast = trb.MeshRasterizer(cams, hard)
+    phong = trb.MeshRenderer(trb.MeshRasterizer(cams, hard),
+                             trb.SoftPhongShader(device=DEV, cameras=cams, blend_params=blend,
+                                                 lights=trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]])))
+    R_ref, T_ref = trb.look_at_view_transform(2.7, 30.0, 60.0)
+    q_ref = torch.cat([T_ref, trb.transforms.matrix_to_quaternion(R_ref)], -1).to(DEV)
+
+    def render(pose):
+        R = trb.transforms.quaternion_to_matrix(pose[:, 3:]); T = pose[:, :3]
+        depth = torch.relu(rast(meshes_world=mesh, R=R, T=T).zbuf[..., 0])
+        alpha = sil(mesh, R=R, T=T)[..., 3]
+        rgb = phong(mesh, R=R, T=T)[..., :3]
+        return depth, alpha, rgb
+
+    with torch.no_grad():
+        d_ref, a_ref, c_ref = render(q_ref)
+    mask = d_ref > 0
+    R0, T0 = trb.look_at_view_transform(2.9, 22.0, 48.0)
+    pose = torch.cat([T0, trb.transforms.matrix_to_quaternion(R0)], -1).to(DEV).requires_grad_(True)
+    opt = torch.optim.Adam([pose], lr=0.01)
+
+    def loss_fn():
+        depth, alpha, rgb = render(pose)
+        both = mask & (depth > 0)
+        return ((alpha - a_ref).abs().mean() + torch.nn.functional.huber_loss(depth[both], d_ref[both])
+                + 0.1 * ((rgb - c_ref) ** 2).mean())
+
+    def pose_error():
+        q = pose.detach()
+        qn = q[:, 3:] / q[:, 3:].norm()
+        qr = q_ref[:, 3:] / q_ref[:, 3:].norm()
+        return float((q[:, :3] - q_ref[:, :3]).norm() + torch.minimum((qn - qr).norm(), (qn + qr).norm()))
+
+    l0, e0 = float(loss_fn().detach()), pose_error()
+    for _ in range(150):
+        opt.zero_grad()
+        loss = loss_fn()
+        loss.backward()
+        opt.step()
+    l1, e1 = float(loss_fn().detach()), pose_error()
+    trb.set_fragment_cache(False)
+    assert l1 < 0.2 * l0, (l0, l1)
+    assert e1 < 0.35 * e0, (e0, e1)
+
+
+def test_vertex_colour_fitting_converges():
+    """mesh_deformer.py:181-222: per-vertex colours fitted to multi-view target images, two random views per
+    iteration through per-call `cameras=` / `lights=` overrides, SGD with momentum."""
+    trb = _trb()
+    torch.manual_seed(0)
+    ico = trb.ico_sphere(3, device=DEV)
+    v, f = ico.get_mesh_verts_faces(0)
+    target_rgb_v = (0.5 + 0.5 * torch.sin(3.0 * v)).clamp(0, 1)
+    nv = 8
+    R, T = trb.look_at_view_transform(dist=2.7, elev=torch.linspace(-40, 40, nv), azim=torch.linspace(-180, 180, nv))
+    cams = [trb.FoVPerspectiveCameras(device=DEV, R=R[i:i + 1].to(DEV), T=T[i:i + 1].to(DEV)) for i in range(nv)]
+    lights = trb.AmbientLights(device=DEV)
+    rend = trb.MeshRenderer(trb.MeshRasterizer(cams[0], trb.RasterizationSettings(image_size=96, perspective_correct=False)),
+                            trb.SoftPhongShader(device=DEV, cameras=cams[0], lights=lights))
+    with torch.no_grad():
+        tgt_mesh = trb.Meshes([v], [f], textures=trb.TexturesVertex(target_rgb_v[None]))
+        targets = [rend(tgt_mesh, cameras=c, lights=lights)[0, ..., :3] for c in cams]
+    verts_rgb = torch.full((1, v.shape[0], 3), 0.5, device=DEV, requires_grad=True)
+    opt = torch.optim.SGD([verts_rgb], lr=1.0, momentum=0.9)
+    mesh = trb.Meshes([v], [f])
+    err0 = float((verts_rgb.detach()[0] - target_rgb_v).abs().mean())
+    g = torch.Generator().manual_seed(1)
+    for _ in range(150):
+        opt.zero_grad()
+        rgb = torch.nn.functional.hardtanh(verts_rgb, min_val=0.0, max_val=1.0)
+        mesh.textures = trb.TexturesVertex(verts_features=rgb)
+        loss = 0.0
+        for j in torch.randperm(nv, generator=g)[:2].tolist():
+            pred = rend(mesh, cameras=cams[j], lights=lights)[0, ..., :3]
+            loss = loss + ((pred - targets[j]) ** 2).mean()
+        (loss * v.shape[0] / 40.0 + ((rgb - verts_rgb) ** 2).sum()).backward()
+        opt.step()
+    err1 = float((verts_rgb.detach()[0] - target_rgb_v).abs().mean())
+    assert err1 < 0.3 * err0, (err0, err1)
+
+
+def test_vertex_offsets_from_silhouettes_converge():
+    """Vertex offsets of an ico-sphere optimised so that its soft silhouettes from six views match those of an
+    ellipsoid (the silhouette term of the reference's deformation scripts), Adam on `deform_verts`."""
+    trb = _trb()
+    ico = trb.ico_sphere(3, device=DEV)
+    v, f = ico.get_mesh_verts_faces(0)
+    scale = torch.tensor([1.25, 0.8, 1.0], device=DEV)
+    nv = 6
+    R, T = trb.look_at_view_transform(dist=3.0, elev=torch.tensor([0.0, 0.0, 0.0, 0.0, 80.0, -80.0]),
+                                      azim=torch.tensor([0.0, 90.0, 180.0, 270.0, 0.0, 0.0]))
+    cams = trb.FoVPerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV))
+    sil = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=96, blur_radius=BLUR,
+                                                                              faces_per_pixel=12)),
+                           trb.SoftSilhouetteShader(trb.BlendParams(SIGMA, 1e-4, (0.0, 0.0, 0.0))))
+    with torch.no_grad():
+        target = sil(trb.Meshes([v * scale], [f]).extend(nv))[..., 3]
+    deform = torch.zeros_like(v, requires_grad=True)
+    opt = torch.optim.Adam([deform], lr=5e-3)
+
+    def loss_fn():
+        pred = sil(trb.Meshes([v + deform], [f]).extend(nv))[..., 3]
+        return ((pred - target) ** 2).mean()
+
+    l0 = float(loss_fn().detach())
+    for _ in range(200):
+        opt.zero_grad()
+        loss = loss_fn() + 1e-3 * (deform ** 2).mean()
+        loss.backward()
+        opt.step()
+    l1 = float(loss_fn().detach())
+    assert l1 < 0.25 * l0, (l0, l1)
+    assert torch.isfinite(deform).all()

@@ -65,6 +65,10 @@ SCENES = [
     ("teapot", (128, 128), 8, 9.21024e-4, True, True),
     ("cow", (128, 128), 1, 0.0, True, False),
     ("cow", (200, 120), 3, 1e-3, False, True),
+    ("teapot", (45, 61), 1, 0.0, True, False),       # rows not 16-byte aligned, partial edge tiles
+    ("teapot", (45, 61), 3, 5e-4, True, True),
+    ("cow", (130, 258), 1, 0.0, False, False),       # W % 4 == 2: scalar fill path of the K=1 strips
+    ("sphere", (33, 47), 30, 2e-3, True, True),      # 8x8 tiles, odd sizes
     ("sphere", (64, 64), 50, 9.21024e-4, True, True),
     ("sphere", (40, 40), 150, 4e-3, False, True),
 ]

@@ -272,6 +272,16 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         const trb_uv_texture* host_uv, int device, trb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Nearest neighbour between batched point sets (replaces knn_points(K=1) inside pytorch3d.loss.chamfer_distance;
+ * reference: mesh_deformer.py:307-311, deform_mesh_from_pcd.py:168-172 -- SURVEY 8f rank 4, the step right after
+ * the render in the deformation loops).  x f32[N,P1,3], y f32[N,P2,3] -> dist f32[N,P1] squared distance to the
+ * nearest y (lowest index on ties), idx i32[N,P1].  Backward ACCUMULATES into grad_x / grad_y (either may be NULL). */
+int trb_nn_forward(const float* x, const float* y, int N, int P1, int P2, float* dist, int32_t* idx, int device,
+                   trb_stream_t stream);
+int trb_nn_backward(const float* x, const float* y, const int32_t* idx, const float* grad_dist, int N, int P1,
+                    int P2, float* grad_x, float* grad_y, int device, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU: one-shot sum all-reduce of the view-shared gradients over peer memory.
  * The reference has no distributed path (every script pins cuda:0); the view batch is sharded over the GPUs of
  * one box and this is the step's only exchange.  host_segments[i] / host_counts[i]: up to 4 local f32 buffers,

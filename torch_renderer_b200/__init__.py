@@ -2,7 +2,7 @@
 silhouette, forward and backward) behind the PyTorch3D call surface used by
 YufengJin/torch_renderer.  All arithmetic runs in hand-written sm_100a kernels in ``libtrb.so``
 (C ABI: ``include/trb.h``); there is no CPU or eager fallback."""
-from . import _lib, io, ops, renderer, structures, transforms, utils  # noqa: F401
+from . import _lib, io, loss, ops, renderer, structures, transforms, utils  # noqa: F401
 from .renderer import *  # noqa: F401,F403
 from .structures import Meshes, join_meshes_as_batch  # noqa: F401
 from .io import load_obj, load_objs_as_meshes, save_obj  # noqa: F401
@@ -10,3 +10,5 @@ from .utils import ico_sphere  # noqa: F401
 from .ops import interpolate_face_attributes  # noqa: F401
 
 __version__ = "0.1.0"
+from .loss import (  # noqa: F401
+    chamfer_distance, mesh_edge_loss, mesh_laplacian_smoothing, mesh_normal_consistency, sample_points_from_meshes)

@@ -42,7 +42,7 @@ def install(force: bool = False) -> None:
     if "pytorch3d" in sys.modules and not force and not getattr(sys.modules["pytorch3d"], "_trb_alias", False):
         raise RuntimeError("a real pytorch3d is already imported; pass force=True to shadow it")
     import torch_renderer_b200 as trb
-    from torch_renderer_b200 import io, ops, renderer, structures, transforms, utils
+    from torch_renderer_b200 import io, loss, ops, renderer, structures, transforms, utils
 
     def alias(name, src, extra=None):
         mod = types.ModuleType(name)
@@ -64,8 +64,12 @@ def install(force: bool = False) -> None:
     root.io = alias("pytorch3d.io", io)
     root.transforms = alias("pytorch3d.transforms", transforms)
     root.utils = alias("pytorch3d.utils", utils)
-    root.ops = alias("pytorch3d.ops", types.SimpleNamespace(interpolate_face_attributes=ops.interpolate_face_attributes))
-    root.loss = alias("pytorch3d.loss", types.SimpleNamespace())
+    root.ops = alias("pytorch3d.ops", types.SimpleNamespace(
+        interpolate_face_attributes=ops.interpolate_face_attributes,
+        sample_points_from_meshes=loss.sample_points_from_meshes))
+    root.loss = alias("pytorch3d.loss", types.SimpleNamespace(
+        chamfer_distance=loss.chamfer_distance, mesh_edge_loss=loss.mesh_edge_loss,
+        mesh_laplacian_smoothing=loss.mesh_laplacian_smoothing, mesh_normal_consistency=loss.mesh_normal_consistency))
     # sub-modules some scripts import from directly
     sys.modules["pytorch3d.renderer.mesh"] = root.renderer
     sys.modules["pytorch3d.renderer.cameras"] = root.renderer

@@ -689,3 +689,42 @@ def test_textures_uv_fused_in_kernels(K, blur, lights):
         assert x is not None and y is not None, name
         assert rel_l2(x.cpu(), y.cpu()) < 1e-3, (name, rel_l2(x.cpu(), y.cpu()))
     assert a[1].abs().sum() > 0
+
+
+def _triangle_soup(seed, n_small=300, n_big=6):
+    """Random triangle soup in NDC: many small faces, a few screen-sized ones, exact depth ties (duplicated faces
+    and faces quantised to a coarse depth grid), degenerate and zero-area faces, faces partly / wholly outside the
+    image, faces at and behind the camera plane."""
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(n_small, 1, 2, generator=g) * 2.6 - 1.3
+    small = torch.cat([c + 0.12 * torch.randn(n_small, 3, 2, generator=g),
+                       torch.round(torch.rand(n_small, 1, 1, generator=g).expand(-1, 3, -1) * 8) / 4 + 0.5
+                       + 0.05 * torch.randn(n_small, 3, 1, generator=g) * (torch.rand(n_small, 1, 1, generator=g) > 0.5)], -1)
+    big = torch.cat([torch.rand(n_big, 3, 2, generator=g) * 3.0 - 1.5, 1.0 + torch.rand(n_big, 3, 1, generator=g) * 2], -1)
+    dup = small[:20].clone()                                  # exact ties: same geometry, later face index
+    flat = small[20:30].clone(); flat[:, 2] = flat[:, 1]      # zero area
+    behind = small[30:40].clone(); behind[:, :, 2] = -behind[:, :, 2]
+    touch = small[40:50].clone(); touch[:, 0, 2] = 0.0        # one vertex on the camera plane
+    tris = torch.cat([small, big, dup, flat, behind, touch], 0)
+    perm = torch.randperm(tris.shape[0], generator=g)
+    verts = tris[perm].reshape(-1, 3).float()
+    return verts, torch.arange(verts.shape[0]).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("seed,image_size,K,blur,persp,clip,cull", [
+    (0, (48, 64), 1, 0.0, False, False, False), (1, (48, 64), 1, 0.0, True, False, True),
+    (2, (37, 53), 1, 2e-3, True, True, False), (3, (64, 48), 2, 0.0, True, False, False),
+    (4, (40, 40), 5, 1e-3, False, True, False), (5, (33, 70), 5, 1e-3, True, True, True),
+    (6, (32, 32), 30, 3e-3, True, True, False), (7, (56, 56), 8, 0.0, False, False, False),
+    (8, (24, 100), 3, 5e-4, True, False, False), (9, (50, 50), 150, 2e-3, False, True, False),
+])
+def test_random_triangle_soups_bit_exact(seed, image_size, K, blur, persp, clip, cull):
+    """Adversarial soups (exact depth ties, degenerate faces, big + tiny faces mixed, faces across the image border
+    and the camera plane) against the oracle: pix_to_face bit-exact for every kernel variant."""
+    verts, faces = _triangle_soup(seed)
+    want = oracle_rasterize(verts[None], faces, image_size, blur, K, persp, clip, cull)
+    got = _cuda_raster_from_ndc(verts[None], faces, image_size, blur, K, persp, clip, cull)
+    _assert_fragments_equal(got, want)
+    assert (want[0] >= 0).sum() > 200
+    if K > 1:
+        assert (want[0][..., 1] >= 0).sum() > 50

@@ -1,15 +1,15 @@
-// Coarse-to-fine mesh rasteriser for sm_100a: per-tile face binning (count -> allocate -> fill),
-// per-pixel top-K fine pass, and the backward scatter.  Replaces pytorch3d._C.rasterize_meshes /
-// rasterize_meshes_backward (reference call sites: torch_renderer.py:113, camera_pose_optimizer.py:244,
-// batch_rendering_test.py:274); semantics: SURVEY.md Appendix A3-A5, A9.
+// Stand-alone rasteriser entry points for sm_100a: per-tile face binning (count -> allocate -> fill), the fine
+// pass (the fused kernels of render.cu / render_kn.cu with the shading compiled out) and the backward scatter.
+// Replaces pytorch3d._C.rasterize_meshes / rasterize_meshes_backward (reference call sites: torch_renderer.py:113,
+// camera_pose_optimizer.py:244, batch_rendering_test.py:274); semantics: SURVEY.md Appendix A3-A5, A9.
 //
 // Differences from the upstream design, all deliberate:
 //  * bin lists are compact (a global cursor hands every tile exactly `count` slots) instead of
-//    N*BH*BW*M fixed slots, so the fine pass never scans sentinels;
+//    N*BH*BW*M fixed slots, so the fine pass never scans sentinels; entries carry the face's min depth;
 //  * a tile whose list does not fit the workspace is rasterised by scanning the whole mesh --
 //    faces are never dropped;
-//  * the per-pixel queue keeps only (z, face) -- 8 B per entry, in registers for K=1 and in
-//    shared memory otherwise -- and barycentrics/distances are recomputed for the K survivors;
+//  * the per-pixel queue keeps only (z, face) -- 8 B per entry in shared memory -- and barycentrics /
+//    distances are recomputed for the K survivors;
 //  * ties are broken by (z, face index), so the result does not depend on list order.
 #include "render_internal.cuh"
 #include "stages.cuh"

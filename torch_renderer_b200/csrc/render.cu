@@ -2,16 +2,16 @@
 // one batch of views, in one C-ABI call each way (reference call sites: renderer.py:100-101,
 // torch_renderer.py:113-120,158, camera_pose_optimizer.py:244-250,303, mesh_deformer.py:197,221).
 //
-// Forward launches: vertex normals (2, Phong only) -> camera centres (1) -> world->NDC (1) -> tile
-// binning (memset + 3) -> ONE fine kernel that rasterises a 16x16 (or 8x8) tile per CTA and, in its
-// epilogue, interpolates attributes, lights and blends.  HBM traffic of the big kernel is exactly the
+// Forward: four small stage kernels packed by block role (render_stages.cu: prep -> count -> alloc -> fill) and
+// ONE fine kernel that rasterises and, in its epilogue, interpolates attributes, samples the texture, lights and
+// blends -- this file for faces_per_pixel == 1, render_kn.cu otherwise.  HBM traffic of the big kernel is the
 // compulsory 28*K + 16 bytes per pixel of output (Fragments + RGBA) plus L2-resident mesh reads.
 //
-// Backward launches: one memset -> ONE kernel that re-reads Fragments + the image gradient, runs the
-// lighting model and the blend backward once per sample and chains straight into the rasteriser
-// backward (no grad_bary / grad_zbuf / grad_dists tensors exist), scattering with warp-aggregated
-// atomics -> camera-centre backward -> NDC->world backward -> vertex-normal backward (2).  Tiles the
-// forward leaves a compact list of covered pixels (`hit_pixels`); the backward visits only those.
+// Backward: ONE kernel that walks the compact list of covered pixels the forward left (`hit_pixels`), re-reads
+// their Fragments + the image gradient, runs the lighting model and the blend backward once per sample and chains
+// straight into the rasteriser backward (no grad_bary / grad_zbuf / grad_dists tensors exist), scattering with
+// warp-aggregated float4 reductions; then one post kernel (render_stages.cu: NDC->world, camera centre, vertex
+// normals, accumulator unpacking).  Every launch is a programmatic dependent launch; there are no memset nodes.
 #include "render_internal.cuh"
 #include "stages.cuh"
 

@@ -297,7 +297,9 @@ __device__ __forceinline__ WarpGroups warp_groups(int key) {
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
   wg.leaders = __ballot_sync(active, (lane == leader) && key >= 0);
-  wg.aggregate = (active == 0xffffffffu) && (__popc(wg.leaders) <= 4);
+  // shuffle-reduce only when it really merges lanes: few groups AND several lanes per group (a layer that only
+  // two or three lanes of the warp still have is cheaper as direct reductions than as 45 shuffles per group)
+  wg.aggregate = (active == 0xffffffffu) && (__popc(wg.leaders) <= 4) && (__popc(have) >= 4 * __popc(wg.leaders));
   return wg;
 }
 

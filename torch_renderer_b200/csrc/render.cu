@@ -222,6 +222,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   const bool overflow = off < 0;
   if (overflow) nlist = vd.face_count;
 
+  __syncthreads();  // a CTA may rasterise several tiles: the previous one's epilogue still reads these arrays
   s_key[tid] = ~0ull;
   if (tid < TX) s_px[tid] = pix_to_ndc(W - 1 - (tile_x0 + tid), W, H);
   else if (tid < TX + TY) s_py[tid - TX] = pix_to_ndc(H - 1 - (tile_y0 + tid - TX), H, W);
@@ -347,33 +348,65 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     }
     __syncthreads();  // staging arrays are rewritten by the next chunk
   }
-  const float px = s_px[lx], py = s_py[ly];
-
-  const unsigned long long key = s_key[tid];
-  const bool hit = live && (key != ~0ull);
-  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
-  if (!live) return;
-
-  Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
-  int best_f = -1;
+  // ---- epilogue.  Only the covered pixels (a third of a busy tile of the cow batch) need the division-heavy
+  // sample evaluation and the shading: they are compacted over the CTA, so that ceil(covered / 32) warps run that
+  // code instead of all eight; every other pixel just streams out its background.
+  __shared__ int s_hitlist[NT];
+  __shared__ int s_hcnt[NT / 32];
+  __shared__ int s_hbase, s_nhit;
+  const bool hit = live && (s_key[tid] != ~0ull);
+  const unsigned ball = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) s_hcnt[warp] = __popc(ball);
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { const int c = s_hcnt[w]; s_hcnt[w] = tot; tot += c; }
+    s_nhit = tot;
+    s_hbase = (tot > 0 && a.hit_pixels != nullptr) ? atomicAdd(a.hit_pixels, tot) : 0;
+  }
+  __syncthreads();
   if (hit) {
-    best_f = (int)(unsigned)(key & 0xffffffffull);
+    const int r = s_hcnt[warp] + __popc(ball & ((1u << lane) - 1u));
+    s_hitlist[r] = tid;
+    // list of covered pixels for the backward (row-major inside the tile: neighbouring entries, neighbouring pixels)
+    if (a.hit_pixels != nullptr) a.hit_pixels[1 + s_hbase + r] = (int)pix;
+  } else if (live) {
+    st_cs(a.p2f + pix, -1ll);
+    st_cs(a.zbuf + pix, -1.0f);
+    st_cs(a.dists + pix, -1.0f);
+    st_cs(a.bary + pix * 3 + 0, -1.0f);
+    st_cs(a.bary + pix * 3 + 1, -1.0f);
+    st_cs(a.bary + pix * 3 + 2, -1.0f);
+    if (SHADER != TRB_SHADER_NONE) {
+      const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
+                                                                : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+      st_cs(reinterpret_cast<float4*>(a.images) + pix, bgv);
+    }
+  }
+  __syncthreads();
+  if (tid >= s_nhit) return;
+  const int hp = s_hitlist[tid];           // pixel of the tile this thread finishes
+  const int hx = hp & (TX - 1), hy = hp >> 4;
+  const float px = s_px[hx], py = s_py[hy];
+  const size_t hpix = ((size_t)n * H + tile_y0 + hy) * W + tile_x0 + hx;
+  const int best_f = (int)(unsigned)(s_key[hp] & 0xffffffffull);
+  Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
+  {
     const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, best_f);
     eval_pixel_face_rt(v, px, py, persp, clip, blur, s);  // same operator sequence => same z as the key
   }
-  st_cs(a.p2f + pix, hit ? (long long)vd.p2f_base + best_f : -1ll);
-  st_cs(a.zbuf + pix, s.z);
-  st_cs(a.dists + pix, s.d);
-  st_cs(a.bary + pix * 3 + 0, s.c0);
-  st_cs(a.bary + pix * 3 + 1, s.c1);
-  st_cs(a.bary + pix * 3 + 2, s.c2);
+  st_cs(a.p2f + hpix, (long long)vd.p2f_base + best_f);
+  st_cs(a.zbuf + hpix, s.z);
+  st_cs(a.dists + hpix, s.d);
+  st_cs(a.bary + hpix * 3 + 0, s.c0);
+  st_cs(a.bary + hpix * 3 + 1, s.c1);
+  st_cs(a.bary + hpix * 3 + 2, s.c2);
   if (SHADER == TRB_SHADER_NONE) return;
   float4 out;
   if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
     // 1 - (1 - p) is not bit-identical to p; keep the product form of sigmoid_alpha_blend
-    out = make_float4(1.0f, 1.0f, 1.0f, hit ? 1.0f - (1.0f - sigmoidf(-s.d / a.sigma)) : 0.0f);
-  } else if (!hit) {
-    out = make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
+    out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - (1.0f - sigmoidf(-s.d / a.sigma)));
   } else {
     const ViewParams vp = load_view_params(a.view_params, n);
     const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces, a.uv};
@@ -393,7 +426,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
                         (w * c.z + delta * a.bg2) * inv, 1.0f - (1.0f - prob));
     }
   }
-  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+  st_cs(reinterpret_cast<float4*>(a.images) + hpix, out);
 }
 
 // ---- fused backward ----------------------------------------------------------------------------

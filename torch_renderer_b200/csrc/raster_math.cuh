@@ -284,14 +284,20 @@ struct WarpGroups {
   unsigned leaders;   // ballot of group leaders that hold a valid key
   bool any;           // some lane has a key
   bool aggregate;     // full warp and few groups: reduce with shuffles
+  // runs of CONSECUTIVE lanes with the same key (neighbouring covered pixels of one face): a segmented suffix sum
+  // over each run lets its first lane issue one reduction for the whole run
+  bool runs;          // full warp and at least one run longer than one lane
+  bool run_head;      // this lane starts a run of a valid key
+  int run_end;        // last lane of this lane's run
+  int run_steps;      // ceil(log2(longest run))
 };
 
-__device__ __forceinline__ WarpGroups warp_groups(int key) {
+__device__ __forceinline__ WarpGroups warp_groups(int key, bool allow_runs = false) {
   WarpGroups wg;
   const unsigned active = __activemask();
   const unsigned have = __ballot_sync(active, key >= 0);
   wg.any = have != 0;
-  wg.leaders = 0; wg.aggregate = false;
+  wg.leaders = 0; wg.aggregate = false; wg.runs = false; wg.run_head = false; wg.run_end = 0; wg.run_steps = 0;
   if (!wg.any) return wg;
   const unsigned peers = __match_any_sync(active, key);
   const int lane = threadIdx.x & 31;
@@ -300,6 +306,24 @@ __device__ __forceinline__ WarpGroups warp_groups(int key) {
   // shuffle-reduce only when it really merges lanes: few groups AND several lanes per group (a layer that only
   // two or three lanes of the warp still have is cheaper as direct reductions than as 45 shuffles per group)
   wg.aggregate = (active == 0xffffffffu) && (__popc(wg.leaders) <= 4) && (__popc(have) >= 4 * __popc(wg.leaders));
+  if (allow_runs && !wg.aggregate && active == 0xffffffffu) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    const unsigned later = (lane == 31) ? 0u : (heads >> (lane + 1));
+    wg.run_end = later ? lane + __ffs(later) - 1 : 31;
+    wg.run_head = ((heads >> lane) & 1u) && key >= 0;
+    // worth it only when the runs remove a good part of the warp's reductions (each costs ~3 L2 sector-ops per
+    // scatter; the segmented sum costs ~20 shuffles per step): at least 8 lanes merged away
+    const unsigned valid_heads = __ballot_sync(0xffffffffu, wg.run_head);
+    if (__popc(have) - __popc(valid_heads) >= 8) {
+      // longest run (only runs of valid keys matter, but an upper bound is fine)
+      int len = wg.run_head ? wg.run_end - lane + 1 : 1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+      wg.runs = true;
+      wg.run_steps = 32 - __clz(len - 1);  // ceil(log2(len)), len >= 2
+    }
+  }
   return wg;
 }
 
@@ -357,6 +381,25 @@ __device__ __forceinline__ void warp_groups_add_xyz3(const WarpGroups& wg, int k
         atomicAdd(base + i1, make_float4(s[3], s[4], s[5], 0.0f));
         atomicAdd(base + i2, make_float4(s[6], s[7], s[8], 0.0f));
       }
+    }
+  } else if (wg.runs) {
+    // segmented suffix sum over runs of equal keys in consecutive lanes; the first lane of a run issues
+    const int lane = threadIdx.x & 31;
+    float s[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s[i] = key >= 0 ? val[i] : 0.0f;
+    for (int step = 0, d = 1; step < wg.run_steps; ++step, d <<= 1) {
+      const bool take = lane + d <= wg.run_end;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const float t = __shfl_down_sync(0xffffffffu, s[i], d);
+        if (take) s[i] += t;
+      }
+    }
+    if (wg.run_head) {
+      atomicAdd(base + i0, make_float4(s[0], s[1], s[2], 0.0f));
+      atomicAdd(base + i1, make_float4(s[3], s[4], s[5], 0.0f));
+      atomicAdd(base + i2, make_float4(s[6], s[7], s[8], 0.0f));
     }
   } else if (key >= 0) {
     atomicAdd(base + i0, make_float4(val[0], val[1], val[2], 0.0f));

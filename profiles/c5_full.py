@@ -25,7 +25,7 @@ trb.set_fragment_cache(False)
 H = W = 1024; K = 8
 v, f = configs.grid_sphere(501, 1000)
 verts = v.to(dev).requires_grad_(True); faces = f.to(dev)
-cols = torch.rand(1, v.shape[0], 3, device=dev)
+cols = torch.rand(1, v.shape[0], 3, generator=torch.Generator().manual_seed(0)).to(dev)   # same colours on every rank
 R, T = trb.look_at_view_transform(eye=configs.fibonacci_eyes(args.views))
 lo, hi = shard_views(args.views, rank, world)
 R, T = R[lo:hi].to(dev), T[lo:hi].to(dev)

@@ -119,3 +119,58 @@ def test_peer_memory_allreduce_two_gpus():
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert [r[:2] for r in res] == [(0, True), (1, True)]
     assert all(r[2] for r in res), "fell back to NCCL: symmetric memory unavailable"
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import torch_renderer_b200 as trb
+        from helpers import uv_sphere
+        torch.manual_seed(0)
+        v, f = uv_sphere(10, 14, noise=0.05, seed=1)
+        cols = torch.rand(1, v.shape[0], 3)
+        nv = 6
+        R, T = trb.look_at_view_transform(dist=2.7, elev=torch.linspace(-30, 40, nv), azim=torch.linspace(0, 300, nv))
+
+        def grads(lo, hi):
+            vd = v.to(dev).requires_grad_(True)
+            cd = cols.to(dev).requires_grad_(True)
+            mesh = trb.Meshes([vd], [f.to(dev)], textures=trb.TexturesVertex(cd)).extend(hi - lo)
+            cams = trb.FoVPerspectiveCameras(device=dev, R=R[lo:hi].to(dev), T=T[lo:hi].to(dev))
+            rend = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=64)),
+                                    trb.SoftPhongShader(device=dev, cameras=cams,
+                                                        lights=trb.PointLights(device=dev, location=[[0.0, 1.0, -3.0]])))
+            (rend(mesh)[..., :3] ** 2).sum().backward()
+            return vd.grad, cd.grad
+
+        lo, hi = shard_views(nv, rank, world)
+        gv, gc = grads(lo, hi)
+        allreduce_shared_grads([gv, gc])
+        wv, wc = grads(0, nv)                      # the whole batch on this GPU alone
+        torch.cuda.synchronize()
+        err = max(float((gv - wv).norm() / wv.norm()), float((gc - wc).norm() / wc.norm()))
+        q.put((rank, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_view_sharded_gradients_equal_single_gpu():
+    """Views sharded over 2 GPUs + the shared-gradient all-reduce == all views on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert all(e < 1e-4 for _, e in res), res

@@ -355,6 +355,8 @@ def run_ours(args):
                          "peak_source": peak_src, "kernel_ms": round(per_launch_ms[dominant], 4),
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "step_achieved": round(step_achieved, 1), "step_frac": round(step_achieved / peak, 4),
+                         "step_note": "step_* uses SURVEY 8d's byte model (Fragments re-read in full by the backward); "
+                                      "the backward really re-reads only the covered pixels, so step_frac can exceed 1",
                          "kernels_ms_per_launch": {k: round(x, 4) for k, x in sorted(per_launch_ms.items())},
                          "calls_ms": {k: round(x, 4) for k, x in sorted(call_ms.items())}},
             "clocks": clocks,
@@ -369,9 +371,9 @@ def run_ours(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
 # filled in after each profiling pass, None until a capture of that kernel exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r01_ncu_full_v11.txt (ncu --set full, one launch each, 64 views of C2)
-    "render_fine_kernel": 695_949_824,      # 6.06 MB read + 689.88 MB written (algorithmic: 751.7 MB)
-    "render_backward_kernel": 22_641_152,   # only covered pixels (1.9% of the image) are re-read
+    # profiles/r01_ncu_full_v13.txt (ncu --set full, one launch each, 64 views of C2)
+    "render_fine_kernel": 694_697_472,      # 6.09 MB read + 688.60 MB written (algorithmic: 751.7 MB)
+    "render_backward_kernel": 22_643_968,   # only covered pixels (1.9% of the image) are re-read
 }
 
 

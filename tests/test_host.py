@@ -231,3 +231,23 @@ def test_allreduce_and_uv_entry_points_reject_bad_arguments_without_gpu():
     cfg.shade.texture_mode = 7
     assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, 0, None) == _lib.TRB_ERR_BAD_ARG
     assert L.trb_abi_struct_size(3) == ctypes.sizeof(_lib.UvTexture)
+
+
+def test_compat_resolves_every_reference_import():
+    """Every `from pytorch3d... import name` of the reference scripts (fixture generated from /root/reference by
+    tests/golden/make_reference_imports.py) resolves after compat.install(): the scripts import unchanged."""
+    import importlib
+    import json
+    import torch_renderer_b200.compat as compat
+    compat.install(force=True)
+    table = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_imports.json")))
+    assert sum(len(v) for v in table.values()) > 40
+    missing = []
+    for module, names in table.items():
+        mod = importlib.import_module(module)
+        missing += [f"{module}.{n}" for n in names if not hasattr(mod, n)]
+    assert not missing, missing
+    # the in-path names are the real thing, not stubs
+    import pytorch3d.loss as p3l
+    import pytorch3d.renderer as p3r
+    assert p3r.MeshRenderer is trb.MeshRenderer and p3l.chamfer_distance is trb.chamfer_distance

@@ -162,10 +162,14 @@ def run_ours(args):
         azim = torch.linspace(-180, 180, N) + 360.0 * rank / world / N
         R, T = trb.look_at_view_transform(dist=0.7, elev=elev, azim=azim)
 
-    verts = v.to(dev).requires_grad_(True)
-    cols = colors.to(dev).requires_grad_(True)
-    Rd = R.to(dev).requires_grad_(True)
-    Td = T.to(dev).requires_grad_(True)
+    # the four parameter tensors live in ONE device buffer (leaf views of it), so that the end-to-end leg brings a
+    # step's inputs in with a single host->device copy that lands directly in the parameters
+    host_params = [t.contiguous().float() for t in (v, colors, R, T)]
+    sizes = [t.numel() for t in host_params]
+    dev_in = torch.cat([t.reshape(-1) for t in host_params]).to(dev)
+    offs = [sum(sizes[:i]) for i in range(len(sizes))]
+    verts, cols, Rd, Td = (dev_in[o:o + n].view(t.shape).detach().requires_grad_(True)
+                           for o, n, t in zip(offs, sizes, host_params))
     faces = f.to(dev)
     mesh = trb.Meshes(verts=[verts], faces=[faces], textures=trb.TexturesVertex(cols[None]))
     meshes = mesh.extend(N)
@@ -189,17 +193,14 @@ def run_ours(args):
         allreduce_shared_grads([verts.grad, cols.grad])
 
     # pinned host buffers for the end-to-end leg: ONE packed buffer each way (inputs in; gradients + metric out)
-    sizes = [t.numel() for t in params]
-    host_in = torch.cat([t.detach().reshape(-1).cpu() for t in params]).pin_memory()
-    dev_in = torch.empty_like(host_in, device=dev)
+    host_in = torch.cat([t.reshape(-1) for t in host_params]).pin_memory()
     host_out = torch.empty(sum(sizes) + 1, dtype=torch.float32).pin_memory()
     dev_out = torch.empty(sum(sizes) + 1, dtype=torch.float32, device=dev)
 
     def core_e2e():             # H2D of this step's inputs + forward + backward + metric
-        dev_in.copy_(host_in, non_blocking=True)
-        for p, chunk in zip(params, dev_in.split(sizes)):
+        for p in params:
             p.grad = None
-            p.data.copy_(chunk.view_as(p))
+        dev_in.copy_(host_in, non_blocking=True)   # lands in verts / cols / Rd / Td (views of dev_in)
         images = renderer(meshes, R=Rd, T=Td)
         images.backward(grad_img)
         # the step's result read back by the host: mean alpha (silhouette coverage) ...

@@ -150,6 +150,10 @@ def run_ours(args):
     # cannot take part in a CUDA-graph capture.
     work_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(work_stream)
+    # warm-up, capture and replay deliberately run on different (non-default) streams
+    _quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if _quiet is not None:
+        _quiet(False)
 
     # every step rasterises: no reuse of Fragments between identical renders (the inputs of the device-resident
     # leg do not change from step to step)

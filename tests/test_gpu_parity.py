@@ -728,3 +728,30 @@ def test_random_triangle_soups_bit_exact(seed, image_size, K, blur, persp, clip,
     assert (want[0] >= 0).sum() > 200
     if K > 1:
         assert (want[0][..., 1] >= 0).sum() > 50
+
+
+def test_integration_md_ctypes_stub_matches_oracle(monkeypatch):
+    """The drop-in `rasterize_meshes` ctypes stub printed in INTEGRATION.md (what a maintainer of the reference
+    would paste in place of pytorch3d._C.rasterize_meshes) is executed as written and checked against the oracle."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    code = next(b for b in blocks if "def rasterize_meshes(" in b and "ctypes.CDLL" in b)
+    monkeypatch.chdir(root)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    v, f = _scene("teapot")
+    R, T = _views(2, seed=3)
+    ndc = _ndc(v, R, T, fov_proj(2))
+    F = f.shape[0]
+    face_verts = ndc[:, f].reshape(-1, 3, 3).contiguous().to(DEV)
+    first = torch.arange(2, dtype=torch.int64) * F
+    count = torch.full((2,), F, dtype=torch.int64)
+    neighbours = torch.full((2 * F,), -1, dtype=torch.int64)
+    for K, blur, persp, clip in ((1, 0.0, True, False), (4, 1e-3, True, True)):
+        got = ns["rasterize_meshes"](face_verts, first.to(DEV), count.to(DEV), neighbours.to(DEV), (48, 64), blur, K,
+                                     0, 0, persp, clip, False)
+        want = oracle_rasterize(ndc, f, (48, 64), blur, K, persp, clip)
+        _assert_fragments_equal(got, want)

@@ -1,10 +1,10 @@
 """Lets the reference scripts keep their ``from pytorch3d... import ...`` lines.
 
 ``install()`` registers alias modules ``pytorch3d``, ``pytorch3d.renderer``, ``pytorch3d.structures``,
-``pytorch3d.io``, ``pytorch3d.transforms``, ``pytorch3d.utils`` and ``pytorch3d.ops`` in ``sys.modules`` that
-resolve to this package (reference imports: renderer.py:7-26, torch_renderer.py:8-36,
-camera_pose_optimizer.py:13-43, mesh_deformer.py:12-40, myrenderer.py:36-49).  Names the hot path does not
-cover (point-cloud renderers, losses) resolve to stubs that raise ``NotImplementedError`` when *used*, so
+``pytorch3d.io``, ``pytorch3d.transforms``, ``pytorch3d.utils``, ``pytorch3d.ops`` and ``pytorch3d.loss`` in
+``sys.modules`` that resolve to this package (reference imports: renderer.py:7-26, torch_renderer.py:8-36,
+camera_pose_optimizer.py:13-43, mesh_deformer.py:12-40, myrenderer.py:36-49).  Names the package does
+not cover (point-cloud renderers, ``Pointclouds``, ICP, ``knn_points``) resolve to stubs that raise ``NotImplementedError`` when *used*, so
 that module-level imports of the scripts still succeed.
 """
 from __future__ import annotations
@@ -17,9 +17,7 @@ _OUT_OF_SCOPE = {
                            "PointsRasterizer", "AlphaCompositor", "NormWeightedCompositor", "TexturesAtlas",
                            "SoftGouraudShader", "HardGouraudShader", "HardFlatShader"],
     "pytorch3d.structures": ["Pointclouds"],
-    "pytorch3d.ops": ["sample_points_from_meshes", "iterative_closest_point", "knn_points"],
-    "pytorch3d.loss": ["chamfer_distance", "mesh_edge_loss", "mesh_laplacian_smoothing",
-                       "mesh_normal_consistency"],
+    "pytorch3d.ops": ["iterative_closest_point", "knn_points"],
     "pytorch3d.io": ["IO"],
 }
 

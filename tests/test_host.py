@@ -251,3 +251,32 @@ def test_compat_resolves_every_reference_import():
     import pytorch3d.loss as p3l
     import pytorch3d.renderer as p3r
     assert p3r.MeshRenderer is trb.MeshRenderer and p3l.chamfer_distance is trb.chamfer_distance
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/trb.h is the C-ABI boundary: it must compile as strict C99 and a C program must link against
+    libtrb.so and call the bookkeeping entry points (what a cgo / JNI / N-API binding would do first)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "trb.h"\n'
+                   'int main(void) { size_t n = 0; trb_render_config c; (void)c;\n'
+                   '  if (trb_abi_version() != TRB_ABI_VERSION) return 1;\n'
+                   '  if (trb_abi_struct_size(0) != (int)sizeof(trb_view)) return 2;\n'
+                   '  if (trb_abi_struct_size(1) != (int)sizeof(trb_shade_config)) return 3;\n'
+                   '  if (trb_abi_struct_size(2) != (int)sizeof(trb_render_config)) return 4;\n'
+                   '  if (trb_abi_struct_size(3) != (int)sizeof(trb_uv_texture)) return 5;\n'
+                   '  if (trb_raster_workspace_bytes(1, 32, 32, 2, 100, &n) != TRB_OK || n == 0) return 6;\n'
+                   '  puts(trb_status_string(TRB_ERR_K_TOO_LARGE)); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-l:libtrb.so", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert "150" in r.stdout

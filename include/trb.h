@@ -10,6 +10,7 @@
  *
  *   _C.rasterize_meshes            -> trb_raster_forward
  *   _C.rasterize_meshes_backward   -> trb_raster_backward
+ *   clipped_faces_neighbor_idx     -> trb_clip_resequence (after clip_faces, torch_renderer_b200/clip.py)
  *   _C.interp_face_attrs_forward   -> trb_interp_forward
  *   _C.interp_face_attrs_backward  -> trb_interp_backward
  *   phong_shading + softmax_rgb_blend / sigmoid_alpha_blend / hard_rgb_blend
@@ -124,6 +125,28 @@ int trb_raster_backward(const float* verts_ndc, const int32_t* faces, const trb_
                         int H, int W, int K, uint32_t flags, const int64_t* pix_to_face,
                         const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
                         float* grad_verts_ndc, int device, trb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Faces cut by the near plane (replaces the `clipped_faces_neighbor_idx` argument of _C.rasterize_meshes;
+ * PyTorch3D renderer/mesh/clip.py + the neighbour rule of rasterize_meshes.cu / rasterize_meshes_cpu.cpp).
+ *
+ * Call after trb_raster_forward(face_verts, faces = NULL, ...) on the clipped face list, with views whose
+ * p2f_base == face_start.  A face cut into a quadrilateral is two consecutive rows t1, t1 + 1 that name each
+ * other in `neighbor` i32[F'] (-1 elsewhere); pair_face i32[P] lists every t1, pair_view i32[P] its view.
+ * Pixels where both halves of a pair are candidates are re-rasterised with upstream's order-dependent queue
+ * (at most one half per pixel) and overwritten in the four outputs; all other pixels are left as they are.
+ * counters i32[1] (may be NULL) accumulates the number of re-rasterised pixels.
+ */
+/* Raises *flag (persistent i32, never reset by the caller) to `epoch` when any (view, vertex) has view-space depth
+ * < z_plane; epochs must grow from call to call.  MeshRasterizer asks this before every render with an active near
+ * plane (upstream's clip_faces reads two sums on the host at the same place). */
+int trb_any_vertex_behind(const float* verts_world, const float* R, const float* T, const trb_view* views, int N,
+                          int max_vert_count, float z_plane, int32_t epoch, int32_t* flag, int device,
+                          trb_stream_t stream);
+int trb_clip_resequence(const float* face_verts, const trb_view* views, const int32_t* pair_face,
+                        const int32_t* pair_view, int64_t num_pairs, const int32_t* neighbor, int N, int H,
+                        int W, int K, float blur_radius, uint32_t flags, int64_t* pix_to_face, float* zbuf,
+                        float* bary, float* dists, int32_t* counters, int device, trb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * interpolate_face_attributes (replaces _C.interp_face_attrs_forward/backward).

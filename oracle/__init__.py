@@ -35,7 +35,8 @@ def lib() -> ctypes.CDLL:
         if not os.path.exists(_SO):
             build()
         _lib = ctypes.CDLL(_SO)
-        for name in ("trb_oracle_rasterize_forward", "trb_oracle_rasterize_backward",
+        for name in ("trb_oracle_rasterize_forward", "trb_oracle_rasterize_forward_clipped",
+                     "trb_oracle_rasterize_backward",
                      "trb_oracle_interp_forward", "trb_oracle_interp_backward",
                      "trb_oracle_num_threads"):
             getattr(_lib, name).restype = ctypes.c_int
@@ -52,8 +53,10 @@ def num_threads() -> int:
 
 def rasterize_forward(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size,
                       blur_radius=0.0, faces_per_pixel=1, perspective_correct=False,
-                      clip_barycentric_coords=False, cull_backfaces=False, num_threads=0):
+                      clip_barycentric_coords=False, cull_backfaces=False, num_threads=0,
+                      clipped_faces_neighbor_idx=None):
     """numpy in / numpy out twin of ``_C.rasterize_meshes`` with ``bin_size=0`` on CPU tensors.
+    ``clipped_faces_neighbor_idx`` i64[F] (-1 = none) is the output of ``clip_ref.clip_faces``.
 
     Returns (pix_to_face i64[N,H,W,K], zbuf, bary[N,H,W,K,3], dists)."""
     fv = np.ascontiguousarray(face_verts, dtype=np.float32).reshape(-1, 3, 3)
@@ -65,8 +68,13 @@ def rasterize_forward(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, im
     zbuf = np.empty((N, H, W, K), np.float32)
     bary = np.empty((N, H, W, K, 3), np.float32)
     dists = np.empty((N, H, W, K), np.float32)
-    rc = lib().trb_oracle_rasterize_forward(
-        _p(fv), _p(first), _p(count), N, H, W, K, ctypes.c_float(blur_radius),
+    nbr = None
+    if clipped_faces_neighbor_idx is not None:
+        nbr = np.ascontiguousarray(clipped_faces_neighbor_idx, dtype=np.int64)
+        if nbr.shape != (fv.shape[0],):
+            raise ValueError("clipped_faces_neighbor_idx must have one entry per face")
+    rc = lib().trb_oracle_rasterize_forward_clipped(
+        _p(fv), _p(first), _p(count), None if nbr is None else _p(nbr), N, H, W, K, ctypes.c_float(blur_radius),
         int(perspective_correct), int(clip_barycentric_coords), int(cull_backfaces),
         _p(p2f), _p(zbuf), _p(bary), _p(dists), int(num_threads))
     if rc == 2:

@@ -122,6 +122,7 @@ typedef struct {
   const float* face_verts; const int64_t* first; const int64_t* count;
   int N, H, W, K; float blur_radius, sqrt_blur; int persp, clip, cull;
   int64_t* pix_to_face; float* zbuf; float* bary; float* dists;
+  const int64_t* neighbor;  /* clipped_faces_neighbor_idx i64[F_total] or NULL */
   atomic_llong next_row;
 } fwd_job_t;
 
@@ -140,6 +141,25 @@ static void rasterize_row(const fwd_job_t* j, int64_t row) {
                            j->clip, j->cull, &c))
         continue;
       c.f = f;
+      /*
+       * A face cut by the near plane into a quadrilateral is drawn as two triangles (t1, t2 = t1 + 1) that
+       * name each other in clipped_faces_neighbor_idx (PyTorch3D renderer/mesh/clip.py).  RasterizeMeshesNaiveCpu
+       * keeps at most one of the two per pixel: when the neighbour is in the queue at this moment, the arriving
+       * face replaces it iff its unsigned distance is strictly smaller, and is dropped otherwise; when the
+       * neighbour is not in the queue (never a candidate, or already pushed out) the face is an ordinary one.
+       * The rule depends on the order faces arrive in -- ascending face index -- and is restated as is.
+       */
+      if (j->neighbor != NULL && j->neighbor[f] >= 0) {
+        const int64_t nb = j->neighbor[f];
+        int at = -1;
+        for (int i = 0; i < qn; ++i)
+          if (q[i].f == nb) { at = i; break; }
+        if (at >= 0) {
+          if (!(fabsf(c.d) < fabsf(q[at].d))) continue;
+          for (int i = at; i + 1 < qn; ++i) q[i] = q[i + 1];   /* take the neighbour out ... */
+          --qn;                                                /* ... and insert the face below */
+        }
+      }
       /* sorted insert by (z, f); drop the largest when more than K. */
       if (qn == K && !cand_less(c.z, c.f, q[K - 1].z, q[K - 1].f)) continue;
       int pos = qn < K ? qn : K - 1;
@@ -187,19 +207,41 @@ int trb_oracle_num_threads(void) {
  * Outputs [N,H,W,K] (+[...,3] for bary), all -1 filled where no face.
  * Image rows are handed out to `num_threads` pthreads (<=0: all online cores).
  */
+int trb_oracle_rasterize_forward_clipped(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                                         const int64_t* num_faces_per_mesh,
+                                         const int64_t* clipped_faces_neighbor_idx, int N, int H, int W, int K,
+                                         float blur_radius, int perspective_correct,
+                                         int clip_barycentric_coords, int cull_backfaces,
+                                         int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                         int num_threads);
+
 int trb_oracle_rasterize_forward(const float* face_verts, const int64_t* mesh_to_face_first_idx,
                                  const int64_t* num_faces_per_mesh, int N, int H, int W, int K,
                                  float blur_radius, int perspective_correct,
                                  int clip_barycentric_coords, int cull_backfaces,
                                  int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
                                  int num_threads) {
+  return trb_oracle_rasterize_forward_clipped(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, NULL, N, H,
+                                              W, K, blur_radius, perspective_correct, clip_barycentric_coords,
+                                              cull_backfaces, pix_to_face, zbuf, bary, dists, num_threads);
+}
+
+/* Same, with `clipped_faces_neighbor_idx` i64[F_total] (-1 = none; NULL = no clipped faces): the fifth argument
+ * of _C.rasterize_meshes that PyTorch3D's clip_faces produces for faces crossing the near plane. */
+int trb_oracle_rasterize_forward_clipped(const float* face_verts, const int64_t* mesh_to_face_first_idx,
+                                         const int64_t* num_faces_per_mesh,
+                                         const int64_t* clipped_faces_neighbor_idx, int N, int H, int W, int K,
+                                         float blur_radius, int perspective_correct,
+                                         int clip_barycentric_coords, int cull_backfaces,
+                                         int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                         int num_threads) {
   if (K < 1 || K > K_MAX_FACES_PER_PIXEL) return 2;
   if (N < 0 || H < 1 || W < 1) return 1;
   if (num_threads <= 0) num_threads = trb_oracle_num_threads();
   if (num_threads > 256) num_threads = 256;
   fwd_job_t job = {face_verts, mesh_to_face_first_idx, num_faces_per_mesh, N, H, W, K,
                    blur_radius, sqrtf(blur_radius), perspective_correct, clip_barycentric_coords,
-                   cull_backfaces, pix_to_face, zbuf, bary, dists, 0};
+                   cull_backfaces, pix_to_face, zbuf, bary, dists, clipped_faces_neighbor_idx, 0};
   atomic_init(&job.next_row, 0);
   if (num_threads == 1) { fwd_worker(&job); return 0; }
   pthread_t th[256];

@@ -81,3 +81,21 @@ def oracle_rasterize(verts_ndc, faces, image_size, blur_radius=0.0, K=1, persp=F
 def rel_l2(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def oracle_rasterize_clipped(verts_ndc, faces, image_size, blur_radius=0.0, K=1, persp=False, clip=False,
+                             cull=False, z_clip_value=None, cull_to_frustum=False, threads=0):
+    """The upstream route for a batch with an active near plane: clip_faces -> rasterise (with the neighbour
+    table) -> convert back to the faces of the batch.  Returns (fragments, ClippedFaces)."""
+    from oracle import clip_ref
+    N, V, _ = verts_ndc.shape
+    F = faces.shape[0]
+    fv = verts_ndc.detach().cpu().float()[:, faces.cpu()].reshape(-1, 3, 3).numpy()
+    first = np.arange(N, dtype=np.int64) * F
+    count = np.full((N,), F, dtype=np.int64)
+    cf = clip_ref.clip_faces(fv, first, count, clip_ref.rasterizer_frustum(persp, z_clip_value, cull_to_frustum))
+    p2f, zbuf, bary, dists = oracle.rasterize_forward(
+        cf.face_verts, cf.mesh_to_face_first_idx, cf.num_faces_per_mesh, image_size, blur_radius, K, persp, clip,
+        cull, threads, clipped_faces_neighbor_idx=cf.clipped_faces_neighbor_idx)
+    p2f_u, bary_u = clip_ref.convert_clipped_rasterization_to_original_faces(p2f, bary, cf)
+    return (p2f_u, zbuf, bary_u, dists), cf, p2f

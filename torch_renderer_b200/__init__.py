@@ -2,7 +2,7 @@
 silhouette, forward and backward) behind the PyTorch3D call surface used by
 YufengJin/torch_renderer.  All arithmetic runs in hand-written sm_100a kernels in ``libtrb.so``
 (C ABI: ``include/trb.h``); there is no CPU or eager fallback."""
-from . import _lib, io, loss, ops, renderer, structures, transforms, utils  # noqa: F401
+from . import _lib, clip, io, loss, ops, renderer, structures, transforms, utils  # noqa: F401
 from .renderer import *  # noqa: F401,F403
 from .structures import Meshes, join_meshes_as_batch  # noqa: F401
 from .io import load_obj, load_objs_as_meshes, save_obj  # noqa: F401

@@ -71,3 +71,6 @@ def install(force: bool = False) -> None:
     # sub-modules some scripts import from directly
     sys.modules["pytorch3d.renderer.mesh"] = root.renderer
     sys.modules["pytorch3d.renderer.cameras"] = root.renderer
+    from torch_renderer_b200 import clip
+    root.renderer.mesh = root.renderer
+    root.renderer.clip = sys.modules["pytorch3d.renderer.mesh.clip"] = alias("pytorch3d.renderer.mesh.clip", clip)

@@ -8,6 +8,13 @@
 
 namespace trb {
 
+// View-space depth of a world-space point: third column of R, third entry of T (A1).  One definition, so that the
+// "is any vertex behind the near plane" question (clip.cu) sees the depths the transform writes.
+__device__ __forceinline__ float view_depth(float X, float Y, float Z, const float* __restrict__ r,
+                                            const float* __restrict__ t) {
+  return X * __ldg(r + 2) + Y * __ldg(r + 5) + Z * __ldg(r + 8) + __ldg(t + 2);
+}
+
 // ---- world -> view -> NDC of one (view, vertex) -------------------------------------------------
 __device__ __forceinline__ void transform_vertex(const float* __restrict__ verts, const float* __restrict__ R,
                                                  const float* __restrict__ T, const float* __restrict__ proj,
@@ -20,7 +27,7 @@ __device__ __forceinline__ void transform_vertex(const float* __restrict__ verts
   const float X = __ldg(x), Y = __ldg(x + 1), Z = __ldg(x + 2);
   const float xv = X * __ldg(r + 0) + Y * __ldg(r + 3) + Z * __ldg(r + 6) + __ldg(t + 0);
   const float yv = X * __ldg(r + 1) + Y * __ldg(r + 4) + Z * __ldg(r + 7) + __ldg(t + 1);
-  const float zv = X * __ldg(r + 2) + Y * __ldg(r + 5) + Z * __ldg(r + 8) + __ldg(t + 2);
+  const float zv = view_depth(X, Y, Z, r, t);
   const float den = perspective ? zv : 1.0f;
   float* o = out + 3 * (size_t)(vd.ndc_vert_start + lv);
   o[0] = __ldg(p + 0) * xv / den + __ldg(p + 2);

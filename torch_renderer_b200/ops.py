@@ -191,7 +191,7 @@ def transform_verts(verts_world, R, T, proj, table: ViewTable, perspective: bool
 # --------------------------------------------------------------------------------------------
 class _RasterizeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts_ndc, faces, table: ViewTable, H, W, K, blur_radius, flags):
+    def forward(ctx, verts_ndc, faces, table: ViewTable, H, W, K, blur_radius, flags, neighbor=None):
         _require_cuda(verts_ndc, "rasterize_meshes")
         verts_ndc = _f32c(verts_ndc)
         dev = verts_ndc.device
@@ -212,6 +212,20 @@ class _RasterizeFn(torch.autograd.Function):
                 float(blur_radius), int(flags), cap, _ptr(ws), nbytes.value, _ptr(p2f), _ptr(zbuf),
                 _ptr(bary), _ptr(dists), _ptr(stats), dev.index, _stream(dev)), "rasterize_meshes")
         _bump(6 if table.max_face_count > 0 else 3)
+        if neighbor is not None:
+            # faces cut into quadrilaterals by clip_faces: at most one half per pixel (trb_clip_resequence)
+            nbr = neighbor.to(torch.int32).contiguous()
+            rows = torch.arange(nbr.shape[0], dtype=torch.int32, device=dev)
+            pair_face = (nbr == rows + 1).nonzero(as_tuple=True)[0].to(torch.int32)
+            if pair_face.numel() > 0:
+                starts = table.views[:, 0].contiguous()
+                pair_view = (torch.searchsorted(starts, pair_face, right=True) - 1).to(torch.int32)
+                with _timed("clip_resequence", dev):
+                    check(L.trb_clip_resequence(
+                        _ptr(verts_ndc), _ptr(table.views), _ptr(pair_face), _ptr(pair_view), pair_face.numel(),
+                        _ptr(nbr), N, H, W, K, float(blur_radius), int(flags), _ptr(p2f), _ptr(zbuf), _ptr(bary),
+                        _ptr(dists), 0, dev.index, _stream(dev)), "rasterize_meshes (clipped faces)")
+                _bump(1)
         if table._pending is None and not torch.cuda.is_current_stream_capturing():
             host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
             host_stats.copy_(stats, non_blocking=True)
@@ -228,13 +242,13 @@ class _RasterizeFn(torch.autograd.Function):
     def backward(ctx, _gp2f, g_zbuf, g_bary, g_dists):
         verts_ndc, faces, p2f = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
-            return (None,) * 8
+            return (None,) * 9
         table = ctx.table
         H, W, K = ctx.dims
         dev = verts_ndc.device
         g_verts = torch.zeros_like(verts_ndc)
         if g_zbuf is None and g_bary is None and g_dists is None:
-            return (g_verts,) + (None,) * 7
+            return (g_verts,) + (None,) * 8
         g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
         g_bary = None if g_bary is None else _f32c(g_bary)
         g_dists = None if g_dists is None else _f32c(g_dists)
@@ -244,7 +258,50 @@ class _RasterizeFn(torch.autograd.Function):
                 _ptr(g_zbuf), _ptr(g_bary), _ptr(g_dists), _ptr(g_verts), dev.index, _stream(dev)),
                 "rasterize_meshes backward")
         _bump(1)
-        return (g_verts,) + (None,) * 7
+        return (g_verts,) + (None,) * 8
+
+
+_behind_flags = {}   # device index -> [persistent int32 flag, epoch]
+
+
+def any_vertex_behind(verts_world, R, T, table: ViewTable, z_plane: float) -> bool:
+    """True when some (view, vertex) has view-space depth < ``z_plane``.  One small kernel and a 4-byte read:
+    this SYNCHRONISES the host with the stream (PyTorch3D's ``clip_faces`` does the same with two ``.item()``s)."""
+    _require_cuda(verts_world, "near-plane test")
+    dev = verts_world.device
+    state = _behind_flags.get(dev.index)
+    if state is None or state[1] >= 2**31 - 2:
+        state = _behind_flags[dev.index] = [torch.zeros((1,), dtype=torch.int32, device=dev), 0]
+    state[1] += 1
+    flag, epoch = state
+    verts_world, R, T = _f32c(verts_world), _f32c(R), _f32c(T)
+    check(_lib.lib().trb_any_vertex_behind(_ptr(verts_world), _ptr(R), _ptr(T), _ptr(table.views), table.N,
+                                           table.max_vert_count, float(z_plane), epoch, _ptr(flag), dev.index,
+                                           _stream(dev)), "near-plane test")
+    _bump(1)
+    return int(flag.item()) == epoch
+
+
+def rasterize_face_verts(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,
+                         faces_per_pixel=1, perspective_correct=False, clip_barycentric_coords=False,
+                         cull_backfaces=False, clipped_faces_neighbor_idx=None):
+    """The ``_C.rasterize_meshes`` signature itself: ``face_verts`` f32 (F, 3, 3) in NDC x, y + view z, per-mesh
+    ranges i64 (N,), optionally the neighbour table of ``clip.clip_faces``.  ``pix_to_face`` indexes ``face_verts``.
+    Reads the two range tensors on the host (this is the clipped-faces path, not the hot one)."""
+    H, W = image_size
+    if faces_per_pixel > _lib.MAX_FACES_PER_PIXEL:
+        raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
+    if face_verts.dim() != 3 or tuple(face_verts.shape[1:]) != (3, 3):
+        raise ValueError("face_verts must have shape (F, 3, 3)")
+    first = [int(v) for v in mesh_to_face_first_idx.tolist()]
+    count = [int(v) for v in num_faces_per_mesh.tolist()]
+    table = ViewTable.build(face_start=first, face_count=count, p2f_base=first, world_vert_start=[3 * f for f in first],
+                            vert_count=[3 * c for c in count], device=face_verts.device, shared_mesh=False)
+    flags = ((_lib.PERSPECTIVE_CORRECT if perspective_correct else 0)
+             | (_lib.CLIP_BARYCENTRIC if clip_barycentric_coords else 0)
+             | (_lib.CULL_BACKFACES if cull_backfaces else 0))
+    return _RasterizeFn.apply(face_verts, None, table, int(H), int(W), int(faces_per_pixel), float(blur_radius),
+                              flags, clipped_faces_neighbor_idx)
 
 
 def rasterize(verts_ndc, faces, table: ViewTable, image_size, blur_radius=0.0, faces_per_pixel=1,

@@ -15,7 +15,7 @@ from typing import NamedTuple, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import _lib, clip, ops
 from .structures import Meshes
 
 kMaxBinsPerDim = 22  # PyTorch3D refuses bin grids this large; kept for error parity
@@ -87,16 +87,70 @@ def rasterize_meshes(meshes: Meshes, image_size=256, blur_radius: float = 0.0, f
     Returns (pix_to_face, zbuf, bary_coords, dists)."""
     H, W = _parse_image_size(image_size)
     _check_bin_size(bin_size, H, W)
-    if z_clip_value is not None or cull_to_frustum:
-        raise NotImplementedError("near-plane clipping / frustum culling (clip_faces) is not built yet "
-                                  "(SURVEY 8f rank 3); pass z_clip_value=None, cull_to_frustum=False")
     table = meshes.view_table()
     verts = meshes._unique_verts()
     if table.shared_mesh:
         # every replica has the same NDC vertices: expand (the kernels index per view)
         verts = verts.repeat(table.N, 1)
+    if z_clip_value is not None or cull_to_frustum:
+        clipped = _rasterize_clipped(verts, meshes.faces_packed_i32(), table, (H, W), blur_radius, faces_per_pixel,
+                                     perspective_correct, clip_barycentric_coords, cull_backfaces, z_clip_value,
+                                     cull_to_frustum)
+        if clipped is not None:
+            return clipped
     return ops.rasterize(verts, meshes.faces_packed_i32(), table, (H, W), blur_radius, faces_per_pixel,
                          perspective_correct, clip_barycentric_coords, cull_backfaces)
+
+
+_clipping_mode = "exact"
+
+
+def set_near_plane_clipping(mode: str = "exact") -> None:
+    """How ``MeshRasterizer`` treats faces that cross the near clipping plane ``z_clip_value`` (``znear / 2`` for
+    cameras that define ``znear``, as upstream) or, with ``cull_to_frustum``, leave the view frustum.
+
+    ``"exact"`` (default): PyTorch3D's behaviour.  Every rasterisation with an active plane first asks the device
+    whether any vertex lies behind it (one small kernel and a 4-byte read -- upstream's ``clip_faces`` reads two
+    sums the same way); only then are the faces cut (``clip.clip_faces``) and drawn by the stand-alone rasteriser.
+    The question cannot be asked while a CUDA graph is being captured: captured renders behave like ``"off"``.
+
+    ``"off"``: never ask.  Faces entirely behind the plane are still culled inside the kernels; a face crossing it
+    is drawn whole (or dropped when a vertex is at / behind the camera plane).  For loops that are known to keep
+    the camera away from the mesh and must not synchronise."""
+    global _clipping_mode
+    if mode not in ("exact", "off"):
+        raise ValueError("mode must be 'exact' or 'off'")
+    _clipping_mode = mode
+
+
+def _face_vertex_rows(faces_i32: torch.Tensor, table) -> torch.Tensor:
+    """i64 (F_packed, 3): rows of the view-major NDC vertex array for every packed face of the batch."""
+    faces = faces_i32.long()
+    if not table.shared_mesh:
+        return faces
+    V = table.max_vert_count
+    shift = torch.arange(table.N, device=faces.device, dtype=torch.long) * V
+    return (faces[None] + shift[:, None, None]).reshape(-1, 3)
+
+
+def _rasterize_clipped(verts_ndc, faces_i32, table, image_size, blur_radius, K, perspective_correct,
+                       clip_barycentric_coords, cull_backfaces, z_clip_value, cull_to_frustum):
+    """``rasterize_meshes`` with ``clip_faces`` in front, as upstream: (pix_to_face, zbuf, bary, dists) indexed by
+    the faces of the batch, or ``None`` when ``clip_faces`` leaves the face list untouched."""
+    host = table.host
+    dev = verts_ndc.device
+    first = host[:, 3].long().to(dev)
+    count = host[:, 1].long().to(dev)
+    face_verts = verts_ndc[_face_vertex_rows(faces_i32, table)]
+    frustum = clip.rasterizer_frustum(perspective_correct, z_clip_value, cull_to_frustum)
+    cf = clip.clip_faces(face_verts, first, count, frustum)
+    if cf.faces_clipped_to_unclipped_idx is None:
+        return None
+    p2f, zbuf, bary, dists = ops.rasterize_face_verts(
+        cf.face_verts, cf.mesh_to_face_first_idx, cf.num_faces_per_mesh, image_size, blur_radius, K,
+        perspective_correct, clip_barycentric_coords, cull_backfaces, cf.clipped_faces_neighbor_idx)
+    p2f, bary = clip.convert_clipped_rasterization_to_original_faces(p2f, bary, cf)
+    return p2f, zbuf, bary, dists
 
 
 def _cached_projection(cameras, proj_kwargs):
@@ -158,7 +212,7 @@ class _FragmentCache:
     def make_key(tensors, spec, table):
         ids = tuple((id(t), t._version) for t in tensors)
         raster = (spec["image_size"], spec["K"], spec["blur_radius"], spec["flags"], spec["z_clip"],
-                  spec["perspective"])
+                  spec["perspective"], spec["cull_to_frustum"])
         return (ids, raster, id(table), torch.is_grad_enabled())
 
     def lookup(self, key, tensors):
@@ -253,14 +307,11 @@ class MeshRasterizer(nn.Module):
         persp_correct = raster_settings.perspective_correct
         if persp_correct is None:
             persp_correct = cameras.is_perspective()
-        if raster_settings.cull_to_frustum:
-            raise NotImplementedError("cull_to_frustum (clip_faces) is not built yet (SURVEY 8f rank 3)")
-        # z_clip_value: like upstream, cameras that define znear clip at znear / 2 unless the settings say
-        # otherwise.  Faces entirely nearer than the plane are culled in the kernels; faces CROSSING it are
-        # not split into clipped polygons yet -- they are drawn whole, or dropped when a
-        # vertex is at/behind the camera plane (A4.2).
+        # z_clip_value: like upstream, a perspective-correct render with a camera that defines znear clips at
+        # znear / 2 unless the settings say otherwise.  Faces entirely nearer than the plane are culled in the
+        # kernels; when a vertex lies behind the plane the call goes through clip_faces (``_clipped_fragments``).
         z_clip = raster_settings.z_clip_value
-        if z_clip is None and cameras.is_perspective():
+        if z_clip is None and persp_correct:
             z_clip = _cached_half_znear(cameras)
         K = int(raster_settings.faces_per_pixel)
         if K > _lib.MAX_FACES_PER_PIXEL:
@@ -268,7 +319,8 @@ class MeshRasterizer(nn.Module):
         flags = ((_lib.PERSPECTIVE_CORRECT if persp_correct else 0) | (_lib.CLIP_BARYCENTRIC if clip_bary else 0)
                  | (_lib.CULL_BACKFACES if raster_settings.cull_backfaces else 0))
         spec = dict(image_size=(H, W), K=K, blur_radius=float(raster_settings.blur_radius), flags=flags,
-                    z_clip=float(z_clip or 0.0),
+                    z_clip=float(z_clip or 0.0), z_clip_value=(None if z_clip is None else float(z_clip)),
+                    cull_to_frustum=bool(raster_settings.cull_to_frustum),
                     perspective=bool(perspective), shader=_lib.SHADER_NONE, light_kind=0, sigma=1.0, gamma=1.0,
                     background=(0.0, 0.0, 0.0), camera_center_from_rt=False)
         return cameras, R, T, proj, spec
@@ -284,12 +336,36 @@ class MeshRasterizer(nn.Module):
         tensors = (meshes_world._unique_verts(), meshes_world.faces_packed_i32()) + tuple(self._identity)
         return _fragment_cache.make_key(tensors, spec, meshes_world.view_table()), tensors
 
+    def _clipped_fragments(self, meshes_world: Meshes, R, T, proj, spec) -> Optional[Fragments]:
+        """The upstream ``clip_faces`` route (``set_near_plane_clipping``): Fragments when some vertex of the batch
+        lies behind the near plane (or ``cull_to_frustum`` removed faces), else ``None`` -- the caller then runs
+        the fused kernels, which cull what is entirely behind the plane themselves."""
+        z_clip, cull = spec["z_clip_value"], spec["cull_to_frustum"]
+        if (z_clip is None and not cull) or _clipping_mode == "off" or torch.cuda.is_current_stream_capturing():
+            if cull and _clipping_mode == "off":
+                raise ValueError("cull_to_frustum needs set_near_plane_clipping('exact')")
+            return None
+        table = meshes_world.view_table()
+        if not cull and not ops.any_vertex_behind(meshes_world._unique_verts(), R, T, table, z_clip):
+            return None
+        verts_ndc = ops.transform_verts(meshes_world._unique_verts(), R, T, proj, table, spec["perspective"])
+        flags = spec["flags"]
+        out = _rasterize_clipped(verts_ndc, meshes_world.faces_packed_i32(), table, spec["image_size"],
+                                 spec["blur_radius"], spec["K"], bool(flags & _lib.PERSPECTIVE_CORRECT),
+                                 bool(flags & _lib.CLIP_BARYCENTRIC), bool(flags & _lib.CULL_BACKFACES), z_clip, cull)
+        if out is None:
+            return None
+        return Fragments(pix_to_face=out[0], zbuf=out[1], bary_coords=out[2], dists=out[3])
+
     def forward(self, meshes_world: Meshes, **kwargs) -> Fragments:
         _, R, T, proj, spec = self._resolve(meshes_world, kwargs)
         key, tensors = self._cache_key(meshes_world, spec)
         cached = _fragment_cache.lookup(key, tensors)
         if cached is not None:
             return cached
+        clipped = self._clipped_fragments(meshes_world, R, T, proj, spec)
+        if clipped is not None:
+            return clipped
         token = {"consumed": False}
         spec["_token"] = token
         _, p2f, zbuf, bary, dists = ops.render(meshes_world._unique_verts(), None, R, T, proj, None,

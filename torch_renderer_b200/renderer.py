@@ -7,8 +7,11 @@ from .cameras import (  # noqa: F401
     SfMPerspectiveCameras, camera_position_from_spherical_angles, get_world_to_view_transform,
     look_at_rotation, look_at_view_transform)
 from .lighting import AmbientLights, DirectionalLights, Materials, PointLights  # noqa: F401
+from .clip import (  # noqa: F401
+    ClipFrustum, ClippedFaces, clip_faces, convert_clipped_rasterization_to_original_faces)
 from .rasterizer import (  # noqa: F401
-    Fragments, MeshRasterizer, RasterizationSettings, rasterize_meshes, set_fragment_cache)
+    Fragments, MeshRasterizer, RasterizationSettings, rasterize_meshes, set_fragment_cache,
+    set_near_plane_clipping)
 from .shader import (  # noqa: F401
     HardPhongShader, MeshRenderer, MeshRendererWithFragments, SoftPhongShader, SoftSilhouetteShader,
     TexturedSoftPhongShader)

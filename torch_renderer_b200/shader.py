@@ -262,6 +262,10 @@ class MeshRenderer(nn.Module):
         cached = _fragment_cache.lookup(key, tensors)
         if cached is not None:
             return shader(cached, meshes_world, **kwargs), cached
+        # a vertex behind the near plane: faces are cut by clip_faces and drawn by the stand-alone rasteriser
+        clipped = rast._clipped_fragments(meshes_world, R, T, proj, spec)
+        if clipped is not None:
+            return shader(clipped, meshes_world, **kwargs), clipped
         bg = blend_params.background_color
         bg = tuple(float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg))
         token = {"consumed": False}

@@ -762,6 +762,19 @@ def test_integration_md_ctypes_stub_matches_oracle(monkeypatch):
                                      0, 0, persp, clip, False)
         want = oracle_rasterize(ndc, f, (48, 64), blur, K, persp, clip)
         _assert_fragments_equal(got, want)
+    # ... and with faces cut by the near plane: the stub forwards clipped_faces_neighbor_idx to trb_clip_resequence
+    from oracle import clip_ref
+    g = torch.Generator().manual_seed(5)
+    soup = torch.cat([torch.rand(90, 3, 2, generator=g) * 1.6 - 0.8 + (torch.rand(90, 1, 2, generator=g) - 0.5),
+                      torch.rand(90, 3, 1, generator=g) * 1.6 + 0.05], dim=2)
+    cf = clip_ref.clip_faces(soup.numpy(), [0, 40], [40, 50], clip_ref.rasterizer_frustum(True, 0.5, False))
+    assert (cf.clipped_faces_neighbor_idx >= 0).sum() > 20
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    got = ns["rasterize_meshes"](t(cf.face_verts), t(cf.mesh_to_face_first_idx), t(cf.num_faces_per_mesh),
+                                 t(cf.clipped_faces_neighbor_idx), (40, 56), 2e-3, 3, 0, 0, True, True, False)
+    want = oracle.rasterize_forward(cf.face_verts, cf.mesh_to_face_first_idx, cf.num_faces_per_mesh, (40, 56), 2e-3, 3,
+                                    True, True, False, 0, clipped_faces_neighbor_idx=cf.clipped_faces_neighbor_idx)
+    _assert_fragments_equal(got, want)
 
 
 @pytest.mark.parametrize("K,blur", [(1, 0.0), (6, 1e-3)])

@@ -264,9 +264,11 @@ class _RasterizeFn(torch.autograd.Function):
 _behind_flags = {}   # device index -> [persistent int32 flag, epoch]
 
 
-def any_vertex_behind(verts_world, R, T, table: ViewTable, z_plane: float) -> bool:
-    """True when some (view, vertex) has view-space depth < ``z_plane``.  One small kernel and a 4-byte read:
-    this SYNCHRONISES the host with the stream (PyTorch3D's ``clip_faces`` does the same with two ``.item()``s)."""
+def any_vertex_behind_async(verts_world, R, T, table: ViewTable, z_plane: float):
+    """Asks the device whether some (view, vertex) has view-space depth < ``z_plane``: one small kernel and a
+    4-byte copy into pinned memory, both enqueued now.  Returns ``answer()``, which blocks until that copy has
+    landed -- NOT until later work on the stream has run -- so a caller can enqueue the render it expects to keep
+    first and read the answer afterwards without leaving the GPU idle."""
     _require_cuda(verts_world, "near-plane test")
     dev = verts_world.device
     state = _behind_flags.get(dev.index)
@@ -279,7 +281,22 @@ def any_vertex_behind(verts_world, R, T, table: ViewTable, z_plane: float) -> bo
                                            table.max_vert_count, float(z_plane), epoch, _ptr(flag), dev.index,
                                            _stream(dev)), "near-plane test")
     _bump(1)
-    return int(flag.item()) == epoch
+    host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+    host.copy_(flag, non_blocking=True)
+    event = torch.cuda.Event()
+    event.record(torch.cuda.current_stream(dev))
+
+    def answer() -> bool:
+        event.synchronize()
+        # epochs grow: a later query on another stream may have raised the flag past ours before the copy ran --
+        # then the answer errs towards True, which only sends the caller to clip_faces (exact) for nothing
+        return int(host[0]) >= epoch
+    return answer
+
+
+def any_vertex_behind(verts_world, R, T, table: ViewTable, z_plane: float) -> bool:
+    """Blocking form of ``any_vertex_behind_async`` (PyTorch3D's ``clip_faces`` reads two sums the same way)."""
+    return any_vertex_behind_async(verts_world, R, T, table, z_plane)()
 
 
 def rasterize_face_verts(face_verts, mesh_to_face_first_idx, num_faces_per_mesh, image_size, blur_radius=0.0,

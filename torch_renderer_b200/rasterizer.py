@@ -109,10 +109,12 @@ def set_near_plane_clipping(mode: str = "exact") -> None:
     """How ``MeshRasterizer`` treats faces that cross the near clipping plane ``z_clip_value`` (``znear / 2`` for
     cameras that define ``znear``, as upstream) or, with ``cull_to_frustum``, leave the view frustum.
 
-    ``"exact"`` (default): PyTorch3D's behaviour.  Every rasterisation with an active plane first asks the device
-    whether any vertex lies behind it (one small kernel and a 4-byte read -- upstream's ``clip_faces`` reads two
-    sums the same way); only then are the faces cut (``clip.clip_faces``) and drawn by the stand-alone rasteriser.
-    The question cannot be asked while a CUDA graph is being captured: captured renders behave like ``"off"``.
+    ``"exact"`` (default): PyTorch3D's behaviour.  Every rasterisation with an active plane asks the device whether
+    any vertex lies behind it (one small kernel and a 4-byte read -- upstream's ``clip_faces`` reads two sums the
+    same way), enqueues the fused render, and reads the answer afterwards, so the GPU is never left waiting for the
+    host; only on "yes" is that render dropped and the faces cut (``clip.clip_faces``) and drawn by the stand-alone
+    rasteriser.  The question cannot be asked while a CUDA graph is being captured: captured renders behave
+    like ``"off"``.
 
     ``"off"``: never ask.  Faces entirely behind the plane are still culled inside the kernels; a face crossing it
     is drawn whole (or dropped when a vertex is at / behind the camera plane).  For loops that are known to keep
@@ -336,23 +338,30 @@ class MeshRasterizer(nn.Module):
         tensors = (meshes_world._unique_verts(), meshes_world.faces_packed_i32()) + tuple(self._identity)
         return _fragment_cache.make_key(tensors, spec, meshes_world.view_table()), tensors
 
-    def _clipped_fragments(self, meshes_world: Meshes, R, T, proj, spec) -> Optional[Fragments]:
-        """The upstream ``clip_faces`` route (``set_near_plane_clipping``): Fragments when some vertex of the batch
-        lies behind the near plane (or ``cull_to_frustum`` removed faces), else ``None`` -- the caller then runs
-        the fused kernels, which cull what is entirely behind the plane themselves."""
+    def _near_plane_question(self, meshes_world: Meshes, R, T, spec):
+        """``None`` when this call has no clipping decision to make (no active plane, ``"off"``, graph capture);
+        else a callable that blocks until the device has said whether any vertex lies behind the plane.  The
+        question is ENQUEUED here; callers enqueue the fused render they expect to keep and only then read the
+        answer, so the host read never leaves the GPU idle (``ops.any_vertex_behind_async``)."""
         z_clip, cull = spec["z_clip_value"], spec["cull_to_frustum"]
+        if cull and _clipping_mode == "off":
+            raise ValueError("cull_to_frustum needs set_near_plane_clipping('exact')")
         if (z_clip is None and not cull) or _clipping_mode == "off" or torch.cuda.is_current_stream_capturing():
-            if cull and _clipping_mode == "off":
-                raise ValueError("cull_to_frustum needs set_near_plane_clipping('exact')")
             return None
+        if cull:
+            return lambda: True      # clip_faces decides (it culls against x, y planes too)
+        return ops.any_vertex_behind_async(meshes_world._unique_verts(), R, T, meshes_world.view_table(), z_clip)
+
+    def _clipped_fragments(self, meshes_world: Meshes, R, T, proj, spec) -> Optional[Fragments]:
+        """The upstream ``clip_faces`` route: transform, cut, draw with the stand-alone rasteriser, map back.
+        ``None`` when ``clip_faces`` leaves the face list untouched."""
         table = meshes_world.view_table()
-        if not cull and not ops.any_vertex_behind(meshes_world._unique_verts(), R, T, table, z_clip):
-            return None
         verts_ndc = ops.transform_verts(meshes_world._unique_verts(), R, T, proj, table, spec["perspective"])
         flags = spec["flags"]
         out = _rasterize_clipped(verts_ndc, meshes_world.faces_packed_i32(), table, spec["image_size"],
                                  spec["blur_radius"], spec["K"], bool(flags & _lib.PERSPECTIVE_CORRECT),
-                                 bool(flags & _lib.CLIP_BARYCENTRIC), bool(flags & _lib.CULL_BACKFACES), z_clip, cull)
+                                 bool(flags & _lib.CLIP_BARYCENTRIC), bool(flags & _lib.CULL_BACKFACES),
+                                 spec["z_clip_value"], spec["cull_to_frustum"])
         if out is None:
             return None
         return Fragments(pix_to_face=out[0], zbuf=out[1], bary_coords=out[2], dists=out[3])
@@ -363,13 +372,21 @@ class MeshRasterizer(nn.Module):
         cached = _fragment_cache.lookup(key, tensors)
         if cached is not None:
             return cached
-        clipped = self._clipped_fragments(meshes_world, R, T, proj, spec)
-        if clipped is not None:
-            return clipped
+        behind = self._near_plane_question(meshes_world, R, T, spec)
+        if behind is not None and spec["cull_to_frustum"]:
+            clipped = self._clipped_fragments(meshes_world, R, T, proj, spec)
+            if clipped is not None:
+                return clipped
+            behind = None
         token = {"consumed": False}
         spec["_token"] = token
         _, p2f, zbuf, bary, dists = ops.render(meshes_world._unique_verts(), None, R, T, proj, None,
                                                   meshes_world.faces_packed_i32(), meshes_world.view_table(), spec)
+        if behind is not None and behind():
+            # a vertex behind the near plane: the render above is discarded, faces are cut by clip_faces
+            clipped = self._clipped_fragments(meshes_world, R, T, proj, spec)
+            if clipped is not None:
+                return clipped
         fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
         _fragment_cache.store(key, tensors, fragments, token)
         return fragments

@@ -262,10 +262,14 @@ class MeshRenderer(nn.Module):
         cached = _fragment_cache.lookup(key, tensors)
         if cached is not None:
             return shader(cached, meshes_world, **kwargs), cached
-        # a vertex behind the near plane: faces are cut by clip_faces and drawn by the stand-alone rasteriser
-        clipped = rast._clipped_fragments(meshes_world, R, T, proj, spec)
-        if clipped is not None:
-            return shader(clipped, meshes_world, **kwargs), clipped
+        # near plane (rasterizer.set_near_plane_clipping): the question is enqueued now and read after the fused
+        # render has been enqueued; on "yes" the faces are cut by clip_faces and drawn by the stand-alone rasteriser
+        behind = rast._near_plane_question(meshes_world, R, T, spec)
+        if behind is not None and spec["cull_to_frustum"]:
+            clipped = rast._clipped_fragments(meshes_world, R, T, proj, spec)
+            if clipped is not None:
+                return shader(clipped, meshes_world, **kwargs), clipped
+            behind = None
         bg = blend_params.background_color
         bg = tuple(float(x) for x in (bg.tolist() if torch.is_tensor(bg) else bg))
         token = {"consumed": False}
@@ -276,6 +280,10 @@ class MeshRenderer(nn.Module):
         images, p2f, zbuf, bary, dists = ops.render(
             meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec,
             tex_map=tex_map)
+        if behind is not None and behind():
+            clipped = rast._clipped_fragments(meshes_world, R, T, proj, spec)
+            if clipped is not None:
+                return shader(clipped, meshes_world, **kwargs), clipped
         fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
         _fragment_cache.store(key, tensors, fragments, token)
         return images, fragments

@@ -5,6 +5,7 @@ mesh_deformer.py:181-222 -- per-vertex colours from multi-view images; deform_me
 autograd, the Fragments cache, TexturesUV and per-call camera overrides the way a user of the reference would."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -151,3 +152,83 @@ def test_vertex_offsets_from_silhouettes_converge():
     l1 = float(loss_fn().detach())
     assert l1 < 0.25 * l0, (l0, l1)
     assert torch.isfinite(deform).all()
+
+
+@pytest.mark.parametrize("kind,K,blur,shader_name", [("point", 1, 0.0, "soft"), ("directional", 4, 1e-3, "soft"),
+                                                     ("ambient", 1, 0.0, "soft"), ("point", 2, 0.0, "hard")])
+def test_light_and_material_colour_gradients(kind, K, blur, shader_name):
+    """d loss / d (light colours, material colours) -- SURVEY 8a row a11 -- against fp64 autograd of the oracle
+    shading on the same Fragments; MeshRenderer and the stand-alone shader give the same numbers."""
+    import torch_renderer_b200 as trb
+    from oracle import shading_ref as sref
+    from helpers import fov_proj, oracle_rasterize, rel_l2, uv_sphere
+    torch.manual_seed(5)
+    v, f = uv_sphere(14, 18, 1.0, noise=0.03, seed=2)
+    N, H, W = 2, 56, 64
+    R, T = trb.look_at_view_transform(dist=2.6, elev=torch.tensor([15.0, -30.0]), azim=torch.tensor([25.0, 140.0]))
+    cols = torch.rand(v.shape[0], 3)
+    names = ("ambient_color",) if kind == "ambient" else ("ambient_color", "diffuse_color", "specular_color")
+    light_vals = {"ambient_color": [[0.4, 0.5, 0.6]], "diffuse_color": [[0.35, 0.25, 0.3]], "specular_color": [[0.2, 0.3, 0.1]]}
+    mat_vals = {"ambient_color": [[0.9, 0.8, 1.0]], "diffuse_color": [[0.7, 1.0, 0.8]], "specular_color": [[1.0, 0.6, 0.9]]}
+    lt = {n: torch.tensor(light_vals[n], device=DEV, requires_grad=True) for n in names}
+    mt = {n: torch.tensor(mat_vals[n], device=DEV, requires_grad=True) for n in ("ambient_color", "diffuse_color", "specular_color")}
+    vec = [[0.5, 1.0, -2.5]]
+    if kind == "point":
+        lights = trb.PointLights(device=DEV, location=vec, **lt)
+    elif kind == "directional":
+        lights = trb.DirectionalLights(device=DEV, direction=vec, **lt)
+    else:
+        lights = trb.AmbientLights(device=DEV, **lt)
+    materials = trb.Materials(device=DEV, shininess=20.0, **mt)
+    mesh = trb.Meshes([v.to(DEV)], [f.to(DEV)], textures=trb.TexturesVertex(cols.to(DEV)[None])).extend(N)
+    cams = trb.FoVPerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV))
+    rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=(H, W), blur_radius=blur, faces_per_pixel=K))
+    blend = trb.BlendParams(1e-4, 1e-4, (0.2, 0.1, 0.3))
+    cls = trb.SoftPhongShader if shader_name == "soft" else trb.HardPhongShader
+    shader = cls(device=DEV, cameras=cams, lights=lights, materials=materials, blend_params=blend)
+    weights = torch.rand(N, H, W, 4)
+    params = list(lt.values()) + list(mt.values())
+    trb.set_fragment_cache(False)
+    try:
+        images, frag = trb.MeshRendererWithFragments(rast, shader)(mesh)
+        (images * weights.to(DEV)).sum().backward()
+        got = [None if p.grad is None else p.grad.clone().cpu() for p in params]
+        for p in params:
+            p.grad = None
+        images2 = shader(rast(mesh), mesh)
+        (images2 * weights.to(DEV)).sum().backward()
+        got2 = [None if p.grad is None else p.grad.clone().cpu() for p in params]
+        ndc = rast.transform(mesh).cpu().reshape(N, -1, 3)
+    finally:
+        trb.set_fragment_cache(True)
+    assert torch.allclose(images, images2, atol=1e-6)
+    for a, b in zip(got, got2):
+        assert (a is None) == (b is None) and (a is None or torch.allclose(a, b, rtol=1e-4, atol=1e-5))
+    # fp64 oracle on the same Fragments
+    want = oracle_rasterize(ndc, f, (H, W), blur, K, True, blur > 0)
+    assert np.array_equal(frag.pix_to_face.cpu().numpy(), want[0])
+    p2f = torch.from_numpy(want[0])
+    v64 = v.double()
+    zbuf, bary, dists = sref.raster_recompute(ndc.double()[:, f].reshape(-1, 3, 3), p2f, True, blur > 0)
+    l64 = {n: torch.tensor(light_vals[n], dtype=torch.float64, requires_grad=True) for n in names}
+    m64 = {n: torch.tensor(mat_vals[n], dtype=torch.float64, requires_grad=True) for n in mt}
+    rep = lambda t: t.expand(N, 3)
+    zero3 = torch.zeros(N, 3, dtype=torch.float64)
+    cam = -torch.matmul(T.double()[:, None, :], torch.linalg.inv(R.double()))[:, 0, :]
+    ref = sref.shade(p2f, bary, zbuf, dists, f.repeat(N, 1), v64, sref.vertex_normals(v64, f), cols.double(),
+                     shader="soft_phong" if shader_name == "soft" else "hard_phong", light_kind=kind,
+                     light_vec=torch.tensor(vec, dtype=torch.float64).expand(N, 3),
+                     light_ambient=rep(l64["ambient_color"]),
+                     light_diffuse=rep(l64["diffuse_color"]) if kind != "ambient" else zero3,
+                     light_specular=rep(l64["specular_color"]) if kind != "ambient" else zero3,
+                     mat_ambient=rep(m64["ambient_color"]), mat_diffuse=rep(m64["diffuse_color"]),
+                     mat_specular=rep(m64["specular_color"]), shininess=torch.full((N,), 20.0, dtype=torch.float64),
+                     camera_center=cam, sigma=1e-4, gamma=1e-4, background=(0.2, 0.1, 0.3), znear=1.0, zfar=100.0)
+    assert (images.detach().cpu().double() - ref).abs().max() < 1e-4
+    (ref * weights.double()).sum().backward()
+    want_grads = [l64[n].grad for n in names] + [m64[n].grad for n in mt]
+    for name, a, b in zip(list(names) + ["m_" + n for n in mt], got, want_grads):
+        if b is None or (kind == "ambient" and name in ("m_diffuse_color", "m_specular_color")):
+            assert a is None or float(a.abs().max()) == 0.0
+            continue
+        assert rel_l2(a, b) < 1e-3, (name, a, b)

@@ -42,6 +42,74 @@ def _scalar_rows(v, N: int, device) -> torch.Tensor:
     return _rows(v.reshape(-1, 1).float(), N, device, "znear/zfar")
 
 
+def _colour_products(N, device, lights, materials):
+    """(ambient, diffuse, specular) = material colour * light colour, f32 (N, 3) each (zeros for the terms an
+    ambient-only light does not have).  Differentiable torch ops: the kernels see the products only."""
+    amb = _rows(materials.ambient_color, N, device, "materials") * _rows(lights.ambient_color, N, device, "lights")
+    if getattr(lights, "kind", None) == "ambient":
+        zeros3 = torch.zeros((N, 3), dtype=torch.float32, device=device)
+        return amb, zeros3, zeros3
+    dif = _rows(materials.diffuse_color, N, device, "materials") * _rows(lights.diffuse_color, N, device, "lights")
+    spec = _rows(materials.specular_color, N, device, "materials") * _rows(lights.specular_color, N, device, "lights")
+    return amb, dif, spec
+
+
+class _ColourGradFn(torch.autograd.Function):
+    """Gradients w.r.t. the light / material COLOURS, without touching the kernels: the blended RGB is linear in
+    the three colour products (colour_k = ambient * texel + diffuse * texel * cos + specular * a^shininess, and the
+    blend weights do not depend on colour), channel by channel.  So d rgb / d ambient is the image shaded with
+    ambient = 1, diffuse = specular = background = 0, and likewise for the other two: three extra shade-only
+    passes over the stored Fragments in the backward, run only when a colour requires a gradient.  Forward is the
+    identity on ``images`` (the kernels' own parameter-block gradient is zero in the colour slots)."""
+
+    @staticmethod
+    def forward(ctx, images, amb, dif, spec, shade_args):
+        ctx.shade_args = shade_args
+        return images
+
+    @staticmethod
+    def backward(ctx, g_images):
+        (bary, zbuf, dists, verts, normals, colors, texels, vp, p2f, faces, table, cfg) = ctx.shade_args
+        need = ctx.needs_input_grad
+        g_rgb = g_images[..., :3]
+        unit = _lib.ShadeConfig()
+        ctypes_copy(unit, cfg)
+        unit.background[0] = unit.background[1] = unit.background[2] = 0.0
+        grads = []
+        for i, lo in enumerate((3, 6, 9)):           # slots of ambient / diffuse / specular in the parameter block
+            if not need[1 + i] or (lo > 3 and cfg.light_kind == _lib.LIGHT_AMBIENT):
+                grads.append(None)
+                continue
+            vp_i = vp.detach().clone()
+            vp_i[:, 3:12] = 0.0
+            vp_i[:, lo:lo + 3] = 1.0
+            img = ops.shade(bary.detach(), zbuf.detach(), dists.detach(), None if verts is None else verts.detach(),
+                            None if normals is None else normals.detach(),
+                            None if colors is None else colors.detach(),
+                            None if texels is None else texels.detach(), vp_i, p2f, faces, table, unit)
+            grads.append((g_rgb * img[..., :3]).sum(dim=(1, 2)))
+        return (g_images, *grads, None)
+
+
+def ctypes_copy(dst, src) -> None:
+    import ctypes
+    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(src))
+
+
+def _colours_require_grad(lights, materials) -> bool:
+    names = ("ambient_color",) if lights.kind == "ambient" else ("ambient_color", "diffuse_color", "specular_color")
+    return torch.is_grad_enabled() and any(getattr(o, n).requires_grad for o in (lights, materials) for n in names)
+
+
+def _with_colour_grads(images, lights, materials, shade_args):
+    """Hooks ``_ColourGradFn`` behind ``images`` when a light / material colour requires a gradient."""
+    if not _colours_require_grad(lights, materials):
+        return images
+    N = images.shape[0]
+    amb, dif, spec = _colour_products(N, images.device, lights, materials)
+    return _ColourGradFn.apply(images, amb, dif, spec, shade_args)
+
+
 def _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera_center=True) -> torch.Tensor:
     """f32 [N, 20] parameter block of the shade kernel (layout: include/trb.h).  With
     ``with_camera_center=False`` the camera-centre slots are left zero (the fused kernel fills them)."""
@@ -49,13 +117,14 @@ def _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera
     if kind not in _LIGHT_KIND:
         raise ValueError(f"unsupported lights object {type(lights).__name__}")
     zeros3 = torch.zeros((N, 3), dtype=torch.float32, device=device)
-    amb = _rows(materials.ambient_color, N, device, "materials") * _rows(lights.ambient_color, N, device, "lights")
+    amb, dif, spec = _colour_products(N, device, lights, materials)
     if kind == "ambient":
-        vec, dif, spec = zeros3, zeros3, zeros3
+        vec = zeros3
     else:
         vec = _rows(lights.location if kind == "point" else lights.direction, N, device, "lights")
-        dif = _rows(materials.diffuse_color, N, device, "materials") * _rows(lights.diffuse_color, N, device, "lights")
-        spec = _rows(materials.specular_color, N, device, "materials") * _rows(lights.specular_color, N, device, "lights")
+    if materials.shininess.requires_grad:
+        raise NotImplementedError("gradients w.r.t. Materials.shininess are not built (colours, light location / "
+                                  "direction and the camera are differentiable)")
     shin = _rows(materials.shininess.reshape(-1, 1), N, device, "materials")
     if kind != "ambient" and with_camera_center:
         cam = _rows(cameras.get_camera_center(), N, device, "cameras")
@@ -149,9 +218,10 @@ class _ShaderBase(nn.Module):
         zfar = kwargs.get("zfar", getattr(cameras, "zfar", 100.0))
         vp = _cached_view_params(self, N, dev, lights, materials, cameras, znear, zfar, True)
         cfg = _shade_config(fragments, shader, _LIGHT_KIND[lights.kind], tex_mode, blend_params)
-        return ops.shade(fragments.bary_coords, fragments.zbuf, fragments.dists, meshes._unique_verts(),
-                         meshes._unique_verts_normals(), colors, texels, vp, fragments.pix_to_face,
-                         meshes.faces_packed_i32(), table, cfg)
+        args = (fragments.bary_coords, fragments.zbuf, fragments.dists, meshes._unique_verts(),
+                meshes._unique_verts_normals(), colors, texels, vp, fragments.pix_to_face,
+                meshes.faces_packed_i32(), table, cfg)
+        return _with_colour_grads(ops.shade(*args), lights, materials, args)
 
 
 class SoftPhongShader(_ShaderBase):
@@ -248,6 +318,8 @@ class MeshRenderer(nn.Module):
             light_kind = _LIGHT_KIND.get(getattr(lights, "kind", None))
             if light_kind is None:
                 return None
+            if _colours_require_grad(lights, materials):
+                return None     # colour gradients hang off the stand-alone shader call (_ColourGradFn)
             # the shader asks its camera object for the centre; when that is the object the rasteriser
             # just used, the centre belongs to this call's R, T and the kernel derives it (and its
             # gradient) itself

@@ -280,3 +280,55 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
     assert "150" in r.stdout
+
+
+def test_clip_entry_points_and_host_logic_without_gpu():
+    """Argument checks of the clipping entry points (before any CUDA call), the face -> NDC-row map of the clipped
+    route, the mode switch, and the upstream module path of clip_faces through compat."""
+    L = _lib.lib()
+    p = 8  # any non-null pointer value: the checks below fail before it is dereferenced
+    ok = (p, p, p, p, 4, p, 1, 16, 16)
+    assert L.trb_clip_resequence(*ok, 151, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_K_TOO_LARGE
+    assert L.trb_clip_resequence(*ok, 0, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_clip_resequence(*ok, 2, -1.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_clip_resequence(p, p, p, p, -1, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_clip_resequence(p, p, p, p, 0, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_OK  # no pairs
+    assert L.trb_clip_resequence(p, p, None, p, 4, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, 0.5, 1, None, 0, None) == _lib.TRB_ERR_BAD_ARG   # no flag
+    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, float("nan"), 1, p, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_any_vertex_behind(p, p, p, p, 0, 10, 0.5, 1, p, 0, None) == _lib.TRB_OK               # empty batch
+
+    from torch_renderer_b200 import rasterizer
+    with pytest.raises(ValueError):
+        trb.set_near_plane_clipping("sometimes")
+    trb.set_near_plane_clipping("off")
+    assert rasterizer._clipping_mode == "off"
+    trb.set_near_plane_clipping()
+    assert rasterizer._clipping_mode == "exact"
+
+    v, f = uv_sphere(4, 6)
+    shared = trb.Meshes(verts=[v], faces=[f]).extend(3)
+    rows = rasterizer._face_vertex_rows(shared.faces_packed_i32(), shared.view_table())
+    assert rows.shape == (3 * f.shape[0], 3)
+    assert torch.equal(rows.reshape(3, -1, 3)[2], f + 2 * v.shape[0])
+    packed = trb.Meshes(verts=[v, v[:10]], faces=[f, f[:3].clamp(max=9)])
+    assert torch.equal(rasterizer._face_vertex_rows(packed.faces_packed_i32(), packed.view_table()),
+                       packed.faces_packed())
+    # z_clip_value resolution: znear / 2 only for perspective-correct renders of cameras that define znear
+    rast = trb.MeshRasterizer(trb.FoVPerspectiveCameras(znear=0.4), trb.RasterizationSettings(image_size=8))
+    one = trb.Meshes(verts=[v], faces=[f])
+    assert rast._resolve(one, {})[4]["z_clip_value"] == pytest.approx(0.2)
+    flat = trb.RasterizationSettings(image_size=8, perspective_correct=False)
+    assert rast._resolve(one, {"raster_settings": flat})[4]["z_clip_value"] is None
+    assert trb.MeshRasterizer(trb.PerspectiveCameras(), trb.RasterizationSettings(image_size=8))._resolve(one, {})[4]["z_clip_value"] is None
+    explicit = trb.RasterizationSettings(image_size=8, z_clip_value=0.05, cull_to_frustum=True)
+    spec = rast._resolve(one, {"raster_settings": explicit})[4]
+    assert spec["z_clip_value"] == pytest.approx(0.05) and spec["cull_to_frustum"] is True
+
+    import subprocess, sys
+    code = ("import torch_renderer_b200.compat as c; c.install()\n"
+            "from pytorch3d.renderer.mesh.clip import ClipFrustum, ClippedFaces, clip_faces, "
+            "convert_clipped_rasterization_to_original_faces\n"
+            "import torch_renderer_b200 as t; assert clip_faces is t.clip.clip_faces; print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

@@ -215,7 +215,7 @@ class _FragmentCache:
         ids = tuple((id(t), t._version) for t in tensors)
         raster = (spec["image_size"], spec["K"], spec["blur_radius"], spec["flags"], spec["z_clip"],
                   spec["perspective"], spec["cull_to_frustum"])
-        return (ids, raster, id(table), torch.is_grad_enabled())
+        return (ids, raster, id(table), torch.is_grad_enabled(), _clipping_mode)
 
     def lookup(self, key, tensors):
         if not self.enabled or self.key != key or self.value is None:

@@ -137,12 +137,14 @@ int trb_raster_backward(const float* verts_ndc, const int32_t* faces, const trb_
  * (at most one half per pixel) and overwritten in the four outputs; all other pixels are left as they are.
  * counters i32[1] (may be NULL) accumulates the number of re-rasterised pixels.
  */
-/* Raises *flag (persistent i32, never reset by the caller) to `epoch` when any (view, vertex) has view-space depth
- * < z_plane; epochs must grow from call to call.  MeshRasterizer asks this before every render with an active near
- * plane (upstream's clip_faces reads two sums on the host at the same place). */
+/* Raises *flag (persistent device i32, never reset by the caller) to `epoch` when any (view, vertex) has
+ * view-space depth < z_plane; epochs must grow from call to call.  With host_flag (pinned host i32) the flag is
+ * copied there on the stream, and with event (cudaEvent_t) the event is recorded after the copy: the caller waits
+ * on the event -- not on the stream -- and reads host_flag >= epoch.  MeshRasterizer asks this for every render
+ * with an active near plane (upstream's clip_faces reads two sums on the host at the same place). */
 int trb_any_vertex_behind(const float* verts_world, const float* R, const float* T, const trb_view* views, int N,
-                          int max_vert_count, float z_plane, int32_t epoch, int32_t* flag, int device,
-                          trb_stream_t stream);
+                          int max_vert_count, float z_plane, int32_t epoch, int32_t* flag, int32_t* host_flag,
+                          void* event, int device, trb_stream_t stream);
 int trb_clip_resequence(const float* face_verts, const trb_view* views, const int32_t* pair_face,
                         const int32_t* pair_view, int64_t num_pairs, const int32_t* neighbor, int N, int H,
                         int W, int K, float blur_radius, uint32_t flags, int64_t* pix_to_face, float* zbuf,

@@ -294,9 +294,9 @@ def test_clip_entry_points_and_host_logic_without_gpu():
     assert L.trb_clip_resequence(p, p, p, p, -1, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
     assert L.trb_clip_resequence(p, p, p, p, 0, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_OK  # no pairs
     assert L.trb_clip_resequence(p, p, None, p, 4, p, 1, 16, 16, 2, 0.0, 0, p, p, p, p, None, 0, None) == _lib.TRB_ERR_BAD_ARG
-    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, 0.5, 1, None, 0, None) == _lib.TRB_ERR_BAD_ARG   # no flag
-    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, float("nan"), 1, p, 0, None) == _lib.TRB_ERR_BAD_ARG
-    assert L.trb_any_vertex_behind(p, p, p, p, 0, 10, 0.5, 1, p, 0, None) == _lib.TRB_OK               # empty batch
+    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, 0.5, 1, None, None, None, 0, None) == _lib.TRB_ERR_BAD_ARG   # no flag
+    assert L.trb_any_vertex_behind(p, p, p, p, 1, 10, float("nan"), 1, p, None, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+
 
     from torch_renderer_b200 import rasterizer
     with pytest.raises(ValueError):

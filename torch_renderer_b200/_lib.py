@@ -59,7 +59,7 @@ _SIGNATURES = {
     "trb_raster_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32, _i64, _vp, _sz, _vp, _vp, _vp, _vp,
                            _vp, _i, _vp],
     "trb_raster_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-    "trb_any_vertex_behind": [_vp, _vp, _vp, _vp, _i, _i, _f, _c.c_int32, _vp, _i, _vp],
+    "trb_any_vertex_behind": [_vp, _vp, _vp, _vp, _i, _i, _f, _c.c_int32, _vp, _vp, _vp, _i, _vp],
     "trb_clip_resequence": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _f, _u32, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "trb_interp_forward": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i, _vp],
     "trb_interp_backward": [_vp, _vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _vp],

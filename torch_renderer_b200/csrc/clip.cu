@@ -176,14 +176,19 @@ using namespace trb;
 
 extern "C" int trb_any_vertex_behind(const float* verts_world, const float* R, const float* T, const trb_view* views,
                                      int N, int max_vert_count, float z_plane, int32_t epoch, int32_t* flag,
-                                     int device, trb_stream_t stream) {
+                                     int32_t* host_flag, void* event, int device, trb_stream_t stream) {
   if (N < 0 || max_vert_count < 0 || !(z_plane == z_plane) || !flag) return TRB_ERR_BAD_ARG;
-  if (N == 0 || max_vert_count == 0) return TRB_OK;
-  if (N > 65535 || !verts_world || !R || !T || !views) return TRB_ERR_BAD_ARG;
+  if (N > 65535) return TRB_ERR_BAD_ARG;
+  if (N > 0 && max_vert_count > 0 && (!verts_world || !R || !T || !views)) return TRB_ERR_BAD_ARG;
   TRB_ENTER(device);
-  any_vertex_behind_kernel<<<dim3(ceil_div(max_vert_count, 256), N), 256, 0, (cudaStream_t)stream>>>(
-      verts_world, R, T, views, z_plane, epoch, flag);
-  TRB_LAUNCH_CHECK();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > 0 && max_vert_count > 0) {
+    any_vertex_behind_kernel<<<dim3(ceil_div(max_vert_count, 256), N), 256, 0, st>>>(verts_world, R, T, views, z_plane,
+                                                                                      epoch, flag);
+    TRB_LAUNCH_CHECK();
+  }
+  if (host_flag) TRB_CUDA_TRY(cudaMemcpyAsync(host_flag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (event) TRB_CUDA_TRY(cudaEventRecord((cudaEvent_t)event, st));
   return TRB_OK;
 }
 

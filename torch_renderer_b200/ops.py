@@ -261,36 +261,49 @@ class _RasterizeFn(torch.autograd.Function):
         return (g_verts,) + (None,) * 8
 
 
-_behind_flags = {}   # device index -> [persistent int32 flag, epoch]
+class _BehindState:
+    """Per-device state of the near-plane question: the persistent device flag, a pinned host word the library
+    copies it into, the event it records after that copy, and the epoch counter."""
+
+    def __init__(self, dev: torch.device):
+        self.flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.host_word = ctypes.c_int32.from_address(self.host.data_ptr())
+        self.event = torch.cuda.Event()
+        with torch.cuda.device(dev):
+            self.event.record()          # materialises the cudaEvent_t handle
+        self.event.synchronize()
+        self.epoch = 0
+
+
+_behind_states = {}   # device index -> _BehindState
 
 
 def any_vertex_behind_async(verts_world, R, T, table: ViewTable, z_plane: float):
-    """Asks the device whether some (view, vertex) has view-space depth < ``z_plane``: one small kernel and a
-    4-byte copy into pinned memory, both enqueued now.  Returns ``answer()``, which blocks until that copy has
-    landed -- NOT until later work on the stream has run -- so a caller can enqueue the render it expects to keep
-    first and read the answer afterwards without leaving the GPU idle."""
+    """Asks the device whether some (view, vertex) has view-space depth < ``z_plane``: one small kernel, a 4-byte
+    copy into pinned memory and an event record, all enqueued by ONE C-ABI call.  Returns ``answer()``, which blocks
+    until that copy has landed -- NOT until later work on the stream has run -- so a caller can enqueue the render
+    it expects to keep first and read the answer afterwards without leaving the GPU idle.  One question per device
+    may be outstanding (ask, enqueue, answer)."""
     _require_cuda(verts_world, "near-plane test")
     dev = verts_world.device
-    state = _behind_flags.get(dev.index)
-    if state is None or state[1] >= 2**31 - 2:
-        state = _behind_flags[dev.index] = [torch.zeros((1,), dtype=torch.int32, device=dev), 0]
-    state[1] += 1
-    flag, epoch = state
+    st = _behind_states.get(dev.index)
+    if st is None or st.epoch >= 2**31 - 2:
+        st = _behind_states[dev.index] = _BehindState(dev)
+    st.epoch += 1
+    epoch = st.epoch
     verts_world, R, T = _f32c(verts_world), _f32c(R), _f32c(T)
     check(_lib.lib().trb_any_vertex_behind(_ptr(verts_world), _ptr(R), _ptr(T), _ptr(table.views), table.N,
-                                           table.max_vert_count, float(z_plane), epoch, _ptr(flag), dev.index,
-                                           _stream(dev)), "near-plane test")
+                                           table.max_vert_count, float(z_plane), epoch, _ptr(st.flag),
+                                           st.host.data_ptr(), st.event.cuda_event, dev.index, _stream(dev)),
+          "near-plane test")
     _bump(1)
-    host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
-    host.copy_(flag, non_blocking=True)
-    event = torch.cuda.Event()
-    event.record(torch.cuda.current_stream(dev))
 
     def answer() -> bool:
-        event.synchronize()
+        st.event.synchronize()
         # epochs grow: a later query on another stream may have raised the flag past ours before the copy ran --
         # then the answer errs towards True, which only sends the caller to clip_faces (exact) for nothing
-        return int(host[0]) >= epoch
+        return st.host_word.value >= epoch
     return answer
 
 

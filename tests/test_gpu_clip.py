@@ -236,3 +236,58 @@ def test_camera_translation_gradient_through_the_whole_clipped_route():
     (alpha * weights.double()).sum().backward()
     assert T64.grad.abs().max() > 1e-2
     assert rel_l2(T.grad.cpu(), T64.grad) < 5e-3
+
+
+def test_everything_behind_the_plane_renders_background():
+    """Camera in front of the whole mesh by less than the clip distance: clip_faces removes every face."""
+    trb = _trb()
+    v, f = uv_sphere(6, 8, 0.1)
+    mesh = trb.Meshes(verts=[v.to(DEV)], faces=[f.to(DEV)], textures=trb.TexturesVertex(torch.ones(1, v.shape[0], 3, device=DEV)))
+    cams = trb.FoVPerspectiveCameras(device=DEV, T=torch.tensor([[0.0, 0.0, 0.3]], device=DEV))   # depths 0.2 .. 0.4 < 0.5
+    rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=32, blur_radius=1e-3, faces_per_pixel=3))
+    trb.set_fragment_cache(False)
+    try:
+        frag = rast(mesh)
+        img = trb.MeshRenderer(rast, trb.SoftPhongShader(device=DEV, cameras=cams, blend_params=trb.BlendParams(
+            background_color=(0.25, 0.5, 0.75))))(mesh)
+    finally:
+        trb.set_fragment_cache(True)
+    assert (frag.pix_to_face == -1).all() and (frag.zbuf == -1).all() and (frag.bary_coords == -1).all()
+    # ... and an optimisation loop that wanders there gets zero gradients, not an exception
+    Tg = torch.tensor([[0.0, 0.0, 0.3]], device=DEV, requires_grad=True)
+    trb.set_fragment_cache(False)
+    try:
+        rast(mesh, T=Tg).zbuf.sum().backward()
+    finally:
+        trb.set_fragment_cache(True)
+    assert Tg.grad is not None and float(Tg.grad.abs().max()) == 0.0
+    assert torch.allclose(img[..., :3], torch.tensor([0.25, 0.5, 0.75], device=DEV).expand(1, 32, 32, 3), atol=1e-6)
+    assert float(img[..., 3].abs().max()) < 1e-6
+
+
+def test_mesh_rasterizer_cull_to_frustum_matches_oracle():
+    """cull_to_frustum through RasterizationSettings: faces wholly outside [-1, 1]^2 disappear -- with blur that
+    changes the band they would have cast into the frame -- on a heterogeneous (packed) batch."""
+    trb = _trb()
+    v0, f0 = uv_sphere(10, 12, 1.0, noise=0.03, seed=1)
+    v1, f1 = uv_sphere(8, 10, 0.8, noise=0.0, seed=2)
+    R, T = trb.look_at_view_transform(dist=torch.tensor([1.45, 1.2]), elev=torch.tensor([10.0, 40.0]), azim=torch.tensor([30.0, -100.0]))
+    mesh = trb.Meshes(verts=[v0.to(DEV), v1.to(DEV)], faces=[f0.to(DEV), f1.to(DEV)])
+    cams = trb.FoVPerspectiveCameras(device=DEV, R=R.to(DEV), T=T.to(DEV), fov=50.0)
+    H, W, K, blur = 48, 56, 4, 3e-3
+    frags = {}
+    for cull in (False, True):
+        rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=(H, W), blur_radius=blur, faces_per_pixel=K,
+                                                                 cull_to_frustum=cull))
+        frags[cull] = rast(mesh)
+        ndc = rast.transform(mesh).cpu()
+    fv = torch.cat([ndc[:v0.shape[0]][f0], ndc[v0.shape[0]:][f1]]).numpy()
+    first, count = np.array([0, f0.shape[0]]), np.array([f0.shape[0], f1.shape[0]])
+    for cull in (False, True):
+        cf = clip_ref.clip_faces(fv, first, count, clip_ref.rasterizer_frustum(True, 0.5, cull))
+        raw = oracle.rasterize_forward(cf.face_verts, cf.mesh_to_face_first_idx, cf.num_faces_per_mesh, (H, W), blur, K,
+                                       True, True, False, 0, clipped_faces_neighbor_idx=cf.clipped_faces_neighbor_idx)
+        p2f, bary = clip_ref.convert_clipped_rasterization_to_original_faces(raw[0], raw[2], cf)
+        fr = frags[cull]
+        _assert_close_fragments((fr.pix_to_face, fr.zbuf, fr.bary_coords, fr.dists), (p2f, raw[1], bary, raw[3]))
+    assert (frags[True].pix_to_face != frags[False].pix_to_face).any()

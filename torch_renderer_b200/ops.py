@@ -247,7 +247,7 @@ class _RasterizeFn(torch.autograd.Function):
         H, W, K = ctx.dims
         dev = verts_ndc.device
         g_verts = torch.zeros_like(verts_ndc)
-        if g_zbuf is None and g_bary is None and g_dists is None:
+        if (g_zbuf is None and g_bary is None and g_dists is None) or verts_ndc.numel() == 0:
             return (g_verts,) + (None,) * 8
         g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
         g_bary = None if g_bary is None else _f32c(g_bary)

@@ -4,7 +4,7 @@ YufengJin/torch_renderer.  All arithmetic runs in hand-written sm_100a kernels i
 (C ABI: ``include/trb.h``); there is no CPU or eager fallback."""
 from . import _lib, clip, io, loss, ops, renderer, structures, transforms, utils  # noqa: F401
 from .renderer import *  # noqa: F401,F403
-from .structures import Meshes, join_meshes_as_batch  # noqa: F401
+from .structures import Meshes, Pointclouds, join_meshes_as_batch, join_pointclouds_as_batch  # noqa: F401
 from .io import load_obj, load_objs_as_meshes, save_obj  # noqa: F401
 from .utils import ico_sphere  # noqa: F401
 from .ops import interpolate_face_attributes  # noqa: F401

@@ -71,6 +71,10 @@ _SIGNATURES = {
     "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _c.POINTER(UvTexture), _i, _vp],
     "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture), _i, _vp],
     "trb_debug_set_events": [_vp, _vp, _vp, _vp],
+    "trb_points_raster_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "trb_points_raster_backward": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "trb_points_composite_forward": [_i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp],
+    "trb_points_composite_backward": [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _i, _vp],
     "trb_nn_forward": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "trb_nn_backward": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "trb_allreduce_grid": [_i64],

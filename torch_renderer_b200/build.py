@@ -17,7 +17,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _OBJ = os.path.join(_PKG, "build")
 LIB_PATH = os.path.join(_PKG, "libtrb.so")
 
-SOURCES = ["api.cu", "raster.cu", "shade.cu", "transform.cu", "render.cu", "render_kn.cu", "render_stages.cu", "allreduce.cu", "points.cu", "clip.cu"]
+SOURCES = ["api.cu", "raster.cu", "shade.cu", "transform.cu", "render.cu", "render_kn.cu", "render_stages.cu", "allreduce.cu", "points.cu", "clip.cu", "points_render.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -4,7 +4,7 @@
 ``pytorch3d.io``, ``pytorch3d.transforms``, ``pytorch3d.utils``, ``pytorch3d.ops`` and ``pytorch3d.loss`` in
 ``sys.modules`` that resolve to this package (reference imports: renderer.py:7-26, torch_renderer.py:8-36,
 camera_pose_optimizer.py:13-43, mesh_deformer.py:12-40, myrenderer.py:36-49).  Names the package does
-not cover (point-cloud renderers, ``Pointclouds``, ICP, ``knn_points``) resolve to stubs that raise ``NotImplementedError`` when *used*, so
+not cover (``PulsarPointsRenderer``, Gouraud / flat shaders, ICP, ``knn_points``) resolve to stubs that raise ``NotImplementedError`` when *used*, so
 that module-level imports of the scripts still succeed.
 """
 from __future__ import annotations
@@ -13,10 +13,9 @@ import sys
 import types
 
 _OUT_OF_SCOPE = {
-    "pytorch3d.renderer": ["PointsRasterizationSettings", "PointsRenderer", "PulsarPointsRenderer",
-                           "PointsRasterizer", "AlphaCompositor", "NormWeightedCompositor", "TexturesAtlas",
-                           "SoftGouraudShader", "HardGouraudShader", "HardFlatShader"],
-    "pytorch3d.structures": ["Pointclouds"],
+    "pytorch3d.renderer": ["PulsarPointsRenderer", "TexturesAtlas", "SoftGouraudShader", "HardGouraudShader",
+                           "HardFlatShader"],
+    "pytorch3d.structures": [],
     "pytorch3d.ops": ["iterative_closest_point", "knn_points"],
     "pytorch3d.io": ["IO"],
 }

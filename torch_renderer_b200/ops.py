@@ -638,3 +638,107 @@ def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec
     if spec["K"] > _lib.MAX_FACES_PER_PIXEL:
         raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
     return _RenderFn.apply(verts, colors, tex_map, R, T, proj, view_params, faces, table, spec)
+
+
+# --------------------------------------------------------------------------------------------
+# Point clouds (csrc/points_render.cu)
+class _RasterizePointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points_ndc, radius, table: ViewTable, H, W, K):
+        _require_cuda(points_ndc, "rasterize_points")
+        points_ndc, radius = _f32c(points_ndc), _f32c(radius)
+        dev = points_ndc.device
+        N = table.N
+        idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        with _timed("points_raster_forward", dev):
+            check(_lib.lib().trb_points_raster_forward(_ptr(points_ndc), _ptr(radius), _ptr(table.views), N, H, W, K,
+                                                       _ptr(idx), _ptr(zbuf), _ptr(dists), dev.index, _stream(dev)),
+                  "rasterize_points")
+        _bump(1)
+        ctx.save_for_backward(points_ndc, idx)
+        ctx.dims = (N, H, W, K)
+        ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
+        return idx, zbuf, dists
+
+    @staticmethod
+    def backward(ctx, _g_idx, g_zbuf, g_dists):
+        points_ndc, idx = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        N, H, W, K = ctx.dims
+        dev = points_ndc.device
+        g_points = torch.zeros_like(points_ndc)
+        if (g_zbuf is None and g_dists is None) or points_ndc.numel() == 0:
+            return (g_points,) + (None,) * 5
+        g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
+        g_dists = None if g_dists is None else _f32c(g_dists)
+        with _timed("points_raster_backward", dev):
+            check(_lib.lib().trb_points_raster_backward(_ptr(points_ndc), _ptr(idx), _ptr(g_zbuf), _ptr(g_dists), N, H,
+                                                        W, K, _ptr(g_points), dev.index, _stream(dev)),
+                  "rasterize_points backward")
+        _bump(1)
+        return (g_points,) + (None,) * 5
+
+
+def rasterize_points_ndc(points_ndc, radius, table: ViewTable, image_size, points_per_pixel):
+    """points_ndc f32 (P, 3) packed, radius f32 (P,), one view per cloud -> (idx i32 (N,H,W,K), zbuf, dists)."""
+    H, W = image_size
+    if points_per_pixel > _lib.MAX_FACES_PER_PIXEL:
+        raise ValueError(f"Must have points_per_pixel <= {_lib.MAX_FACES_PER_PIXEL}")
+    return _RasterizePointsFn.apply(points_ndc, radius, table, int(H), int(W), int(points_per_pixel))
+
+
+COMPOSITE_ALPHA, COMPOSITE_NORM_WEIGHTED = 0, 1
+
+
+class _CompositeFn(torch.autograd.Function):
+    """idx i32 (N,H,W,K), alphas f32 (N,H,W,K), features f32 (P,C) -> images f32 (N,H,W,C)."""
+
+    @staticmethod
+    def forward(ctx, idx, alphas, features, background, mode: int):
+        _require_cuda(alphas, "compositor")
+        idx = idx.to(torch.int32).contiguous()
+        alphas, features = _f32c(alphas), _f32c(features)
+        background = None if background is None else _f32c(background)
+        dev = alphas.device
+        N, H, W, K = alphas.shape
+        C = features.shape[1]
+        images = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
+        with _timed("points_composite_forward", dev):
+            check(_lib.lib().trb_points_composite_forward(mode, _ptr(idx), _ptr(alphas), _ptr(features), N * H * W, K,
+                                                          C, _ptr(background), _ptr(images), dev.index, _stream(dev)),
+                  "compositor")
+        _bump(1)
+        ctx.save_for_backward(idx, alphas, features)
+        ctx.mode, ctx.has_background = mode, background is not None
+        return images
+
+    @staticmethod
+    def backward(ctx, g_images):
+        idx, alphas, features = ctx.saved_tensors
+        dev = alphas.device
+        N, H, W, K = alphas.shape
+        C = features.shape[1]
+        need = ctx.needs_input_grad
+        g_alphas = torch.empty_like(alphas) if need[1] else None
+        g_features = torch.zeros_like(features) if need[2] else None
+        with _timed("points_composite_backward", dev):
+            check(_lib.lib().trb_points_composite_backward(
+                ctx.mode, _ptr(idx), _ptr(alphas), _ptr(features), _ptr(_f32c(g_images)), N * H * W, K, C,
+                int(ctx.has_background), _ptr(g_alphas), _ptr(g_features), dev.index, _stream(dev)),
+                "compositor backward")
+        _bump(1)
+        return None, g_alphas, g_features, None, None
+
+
+def composite(idx, alphas, features, mode: int, background=None):
+    if idx.shape != alphas.shape or alphas.dim() != 4:
+        raise ValueError("idx and alphas must both have shape (N, H, W, K)")
+    if features.dim() != 2:
+        raise ValueError("features must have shape (P, C)")
+    if alphas.shape[-1] > _lib.MAX_FACES_PER_PIXEL:
+        raise ValueError(f"points_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
+    return _CompositeFn.apply(idx, alphas, features, background, mode)

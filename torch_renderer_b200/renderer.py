@@ -12,6 +12,9 @@ from .clip import (  # noqa: F401
 from .rasterizer import (  # noqa: F401
     Fragments, MeshRasterizer, RasterizationSettings, rasterize_meshes, set_fragment_cache,
     set_near_plane_clipping)
+from .points_renderer import (  # noqa: F401
+    AlphaCompositor, NormWeightedCompositor, PointFragments, PointsRasterizationSettings, PointsRasterizer,
+    PointsRenderer, alpha_composite, norm_weighted_sum, rasterize_points)
 from .shader import (  # noqa: F401
     HardPhongShader, MeshRenderer, MeshRendererWithFragments, SoftPhongShader, SoftSilhouetteShader,
     TexturedSoftPhongShader)

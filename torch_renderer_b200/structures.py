@@ -423,3 +423,6 @@ def join_meshes_as_batch(meshes: Sequence[Meshes], include_textures: bool = True
     if include_textures and all(m.textures is not None for m in meshes) and len(meshes) > 0:
         tex = meshes[0].textures.join_batch([m.textures for m in meshes[1:]])
     return Meshes(verts, faces, textures=tex)
+
+
+from .pointclouds import Pointclouds, join_pointclouds_as_batch  # noqa: E402,F401

@@ -142,7 +142,7 @@ def test_points_renderer_end_to_end(mode):
     want = pr.rasterize_points(ndc.numpy(), first, np.array(n_pts), radius, (H, W), K)
     assert (want[0][..., -1] >= 0).sum() > 50 and (want[0][..., 0] < 0).sum() > 50      # full and empty pixels both occur
     assert np.array_equal(frag.idx.cpu().numpy(), want[0])
-    assert np.allclose(frag.zbuf.cpu().numpy(), want[1], **TOL) and np.allclose(frag.dists.cpu().numpy(), want[2], **TOL)
+    assert np.allclose(frag.zbuf.detach().cpu().numpy(), want[1], **TOL) and np.allclose(frag.dists.detach().cpu().numpy(), want[2], **TOL)
     # fp64 route with idx fixed: transform -> dist^2 to the pixel centre -> weights -> compositor -> background
     p64 = [c.double().requires_grad_(True) for c in clouds]
     f64 = [f.double().requires_grad_(True) for f in feats]

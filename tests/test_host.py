@@ -203,7 +203,8 @@ def test_compat_alias_keeps_reference_import_lines_working():
         " Translate, axis_angle_to_matrix\n"
         "from pytorch3d.loss import chamfer_distance\n"
         "import torch_renderer_b200 as t; assert MeshRenderer is t.MeshRenderer\n"
-        "try:\n    Pointclouds()\nexcept NotImplementedError:\n    print('ok')\n")
+        "assert Pointclouds is t.Pointclouds and PointsRenderer is t.PointsRenderer\n"
+        "try:\n    PulsarPointsRenderer()\nexcept NotImplementedError:\n    print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
 

@@ -2,7 +2,7 @@
 // PointsRenderer uses (alpha compositing, normalised weighted sum; forward, backward).  Replaces
 // pytorch3d._C.rasterize_points(_backward), _C.accum_alphacomposite(_backward), _C.accum_weightedsumnorm(_backward)
 // behind the reference's AlphaPointRender / NormPointRender (torch_renderer.py:163-208) -- SURVEY 8f rank 4, last item.
-// Semantics: oracle/trb_oracle.c (trb_oracle_rasterize_points_*), oracle/points_render_ref.py.
+// Semantics: the point-rasteriser section of oracle/trb_oracle.c and oracle/points_render_ref.py.
 //
 // Rasteriser: one CTA per 16x16 pixel tile.  The view's points stream through the CTA 256 at a time; a point whose
 // disc can reach the tile is compacted into shared memory (x, y, z, r^2, index), then every thread tests its pixel

@@ -16,7 +16,7 @@ from typing import NamedTuple, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import ops
 from .pointclouds import Pointclouds
 from .rasterizer import _cached_projection, _check_bin_size, _expand_views, _parse_image_size
 

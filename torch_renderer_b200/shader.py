@@ -8,6 +8,7 @@ lighting and blending; the backward is one kernel as well.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -73,7 +74,7 @@ class _ColourGradFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         g_rgb = g_images[..., :3]
         unit = _lib.ShadeConfig()
-        ctypes_copy(unit, cfg)
+        ctypes.memmove(ctypes.byref(unit), ctypes.byref(cfg), ctypes.sizeof(cfg))
         unit.background[0] = unit.background[1] = unit.background[2] = 0.0
         grads = []
         for i, lo in enumerate((3, 6, 9)):           # slots of ambient / diffuse / specular in the parameter block
@@ -89,11 +90,6 @@ class _ColourGradFn(torch.autograd.Function):
                             None if texels is None else texels.detach(), vp_i, p2f, faces, table, unit)
             grads.append((g_rgb * img[..., :3]).sum(dim=(1, 2)))
         return (g_images, *grads, None)
-
-
-def ctypes_copy(dst, src) -> None:
-    import ctypes
-    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(src))
 
 
 def _colours_require_grad(lights, materials) -> bool:

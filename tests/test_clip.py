@@ -250,3 +250,31 @@ def test_ground_plane_through_the_near_plane_has_the_analytic_depth(K, blur):
     # no clipping: a vertex behind the camera kills both faces (A4.2)
     unclipped = oracle.rasterize_forward(ndc[faces].numpy(), [0], [2], (H, W), blur, K, True, blur > 0, False, 1)
     assert (unclipped[0] == -1).all()
+
+
+def test_neighbour_rule_only_matters_where_both_halves_are_candidates():
+    """The premise of the GPU design (csrc/clip.cu): upstream's order-dependent queue can differ from the plain
+    top-K only at pixels where BOTH halves of some cut face pass the candidate test -- everywhere else the fast
+    kernels' result stands.  Checked on random cut soups with the oracle alone (K = 150 lists every candidate)."""
+    rng = np.random.default_rng(3)
+    for trial, (K, blur, persp) in enumerate([(1, 2e-3, True), (2, 4e-3, False), (3, 1e-3, True), (1, 0.0, True)]):
+        F = 70
+        c = rng.uniform(-1.1, 1.1, size=(F, 1, 2))
+        fv = np.concatenate([c + rng.uniform(-0.35, 0.35, size=(F, 3, 2)), rng.uniform(0.05, 1.6, size=(F, 3, 1))], axis=2).astype(f32)
+        cf = clip_ref.clip_faces(fv, [0], [F], _frustum(persp))
+        nbr = cf.clipped_faces_neighbor_idx
+        assert (nbr >= 0).sum() >= 20
+        args = (cf.face_verts, cf.mesh_to_face_first_idx, cf.num_faces_per_mesh, (36, 36), blur)
+        ruled = oracle.rasterize_forward(*args, K, persp, blur > 0, False, 1, clipped_faces_neighbor_idx=nbr)
+        plain = oracle.rasterize_forward(*args, K, persp, blur > 0, False, 1)
+        every = oracle.rasterize_forward(*args, 150, persp, blur > 0, False, 1)[0]      # all candidates of every pixel
+        assert (every[..., -1] == -1).all()
+        partner = np.where(every >= 0, nbr[np.clip(every, 0, None)], -2)
+        partner = np.where(partner < 0, -2, partner)
+        both = (every[..., :, None] == partner[..., None, :]).any(axis=(-1, -2))         # some pair fully present
+        differs = (ruled[0] != plain[0]).any(axis=-1)
+        assert not (differs & ~both).any()
+        if blur > 0:
+            assert differs.any()
+        else:
+            assert not differs.any()

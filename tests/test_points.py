@@ -114,3 +114,21 @@ def test_points_call_surface_and_errors_without_gpu():
     assert L.trb_points_composite_forward(0, p, p, p, 10, 151, 3, None, p, 0, None) == _lib.TRB_ERR_K_TOO_LARGE
     assert L.trb_points_composite_forward(1, p, p, p, 0, 1, 3, None, p, 0, None) == _lib.TRB_OK
     assert L.trb_points_composite_backward(0, p, p, p, None, 10, 1, 3, 0, p, p, 0, None) == _lib.TRB_ERR_BAD_ARG
+
+
+def test_oracle_point_backward_matches_fp64_autograd():
+    torch.manual_seed(0)
+    pts = torch.rand(120, 3) * torch.tensor([2.0, 2.0, 2.0]) - torch.tensor([1.0, 1.0, 0.1])
+    H, W, K, r = 12, 10, 3, 0.25
+    idx, z, d = pr.rasterize_points(pts.numpy(), [0, 70], [70, 50], r, (H, W), K)
+    gz, gd = torch.randn(2, H, W, K), torch.randn(2, H, W, K)
+    m = torch.from_numpy(idx >= 0)
+    got = pr.rasterize_points_backward(pts.numpy(), idx, (gz * m).numpy(), (gd * m).numpy())
+    from oracle import shading_ref as sref
+    p64 = pts.double().requires_grad_(True)
+    ys, xs = sref.pixel_centers(H, W, torch.float64)
+    sel = p64[torch.from_numpy(idx).long().clamp(min=0)]
+    d2 = (xs.view(1, 1, W, 1) - sel[..., 0]) ** 2 + (ys.view(1, H, 1, 1) - sel[..., 1]) ** 2
+    assert np.allclose(d2.detach().numpy()[idx >= 0], d[idx >= 0], atol=1e-6)
+    ((d2 * gd * m).sum() + (sel[..., 2] * gz * m).sum()).backward()
+    assert np.allclose(got, p64.grad.numpy(), rtol=1e-5, atol=1e-6)

@@ -178,6 +178,25 @@ def test_obj_roundtrip_and_ico_sphere(tmp_path):
     assert f.verts_idx.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
     assert f.textures_idx.tolist()[:2] == [[0, 1, 2], [0, 2, 3]] and f.textures_idx.tolist()[2] == [-1, -1, -1]
     assert aux.verts_uvs.shape == (4, 2) and aux.normals.shape == (1, 3)
+    # textured save (deform_mesh_with_color.py:460): .obj + .mtl + .png, read back by load_obj / load_objs_as_meshes
+    uvs = torch.tensor([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    tex = (torch.arange(6 * 5 * 3, dtype=torch.float32).reshape(6, 5, 3) % 256) / 255.0
+    t = tmp_path / "colored.obj"
+    trb.save_obj(str(t), v, f.verts_idx, verts_uvs=uvs, faces_uvs=f.verts_idx[:, [0, 2, 1]], texture_map=tex)
+    assert (tmp_path / "colored.mtl").read_text().startswith("newmtl mesh\nmap_Kd colored.png\n")
+    v2, f2, aux2 = trb.load_obj(str(t))
+    assert torch.allclose(v2, v) and torch.equal(f2.verts_idx, f.verts_idx)
+    assert torch.equal(f2.textures_idx, f.verts_idx[:, [0, 2, 1]]) and torch.allclose(aux2.verts_uvs, uvs)
+    assert list(aux2.texture_images) == ["mesh"] and torch.allclose(aux2.texture_images["mesh"], tex, atol=1 / 255.0)
+    mesh = trb.load_objs_as_meshes([str(t)])
+    assert isinstance(mesh.textures, trb.TexturesUV) and torch.allclose(mesh.textures.maps_padded()[0], tex, atol=1 / 255.0)
+    with pytest.raises(ValueError):
+        trb.save_obj(str(t), v, f.verts_idx, verts_uvs=uvs[:, :1], faces_uvs=f.verts_idx, texture_map=tex)
+    with pytest.raises(ValueError):
+        trb.save_obj(str(t), v, f.verts_idx, verts_uvs=uvs, faces_uvs=f.verts_idx, texture_map=tex[..., :2])
+    plain = tmp_path / "plain.obj"     # a partial texture triple is ignored, as upstream
+    trb.save_obj(str(plain), v, f.verts_idx, verts_uvs=uvs)
+    assert "vt" not in plain.read_text() and not (tmp_path / "plain.mtl").exists()
 
 
 def test_golden_meshes_fixture():

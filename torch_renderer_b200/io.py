@@ -1,6 +1,6 @@
 """OBJ I/O with the ``pytorch3d.io`` surface the reference uses: ``load_obj`` (camera_pose_optimizer.py:87,
 myrenderer.py:66, mesh_deformer.py:12), ``load_objs_as_meshes`` (camera_pose_optimizer.py:102,
-renderer.py:106, mesh_deformer.py:92), ``save_obj`` (mesh_deformer.py:376).  Host-side only.
+renderer.py:106, mesh_deformer.py:92), ``save_obj`` (mesh_deformer.py:376; with a UV texture: deform_mesh_with_color.py:460).  Host-side only.
 """
 from __future__ import annotations
 
@@ -144,16 +144,50 @@ def load_objs_as_meshes(files: Sequence, device=None, load_textures: bool = True
     return join_meshes_as_batch(mesh_list)
 
 
-def save_obj(f, verts: torch.Tensor, faces: torch.Tensor, decimal_places: Optional[int] = None, **kwargs) -> None:
+def save_obj(f, verts: torch.Tensor, faces: torch.Tensor, decimal_places: Optional[int] = None, path_manager=None, *,
+             verts_uvs: Optional[torch.Tensor] = None, faces_uvs: Optional[torch.Tensor] = None,
+             texture_map: Optional[torch.Tensor] = None) -> None:
+    """Writes ``verts`` (V, 3) / ``faces`` (F, 3) as Wavefront OBJ.  With ``verts_uvs`` (Vt, 2), ``faces_uvs`` (F, 3)
+    and ``texture_map`` (H, W, 3) in [0, 1] all given (deform_mesh_with_color.py:460) the texture goes along as
+    upstream writes it: ``vt`` lines and ``v/vt`` face corners, ``<stem>.mtl`` naming ``<stem>.png``, and the map
+    saved as that PNG (``load_obj`` reads the triple back)."""
     if verts.dim() != 2 or verts.shape[1] != 3:
         raise ValueError("Argument 'verts' should either be empty or of shape (num_verts, 3).")
     if faces.numel() and (faces.dim() != 2 or faces.shape[1] != 3):
         raise ValueError("Argument 'faces' should either be empty or of shape (num_faces, 3).")
+    if faces_uvs is not None and (faces_uvs.dim() != 2 or faces_uvs.shape[1] != 3):
+        raise ValueError("Argument 'faces_uvs' should either be empty or of shape (num_faces, 3).")
+    if verts_uvs is not None and (verts_uvs.dim() != 2 or verts_uvs.shape[1] != 2):
+        raise ValueError("Argument 'verts_uvs' should either be empty or of shape (num_verts, 2).")
+    if texture_map is not None and (texture_map.dim() != 3 or texture_map.shape[2] != 3):
+        raise ValueError("Argument 'texture_map' should either be empty or of shape (H, W, 3).")
+    textured = verts_uvs is not None and faces_uvs is not None and texture_map is not None
+    if textured and faces_uvs.shape[0] != faces.shape[0]:
+        raise ValueError("faces_uvs must have one row per face")
+    path = os.fspath(f)
+    stem = os.path.splitext(os.path.basename(path))[0]
     fmt = "%f" if decimal_places is None else "%." + str(decimal_places) + "f"
     v = verts.detach().cpu().tolist()
     fc = (faces.detach().cpu() + 1).tolist()
-    with open(os.fspath(f), "w") as fh:
+    with open(path, "w") as fh:
+        if textured:
+            fh.write("\nmtllib %s.mtl\nusemtl mesh\n\n" % stem)
         for x in v:
             fh.write("v " + " ".join(fmt % c for c in x) + "\n")
-        for t in fc:
-            fh.write("f %d %d %d\n" % tuple(t))
+        if textured:
+            for uv in verts_uvs.detach().cpu().tolist():
+                fh.write("vt " + " ".join(fmt % c for c in uv) + "\n")
+            ft = (faces_uvs.detach().cpu() + 1).tolist()
+            for a, b in zip(fc, ft):
+                fh.write("f %d/%d %d/%d %d/%d\n" % (a[0], b[0], a[1], b[1], a[2], b[2]))
+        else:
+            for t in fc:
+                fh.write("f %d %d %d\n" % tuple(t))
+    if textured:
+        from PIL import Image
+        base = os.path.splitext(path)[0]
+        pixels = (texture_map.detach().cpu().float() * 255.0).clamp(0.0, 255.0).numpy().astype(np.uint8)
+        Image.fromarray(pixels).save(base + ".png")
+        with open(base + ".mtl", "w") as fh:
+            fh.write("newmtl mesh\nmap_Kd %s.png\n# Test colors\nKa 1.000 1.000 1.000\nKd 1.000 1.000 1.000\n"
+                     "Ks 0.000 0.000 0.000\nNs 10.0\n" % stem)

@@ -33,6 +33,8 @@ def laplacian_uniform(verts: np.ndarray, faces: np.ndarray) -> float:
     for i in range(len(verts)):
         if nb[i]:
             tot += np.linalg.norm(np.mean([verts[j] for j in nb[i]], axis=0) - verts[i])
+        else:
+            tot += np.linalg.norm(verts[i])     # upstream keeps L_ii = -1 for a vertex without neighbours
     return float(tot / len(verts))
 
 

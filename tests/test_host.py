@@ -352,3 +352,56 @@ def test_clip_entry_points_and_host_logic_without_gpu():
             "import torch_renderer_b200 as t; assert clip_faces is t.clip.clip_faces; print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_memoised_parameter_blocks_see_parameters_and_grad_flags():
+    """a light / camera attribute assigned as ``nn.Parameter`` lands in ``_parameters``; the memoised
+    view-parameter block and projection must see it (no stale values, no stale autograd graph), and the Fragments
+    cache key carries ``requires_grad``."""
+    import torch.nn as nn
+    from torch_renderer_b200 import shader as sh
+    from torch_renderer_b200.rasterizer import _cached_projection, _FragmentCache, _fragment_cache
+    from torch_renderer_b200.common import named_tensors
+
+    lights = trb.PointLights(location=[[0.0, 0.0, -3.0]])
+    materials = trb.Materials()
+    cams = trb.FoVPerspectiveCameras()
+    owner = nn.Module()
+    a = sh._cached_view_params(owner, 1, torch.device("cpu"), lights, materials, cams, 1.0, 100.0, False)
+    b = sh._cached_view_params(owner, 1, torch.device("cpu"), lights, materials, cams, 1.0, 100.0, False)
+    assert a is b                                              # constants: memoised
+    lights.location = nn.Parameter(torch.tensor([[1.0, 2.0, 3.0]]))
+    assert "location" in named_tensors(lights) and "location" not in lights.__dict__
+    c = sh._cached_view_params(owner, 1, torch.device("cpu"), lights, materials, cams, 1.0, 100.0, False)
+    assert c is not a and c.requires_grad and torch.equal(c[0, :3].detach(), torch.tensor([1.0, 2.0, 3.0]))
+    with torch.no_grad():
+        lights.location.mul_(2.0)
+    d = sh._cached_view_params(owner, 1, torch.device("cpu"), lights, materials, cams, 1.0, 100.0, False)
+    assert d is not c and torch.equal(d[0, :3].detach(), torch.tensor([2.0, 4.0, 6.0]))
+    d.sum().backward()                                         # a fresh graph every call
+    assert lights.location.grad is not None
+
+    pc = trb.PerspectiveCameras(focal_length=((1.0, 1.0),))
+    p0, _ = _cached_projection(pc, {})
+    pc.focal_length = nn.Parameter(torch.tensor([[1.0, 1.0]]))
+    with torch.no_grad():
+        pc.focal_length.mul_(2.0)
+    p1, _ = _cached_projection(pc, {})
+    assert p1.requires_grad and torch.allclose(p1[0, :2].detach(), 2.0 * p0[0, :2])
+    # .to() / clone() / indexing carry Parameter-valued attributes too
+    assert torch.equal(lights.clone().location, lights.location.detach())
+    assert lights[0].location.shape == (1, 3)
+
+    # the Fragments cache is opt-in, and its key sees requires_grad
+    assert _fragment_cache.enabled is False
+    t = torch.zeros(3)
+    spec = dict(image_size=(4, 4), K=1, blur_radius=0.0, flags=0, z_clip=0.0, perspective=True, cull_to_frustum=False)
+    k0 = _FragmentCache.make_key((t,), spec, None)
+    t.requires_grad_(True)
+    assert _FragmentCache.make_key((t,), spec, None) != k0
+
+    # get_camera_center remembers R / T overrides on the camera, like upstream
+    R = torch.eye(3)[None] * torch.tensor([1.0, -1.0, -1.0])
+    T = torch.tensor([[0.0, 0.0, 5.0]])
+    cams.get_camera_center(R=R, T=T)
+    assert cams.R is R and cams.T is T

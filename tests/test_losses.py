@@ -110,3 +110,18 @@ def test_deformation_losses_step_like_the_reference():
         opt.step()
         losses.append(float(l_ch.detach()))
     assert losses[-1] < 0.5 * losses[0], losses[::6]
+
+
+def test_regularisers_isolated_vertices_and_non_manifold_edges():
+    """Upstream keeps L_ii = -1 for a vertex no face uses (it contributes |v|), and pairs EVERY two faces that
+    share an edge, however many there are (a fan of 6 faces around one edge: 15 pairs)."""
+    verts = torch.tensor([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [3.0, 4.0, 0.0]])     # vertex 3 is isolated
+    faces = torch.tensor([[0, 1, 2]])
+    got = float(trb.mesh_laplacian_smoothing(trb.Meshes([verts], [faces])))
+    assert abs(got - points_ref.laplacian_uniform(verts.numpy(), faces.numpy())) < 1e-6
+    assert got > 5.0 / 4 - 1e-6                                                   # |(3,4,0)| / V alone is 1.25
+    g = torch.Generator().manual_seed(3)
+    fan_v = torch.cat([torch.tensor([[0.0, 0, 0], [0, 0, 1.0]]), torch.randn(6, 3, generator=g)])
+    fan_f = torch.tensor([[0, 1, 2 + i] for i in range(6)])
+    got = float(trb.mesh_normal_consistency(trb.Meshes([fan_v], [fan_f])))
+    assert abs(got - points_ref.normal_consistency(fan_v.numpy().astype(np.float64), fan_f.numpy())) < 1e-5

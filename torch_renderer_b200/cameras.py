@@ -113,14 +113,23 @@ class CamerasBase(TensorProperties):
         T = self.T if T is None else T
         return R, T
 
+    def _store_rt(self, R, T) -> None:
+        """Upstream's ``get_world_to_view_transform`` stores per-call overrides on the camera object."""
+        if R is not self.R:
+            self._set_tensor("R", R)
+        if T is not self.T:
+            self._set_tensor("T", T)
+
     def get_world_to_view_transform(self, **kwargs) -> Transform3d:
         R, T = self._rt(kwargs)
-        self.R, self.T = R, T  # upstream stores the overrides on the camera object
+        self._store_rt(R, T)
         return get_world_to_view_transform(R=R, T=T)
 
     def get_camera_center(self, **kwargs) -> torch.Tensor:
-        """Camera centre in world coordinates: ``-T @ inv(R)``."""
+        """Camera centre in world coordinates: ``-T @ inv(R)``.  Like upstream (which goes through
+        ``get_world_to_view_transform(**kwargs)``), ``R=`` / ``T=`` overrides are remembered on the camera."""
         R, T = self._rt(kwargs)
+        self._store_rt(R, T)
         return -torch.matmul(T[:, None, :], torch.linalg.inv_ex(R)[0])[:, 0, :]  # inv_ex: no host sync
 
     def get_full_projection_transform(self, **kwargs) -> Transform3d:

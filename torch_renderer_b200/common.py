@@ -53,6 +53,19 @@ def convert_to_tensors_and_broadcast(*args, dtype=torch.float32, device: Device 
 _MODULE_INTERNALS = frozenset(nn.Module().__dict__.keys())
 
 
+def named_tensors(obj) -> Dict[str, torch.Tensor]:
+    """Every tensor-valued attribute of ``obj``: plain attributes AND the ones ``nn.Module.__setattr__`` files
+    under ``_parameters`` / ``_buffers`` (``lights.location = nn.Parameter(...)``).  The memoised parameter blocks
+    (shader / rasteriser) key on these, so none may be skipped."""
+    d = obj.__dict__
+    out = {k: v for k, v in d.items() if torch.is_tensor(v)}
+    for store in ("_parameters", "_buffers"):
+        for k, v in (d.get(store) or {}).items():
+            if v is not None:
+                out[k] = v
+    return out
+
+
 class TensorProperties(nn.Module):
     """Holds named tensors broadcast to a common batch size N."""
 
@@ -93,12 +106,21 @@ class TensorProperties(nn.Module):
         return self._N == 0
 
     def _tensor_props(self):
-        return [k for k, v in self.__dict__.items() if torch.is_tensor(v)]
+        return list(named_tensors(self).keys())
+
+    def _set_tensor(self, k: str, v: torch.Tensor) -> None:
+        """Replaces a tensor attribute wherever it lives; a Parameter slot takes plain tensors only by
+        leaving ``_parameters`` (nn.Module refuses the assignment otherwise)."""
+        params = self.__dict__.get("_parameters")
+        if params is not None and k in params and not isinstance(v, nn.Parameter):
+            del params[k]
+        setattr(self, k, v)
 
     def to(self, device: Device = "cpu"):
         device = make_device(device)
-        for k in self._tensor_props():
-            setattr(self, k, self.__dict__[k].to(device))
+        for k, v in named_tensors(self).items():
+            if v.device != device:
+                self._set_tensor(k, v.to(device))
         self.device = device
         return self
 
@@ -115,6 +137,10 @@ class TensorProperties(nn.Module):
             if k in _MODULE_INTERNALS:
                 continue
             other.__dict__[k] = v.clone() if torch.is_tensor(v) else copy.copy(v)
+        for store in ("_parameters", "_buffers"):
+            for k, v in self.__dict__[store].items():
+                if v is not None:
+                    other.__dict__[k] = v.clone()     # a clone is a plain (non-leaf) tensor, as upstream
         return other
 
     def __getitem__(self, index):
@@ -122,8 +148,7 @@ class TensorProperties(nn.Module):
             index = [index]
         other = self.clone()
         n = None
-        for k in self._tensor_props():
-            v = other.__dict__[k]
+        for k, v in named_tensors(other).items():
             if v.dim() >= 1 and v.shape[0] == self._N:
                 sel = v[index]
                 setattr(other, k, sel)

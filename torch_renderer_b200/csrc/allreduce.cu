@@ -7,8 +7,9 @@
 // Push protocol, one kernel, ONE one-way NVLink latency: every rank writes each of its values, paired with
 // the call's epoch in the same 8-byte word, straight into an inbox in every peer's memory (torch symmetric
 // memory: each rank has all peers' inboxes mapped); the receiver polls its own inbox word by word until the
-// epoch matches -- an aligned 8-byte store is observed whole, so the flag validates the value it travels with
-// and no fence or barrier is needed -- and sums the contributions in rank order (every rank gets the
+// epoch matches -- value and epoch travel as ONE 64-bit scalar (st/ld.relaxed.sys.b64: single-copy atomic in
+// the PTX memory model, unlike a .v2.b32 pair), so the flag validates the value it arrives with and no fence
+// or barrier is needed -- and sums the contributions in rank order (every rank gets the
 // bit-identical result).  Inboxes are double-buffered by epoch parity: a sender rewrites a parity only two
 // calls later, after it has received the intervening call's data from that peer, i.e. after the peer finished
 // reading.  Block b always owns elements [b*1024, (b+1)*1024) and keeps its own epoch counter in device
@@ -28,16 +29,17 @@ struct ArSegments {
 };
 
 struct ArPeers {
-  uint2* inbox[kMaxPeers];  // rank r's inbox as mapped here: [2 parities][world senders][capacity] {value bits, epoch}
+  // rank r's inbox as mapped here: [2 parities][world senders][capacity] words of (epoch << 32 | value bits)
+  unsigned long long* inbox[kMaxPeers];
 };
 
-__device__ __forceinline__ void st_relaxed_sys_v2(uint2* addr, unsigned a, unsigned b) {
-  asm volatile("st.global.relaxed.sys.v2.b32 [%0], {%1, %2};" ::"l"(addr), "r"(a), "r"(b) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_b64(unsigned long long* addr, unsigned long long w) {
+  asm volatile("st.global.relaxed.sys.b64 [%0], %1;" ::"l"(addr), "l"(w) : "memory");
 }
-__device__ __forceinline__ uint2 ld_relaxed_sys_v2(const uint2* addr) {
-  uint2 v;
-  asm volatile("ld.global.relaxed.sys.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(addr) : "memory");
-  return v;
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_b64(const unsigned long long* addr) {
+  unsigned long long w;
+  asm volatile("ld.global.relaxed.sys.b64 %0, [%1];" : "=l"(w) : "l"(addr) : "memory");
+  return w;
 }
 
 __global__ void __launch_bounds__(256)
@@ -61,28 +63,33 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
       dst[u] = seg.ptr[s] + (i - seg.start[s]);
       v[u] = *dst[u];
       for (int r = 0; r < world; ++r)
-        if (r != rank) st_relaxed_sys_v2(p.inbox[r] + parity_off + (size_t)rank * capacity + i, __float_as_uint(v[u]), epoch);
+        if (r != rank)
+          st_relaxed_sys_b64(p.inbox[r] + parity_off + (size_t)rank * capacity + i,
+                             ((unsigned long long)epoch << 32) | __float_as_uint(v[u]));
     }
   }
   // ---- 2. collect the peers' values from my inbox, sum in rank order
-  const uint2* mine = p.inbox[rank] + parity_off;
+  const unsigned long long* mine = p.inbox[rank] + parity_off;
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
     if (dst[u] == nullptr) continue;
     const long long i = (long long)blockIdx.x * kArChunk + u * 256 + threadIdx.x;
     float acc = 0.0f;
-    for (int r = 0; r < world; ++r) {
+    bool ok = true;
+    for (int r = 0; r < world && ok; ++r) {
       if (r == rank) { acc += v[u]; continue; }
-      const uint2* src = mine + (size_t)r * capacity + i;
-      uint2 w = ld_relaxed_sys_v2(src);
+      const unsigned long long* src = mine + (size_t)r * capacity + i;
+      unsigned long long w = ld_relaxed_sys_b64(src);
       unsigned spins = 0;
-      while (w.y != epoch) {
-        if (++spins > (1u << 26)) { atomicExch(error, 1); break; }
-        w = ld_relaxed_sys_v2(src);
+      while ((unsigned)(w >> 32) != epoch) {
+        if (++spins > (1u << 26)) { atomicExch(error, 1); ok = false; break; }
+        w = ld_relaxed_sys_b64(src);
       }
-      acc += __uint_as_float(w.x);
+      acc += __uint_as_float((unsigned)w);
     }
-    *dst[u] = acc;
+    // a peer that never arrived: the partial sum is NOT written (the local gradient stays as it was and the
+    // error flag tells the host -- PeerAllReduce.check())
+    if (ok) *dst[u] = acc;
   }
   __syncthreads();
   if (threadIdx.x == 0) epochs[blockIdx.x] = epoch;
@@ -121,7 +128,7 @@ extern "C" int trb_allreduce_sum_f32(float* const* host_segments, const int64_t*
   if (total > capacity_floats) return TRB_ERR_BAD_ARG;
   ArPeers p;
   for (int r = 0; r < kMaxPeers; ++r) {
-    p.inbox[r] = r < world ? (uint2*)host_peer_inbox[r] : nullptr;
+    p.inbox[r] = r < world ? (unsigned long long*)host_peer_inbox[r] : nullptr;
     if (r < world && !p.inbox[r]) return TRB_ERR_BAD_ARG;
   }
   TRB_ENTER(device);

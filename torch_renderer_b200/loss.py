@@ -133,7 +133,7 @@ def mesh_laplacian_smoothing(meshes: Meshes, method: str = "uniform") -> torch.T
     deg = deg.index_add(0, e0, ones).index_add(0, e1, ones)
     nb = torch.zeros_like(verts).index_add(0, e0, verts[e1]).index_add(0, e1, verts[e0])
     inv = torch.where(deg > 0, 1.0 / deg.clamp(min=1.0), torch.zeros_like(deg))
-    lap = nb * inv[:, None] - verts * (deg > 0).to(verts.dtype)[:, None]   # L v with L_ii = -1, L_ij = 1/deg(i)
+    lap = nb * inv[:, None] - verts   # L v with L_ii = -1 for EVERY vertex (isolated ones contribute |v|, as upstream)
     v2m = torch.bucketize(torch.arange(V, device=verts.device), meshes.mesh_to_verts_packed_first_idx(), right=True) - 1
     per_mesh = meshes.num_verts_per_mesh().clamp(min=1).to(verts.dtype)
     w = 1.0 / per_mesh[v2m]
@@ -160,13 +160,17 @@ def mesh_normal_consistency(meshes: Meshes) -> torch.Tensor:
     same_next = key_s[1:] == key_s[:-1]
     if not bool(same_next.any()):
         return torch.zeros((), dtype=verts.dtype, device=verts.device)
-    # runs are short (2 for a manifold edge); pair (i, j) for j in the same run, offsets 1..3
+    # every pair (i, j), i < j, of a run (2 entries for a manifold edge; longer runs for non-manifold ones):
+    # offset by offset until no run is that long
     pairs = []
-    for off in (1, 2, 3):
-        if key_s.shape[0] > off:
-            m = key_s[off:] == key_s[:-off]
-            i = torch.nonzero(m, as_tuple=False)[:, 0]
-            pairs.append(torch.stack([order[i], order[i + off]], dim=1))
+    off = 1
+    while key_s.shape[0] > off:
+        m = key_s[off:] == key_s[:-off]
+        i = torch.nonzero(m, as_tuple=False)[:, 0]
+        if i.numel() == 0:
+            break
+        pairs.append(torch.stack([order[i], order[i + off]], dim=1))
+        off += 1
     pairs = torch.cat(pairs, dim=0)
     a, b = pairs[:, 0], pairs[:, 1]
     v0, v1 = verts[lo[a]], verts[hi[a]]

@@ -4,9 +4,11 @@ Views are independent in the forward pass, so every rank renders a contiguous sl
 batch against a replicated mesh with no data-path collective.  The backward needs exactly one
 exchange: parameters shared by all views (vertices, vertex colours / texture map, a shared pose)
 receive per-rank partial gradients that are summed in ONE kernel over NVLink / NVSwitch peer memory
-(``PeerAllReduce`` -> csrc/allreduce.cu: stage, flag barrier, sum the peers' buffers; 35 KB for the cow ..
-12 MB for a 1M-face mesh -- latency regime), with a single fused NCCL all-reduce as the fallback when
-symmetric memory is not available (and on CPU / gloo).  Per-view camera gradients stay local.
+(``PeerAllReduce`` -> csrc/allreduce.cu: every rank pushes (epoch, value) words straight into all peers'
+inboxes and sums what arrives in its own -- one one-way NVLink latency, no barrier; messages up to 256 KB,
+e.g. 70 KB for the cow), with a single fused NCCL all-reduce for larger sums (12 MB for a 1M-face mesh:
+bandwidth regime), when symmetric memory is not available, and on CPU / gloo.  Per-view camera gradients
+stay local.
 
 The reference has no distributed path at all (every script pins cuda:0); this is the
 B200-native addition BASELINE.json's north_star asks for.
@@ -89,10 +91,12 @@ class PeerAllReduce:
     def check(self) -> None:
         """Raises if a peer's data did not arrive (synchronises; call outside timed regions)."""
         if int(self.error.item()) != 0:
-            raise RuntimeError("PeerAllReduce: a peer's contribution did not arrive within the spin limit")
+            raise RuntimeError("PeerAllReduce: a peer's contribution did not arrive within the spin limit; "
+                               "the affected gradients were left un-reduced")
 
 
 _peer_allreduce = {}
+_CHECK_EVERY = 1024     # allreduce_shared_grads reads the error flag (one device sync) every this many calls
 
 
 def _get_peer_allreduce(n_floats: int, device: torch.device, group):
@@ -107,10 +111,24 @@ def _get_peer_allreduce(n_floats: int, device: torch.device, group):
         try:
             cur = PeerAllReduce(PeerAllReduce.MAX_FLOATS, device, group)
         except Exception:  # noqa: BLE001 -- no symmetric memory / no P2P: NCCL does it
+            cur = None
+        # The route is agreed on COLLECTIVELY: if set-up failed on any rank, every rank takes NCCL (a rank that
+        # pushed while a peer sat in dist.all_reduce would spin until the limit).
+        ok = torch.tensor([0 if cur is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
             _peer_allreduce[key] = False
             return None
+        cur.calls = 0
         _peer_allreduce[key] = cur
     return cur
+
+
+def check_peer_allreduce() -> None:
+    """Raises if any peer-memory all-reduce issued so far timed out (synchronises the device)."""
+    for v in _peer_allreduce.values():
+        if v not in (None, False):
+            v.check()
 
 
 def allreduce_shared_grads(tensors: Sequence[Optional[torch.Tensor]], group=None, async_op: bool = False):
@@ -129,6 +147,9 @@ def allreduce_shared_grads(tensors: Sequence[Optional[torch.Tensor]], group=None
         peer = _get_peer_allreduce(sum(g.numel() for g in grads), grads[0].device, group)
         if peer is not None:
             peer(grads)
+            peer.calls += 1
+            if peer.calls % _CHECK_EVERY == 0 and not torch.cuda.is_current_stream_capturing():
+                peer.check()
             return None
     flat = torch.cat([g.reshape(-1).float() for g in grads])
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, clip, ops
+from .common import named_tensors
 from .structures import Meshes
 
 kMaxBinsPerDim = 22  # PyTorch3D refuses bin grids this large; kept for error parity
@@ -160,7 +161,7 @@ def _cached_projection(cameras, proj_kwargs):
     untouched constants (keyed on tensor identity + version) -- a handful of tiny launches saved per call."""
     if proj_kwargs:
         return cameras.ndc_projection_params(**proj_kwargs)
-    tensors = [(k, v) for k, v in cameras.__dict__.items() if torch.is_tensor(v) and k not in ("R", "T")]
+    tensors = [(k, v) for k, v in named_tensors(cameras).items() if k not in ("R", "T")]
     if any(v.requires_grad for _, v in tensors):
         return cameras.ndc_projection_params()
     key = tuple((k, id(v), v._version) for k, v in tensors)
@@ -196,10 +197,15 @@ class _FragmentCache:
     on the stored Fragments, and the backward rasterises once (autograd sums the three gradient streams).
 
     One entry; entries above ``max_bytes`` are not kept (a chunk of a 1024-view job must not stay alive past
-    its iteration); nothing is stored while a CUDA graph is being captured."""
+    its iteration); nothing is stored while a CUDA graph is being captured.
+
+    OPT-IN (``set_fragment_cache(True)``).  The key sees tensor identity, ``_version`` and ``requires_grad``;
+    writes that do not bump ``_version`` -- through ``.data``, a numpy view of a CPU tensor, a raw pointer in a
+    custom kernel -- are invisible to it and would return the previous Fragments.  A loop that updates its inputs
+    only through autograd-visible in-place ops (every torch optimiser) or by building new tensors is safe."""
 
     def __init__(self):
-        self.enabled = True
+        self.enabled = False
         self.max_bytes = 2 << 30
         self.key = None
         self.refs = ()
@@ -212,7 +218,7 @@ class _FragmentCache:
 
     @staticmethod
     def make_key(tensors, spec, table):
-        ids = tuple((id(t), t._version) for t in tensors)
+        ids = tuple((id(t), t._version, t.requires_grad) for t in tensors)
         raster = (spec["image_size"], spec["K"], spec["blur_radius"], spec["flags"], spec["z_clip"],
                   spec["perspective"], spec["cull_to_frustum"])
         return (ids, raster, id(table), torch.is_grad_enabled(), _clipping_mode)
@@ -245,7 +251,8 @@ _fragment_cache = _FragmentCache()
 
 
 def set_fragment_cache(enabled: bool = True, max_bytes: Optional[int] = None) -> None:
-    """Switches the reuse of Fragments between back-to-back renders of identical inputs on or off."""
+    """Switches the reuse of Fragments between back-to-back renders of identical inputs on or off (default: off;
+    see ``_FragmentCache`` for what "identical" can and cannot see)."""
     _fragment_cache.enabled = bool(enabled)
     if max_bytes is not None:
         _fragment_cache.max_bytes = int(max_bytes)

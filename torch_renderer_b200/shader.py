@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .blending import BlendParams
+from .common import named_tensors
 from .lighting import AmbientLights, DirectionalLights, Materials, PointLights
 from .rasterizer import Fragments
 from .structures import Meshes
@@ -133,7 +134,8 @@ def _view_params(N, device, lights, materials, cameras, znear, zfar, with_camera
 
 def _cached_view_params(owner, N, device, lights, materials, cameras, znear, zfar, with_camera_center):
     """Memoises the parameter block on the shader while every input is an unmodified constant."""
-    tensors = [v for obj in (lights, materials) for v in obj.__dict__.values() if torch.is_tensor(v)]
+    # plain attributes, Parameters and buffers alike (``lights.location = nn.Parameter(...)`` lands in _parameters)
+    tensors = [v for obj in (lights, materials) for v in named_tensors(obj).values()]
     tensors += [v for v in (znear, zfar) if torch.is_tensor(v)]
     if with_camera_center:
         tensors += [cameras.R, cameras.T]

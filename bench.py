@@ -118,7 +118,7 @@ class ClockSampler:
 
 def _scene(device):
     import torch_renderer_b200 as trb
-    from helpers import load_mesh
+    from bench_workloads import load_mesh      # reads tests/golden/meshes.npz itself; no oracle import on this arm
     v, f = load_mesh("cow")
     torch.manual_seed(0)
     colors = torch.rand(v.shape[0], 3)
@@ -246,20 +246,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    def timed(fn, steps, repeats=None):
+        """Median over `repeats` repeats of: EXACTLY `steps` steps between CUDA events on the launching stream,
+        bracketed by barrier + synchronize on both sides, max over ranks.  Returns (median ms, all repeats)."""
+        out = []
+        for _ in range(repeats or args.repeats):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out.append(ms)
+        return statistics.median(out), out
 
     for _ in range(args.warmup):
         step_device()
@@ -281,7 +286,7 @@ def run_ours(args):
     # a fixed step count so that every rank issues the same number of all-reduces
     for _ in range(1500):
         run_device()
-    ms_total = timed(run_device, args.steps)
+    ms_total, ms_repeats = timed(run_device, args.steps)
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -334,7 +339,7 @@ def run_ours(args):
 
     for _ in range(max(3, args.warmup)):
         run_e2e()
-    ms_e2e = timed(run_e2e, args.steps) / args.steps
+    ms_e2e = timed(run_e2e, args.steps)[0] / args.steps
     e2e_value = world * N / (ms_e2e / 1e3)
     h2d = host_in.numel() * 4
     d2h = host_out.numel() * 4
@@ -342,8 +347,54 @@ def run_ours(args):
     from torch_renderer_b200 import parallel as _par
     peer = [v for v in _par._peer_allreduce.values() if v not in (None, False)]
     for v in peer:
-        v.check()   # no rank missed a flag barrier
+        v.check()   # no peer's contribution timed out
     collective = "none" if world == 1 else ("peer-memory one-shot kernel (csrc/allreduce.cu)" if peer else "nccl all-reduce")
+
+    # Is the reduced gradient RIGHT?  One more step: the local (pre-reduction) gradients are kept, reduced by the
+    # product path, and compared with (a) the rank-ordered sum of an all_gather of the local copies -- bit-exact,
+    # the peer kernel sums in rank order -- and (b) NCCL's own all-reduce of the copies (its order is its own:
+    # tolerance).  Every rank checks its own result; the verdicts are AND-ed.
+    collective_check = None
+    if world > 1:
+        core_device()
+        local = [verts.grad.detach().clone(), cols.grad.detach().clone()]
+        allreduce_shared_grads([verts.grad, cols.grad])
+        ok_exact = ok_close = True
+        for mine, loc in zip((verts.grad, cols.grad), local):
+            gathered = [torch.empty_like(loc) for _ in range(world)]
+            dist.all_gather(gathered, loc)
+            want = gathered[0].clone()
+            for g in gathered[1:]:
+                want += g
+            ok_exact = ok_exact and bool(torch.equal(mine, want))
+            nccl = loc.clone()
+            dist.all_reduce(nccl)
+            ok_close = ok_close and bool(torch.allclose(mine, nccl, rtol=1e-4, atol=1e-6 * float(nccl.abs().max())))
+        flags = torch.tensor([int(ok_exact), int(ok_close)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        ok_exact, ok_close = bool(flags[0].item()), bool(flags[1].item())
+        collective_check = ("ok" if (ok_close and (ok_exact or not peer)) else "MISMATCH") + \
+            f" (rank-ordered sum bit-exact: {ok_exact}; vs NCCL all-reduce within 1e-4: {ok_close}; all {world} ranks)"
+
+    # the same step launched EAGERLY with the default near-plane handling ("exact": every render asks the device
+    # whether a vertex lies behind z_clip and reads the answer after enqueueing) -- what a reference script that
+    # only switched its imports gets without graph capture
+    trb.set_near_plane_clipping("exact")
+    for _ in range(args.warmup):
+        step_device()
+    ms_eager = timed(step_device, args.steps)[0] / args.steps
+    trb.set_near_plane_clipping("off")
+    eager = {"value": round(world * N / (ms_eager / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms_eager, 4),
+             "launch_mode": "eager", "near_plane": "exact (asked every step)"}
+
+    # every other BASELINE config (C1, C3, C4, the reference's pose step, one chunk of C5) on this GPU, and C5 as
+    # specified (1024 views in total, strong-scaled over the ranks)
+    other = None
+    if world == 1 and not args.no_configs:
+        other = measure_other_configs(dev, args, peak)
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5_spec(dev, world, rank, args, peak, barrier)
 
     cpu = cpu_baseline(sample_views=args.cpu_views) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -362,6 +413,10 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e, 4)},
             "gpu_launches": launches,
+            "timing": {"protocol": f"median of {args.repeats} repeats of {args.steps} steps, CUDA events on the launching "
+                                   "stream, barrier + synchronize around every repeat, max over ranks",
+                       "ms_per_step_repeats": [round(m / args.steps, 4) for m in ms_repeats]},
+            "eager_exact": eager,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": round(per_launch_ms[dominant], 4),
@@ -375,9 +430,158 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if collective_check is not None:
+            line["collective_check"] = collective_check
+        if other is not None:
+            line["other_configs"] = other
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_other_configs(dev, args, peak):
+    """C1, C3 (teapot, cow), C4, the reference's camera_pose_optimizer step and one 4-view chunk of C5 through the
+    public API, eager: ms/step = median of `repeats` repeats of `steps` steps (CUDA events), the two fused kernels'
+    own durations (events recorded by libtrb around them), per C-ABI-call times, algorithmic GB/s (SURVEY 8d byte
+    model) and its fraction of the measured HBM peak."""
+    import torch_renderer_b200 as trb
+    import bench_workloads as wl
+    from torch_renderer_b200 import _lib, ops
+    out = {}
+    plan = (("C1", 20), ("C3", 20), ("C3cow", 20), ("C4", 20), ("pose_step", 20), ("pose_step_cached", 20), ("C5", 3))
+    for name, steps in plan:
+        trb.set_fragment_cache(False)
+        trb.set_near_plane_clipping("exact")     # the defaults a drop-in script gets
+        try:
+            step, info = wl.BUILDERS[name](dev)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            reps, host = [], []
+            for _ in range(args.repeats):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                for _ in range(steps):
+                    step()
+                host.append((time.perf_counter() - t0) / steps * 1e3)
+                e1.record()
+                torch.cuda.synchronize()
+                reps.append(e0.elapsed_time(e1) / steps)
+            ms = statistics.median(reps)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for e in evs:
+                e.record()
+            torch.cuda.synchronize()
+            _lib.lib().trb_debug_set_events(*[e.cuda_event for e in evs])
+            ops.start_event_log()
+            fine, bwd = [], []
+            for _ in range(min(steps, 10)):
+                step()
+                torch.cuda.synchronize()
+                fine.append(evs[0].elapsed_time(evs[1]))
+                if name != "C1":
+                    bwd.append(evs[2].elapsed_time(evs[3]))
+            _lib.lib().trb_debug_set_events(None, None, None, None)
+            calls = ops.stop_event_log()
+            gbs = info["bytes"] / ms / 1e6
+            out[name] = {"what": info["what"], "views_per_s": round(info["views"] / ms * 1e3, 2),
+                         "ms_per_step": round(ms, 4), "ms_per_step_repeats": [round(r, 4) for r in reps],
+                         "host_issue_ms_per_step": round(statistics.median(host), 4), "steps": steps,
+                         "fine_kernel_ms": round(statistics.median(fine), 4),
+                         "backward_kernel_ms": round(statistics.median(bwd), 4) if bwd else None,
+                         "calls_ms": {k: round(t / n, 4) for k, (n, t) in sorted(calls.items())},
+                         "algorithmic_bytes_per_step": int(info["bytes"]), "algorithmic_GBps": round(gbs, 1),
+                         "hbm_frac": round(gbs / peak, 4), "launch_mode": "eager", "near_plane": "exact"}
+        except Exception as e:  # noqa: BLE001 -- one failing config must not lose the headline line
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            step = None
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+    trb.set_fragment_cache(False)
+    trb.set_near_plane_clipping("off")
+    return out
+
+
+def run_c5_spec(dev, world, rank, args, peak, barrier):
+    """BASELINE configs[4] as written: the 1M-face sphere x 1024 views at 1024^2, K=8, blur, SoftPhong, loss =
+    mean(image^2), gradient to the vertices.  STRONG scaling: the 1024 views are sharded contiguously over the
+    ranks (`parallel.shard_views`), each rank renders its slice in memory-bounded chunks (`parallel.chunk_views`),
+    and the 6 MB vertex gradient is summed once per pass (`allreduce_shared_grads`: above 256 KB that is the fused
+    NCCL all-reduce).  One warm-up pass, then `--c5-passes` timed passes (CUDA events, max over ranks)."""
+    import torch.distributed as dist
+    import torch_renderer_b200 as trb
+    import bench_workloads as wl
+    from torch_renderer_b200.parallel import allreduce_shared_grads, chunk_views, shard_views
+    views = args.c5_views
+    Hc = Wc = 1024
+    Kc = 8
+    trb.set_fragment_cache(False)
+    trb.set_near_plane_clipping("exact")
+    v, f = wl.grid_sphere(501, 1000)
+    verts = v.to(dev).requires_grad_(True)
+    faces = f.to(dev)
+    cols = torch.rand(1, v.shape[0], 3, generator=torch.Generator().manual_seed(0)).to(dev)
+    Rall, Tall = trb.look_at_view_transform(eye=wl.fibonacci_eyes(views))
+    lo, hi = shard_views(views, rank, world)
+    R, T = Rall[lo:hi].to(dev), Tall[lo:hi].to(dev)
+    chunk = args.c5_chunk
+    cams = trb.FoVPerspectiveCameras(device=dev)
+    rend = trb.MeshRenderer(
+        trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=Hc, blur_radius=wl.BLUR, faces_per_pixel=Kc)),
+        trb.SoftPhongShader(device=dev, cameras=cams, lights=trb.PointLights(device=dev, location=[[0, 0, -3.0]])))
+    loss_acc = torch.zeros((), device=dev)
+
+    def one_pass():
+        verts.grad = None
+        loss_acc.zero_()
+        for s0, s1 in chunk_views(hi - lo, chunk):
+            m = trb.Meshes([verts], [faces], textures=trb.TexturesVertex(cols)).extend(s1 - s0)
+            img = rend(m, R=R[s0:s1], T=T[s0:s1])
+            loss = (img ** 2).sum() / (views * Hc * Wc * 4)
+            loss.backward()
+            loss_acc.add_(loss.detach())
+        allreduce_shared_grads([verts.grad])
+
+    torch.cuda.reset_peak_memory_stats(dev)
+    one_pass()          # warm-up (also grows the (tile, face) pair capacity)
+    times = []
+    for _ in range(args.c5_passes):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_pass()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times.append(ms)
+    sec = statistics.median(times) / 1e3
+    loss_total = loss_acc.clone()
+    if world > 1:
+        dist.all_reduce(loss_total)
+    bytes_view = wl.bview(Kc, Hc, Wc, v.shape[0], f.shape[0])
+    gbs_per_gpu = views / world * bytes_view / sec / 1e9
+    trb.set_near_plane_clipping("off")
+    out = {"workload": f"{f.shape[0]}-face sphere (V={v.shape[0]}) x {views} views at {Hc}x{Wc}, K={Kc}, blur {wl.BLUR:.3e}, "
+                       "SoftPhong+PointLights, fwd+bwd to verts (BASELINE configs[4])",
+           "scaling": "strong", "n_gpus": world, "views_total": views, "views_per_gpu": hi - lo, "chunk_views": chunk,
+           "views_per_s": round(views / sec, 2), "views_per_s_per_gpu": round(views / sec / world, 2),
+           "seconds_per_pass": round(sec, 4), "passes_ms": [round(t, 1) for t in times],
+           "algorithmic_bytes_per_view": int(bytes_view), "algorithmic_GBps_per_gpu": round(gbs_per_gpu, 1),
+           "hbm_frac": round(gbs_per_gpu / peak, 4),
+           "collective": "none" if world == 1 else "fused NCCL all-reduce of the 6 MB vertex gradient, once per pass",
+           "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
+           "loss": float(loss_total), "grad_norm": float(verts.grad.norm()), "launch_mode": "eager", "near_plane": "exact"}
+    del rend, verts, faces, cols
+    torch.cuda.empty_cache()
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
@@ -469,6 +673,12 @@ def main():
     ap.add_argument("--cpu-views", type=int, default=8, help="views in the cpu_baseline sample (~1.5 s each)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--repeats", type=int, default=5, help="timed repeats of --steps steps; the median is reported")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other_configs block (C1, C3, C4, pose step, C5 chunk)")
+    ap.add_argument("--no-c5", action="store_true", help="skip BASELINE configs[4] at spec (1M faces x 1024 views)")
+    ap.add_argument("--c5-views", type=int, default=1024)
+    ap.add_argument("--c5-chunk", type=int, default=32, help="views per chunk of a rank's C5 slice (bounds Fragments memory)")
+    ap.add_argument("--c5-passes", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -232,3 +232,65 @@ def test_dense_tile_lists_ordered_in_super_chunks(nlat, nlon, size, K):
     want = oracle_rasterize(ndc, f, (size, size), BLUR, K, True, True)
     _check_fragments(frag, want)
     assert (want[0][..., K - 1] >= 0).sum() > 500
+
+
+def test_c2_headline_workload_exact_at_its_own_size():
+    """The bench.py workload itself: the UN-normalised cow (+-0.1 units) from the dist-0.7 orbit
+    of 64 cameras at 512^2, K=1 -- ~3.5 px per face, >90 % empty tiles, the strip-fill fast path.  The whole 64-view
+    batch goes through the fused renderer as in the bench; views 5 and 37 of it are checked against the oracle:
+    pix_to_face bit-exact, zbuf / bary / dists 1e-5, image 1e-4, gradients 1e-3 vs fp64 autograd."""
+    trb = _trb()
+    v, f = load_mesh("cow")
+    torch.manual_seed(0)
+    colors = torch.rand(v.shape[0], 3)
+    N, H, W = 64, 512, 512
+    R, T = trb.look_at_view_transform(dist=0.7, elev=torch.linspace(0, 360, N), azim=torch.linspace(-180, 180, N))
+    pick = [5, 37]
+    vd, cd = v.to(DEV).requires_grad_(True), colors.to(DEV).requires_grad_(True)
+    Rd, Td = R.to(DEV).requires_grad_(True), T.to(DEV).requires_grad_(True)
+    meshes = trb.Meshes(verts=[vd], faces=[f.to(DEV)], textures=trb.TexturesVertex(cd[None])).extend(N)
+    cams = trb.FoVPerspectiveCameras(device=DEV)
+    rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=H, blur_radius=0.0, faces_per_pixel=1))
+    shader = trb.SoftPhongShader(device=DEV, cameras=cams, lights=trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]]))
+    images, frag = trb.MeshRendererWithFragments(rast, shader)(meshes, R=Rd, T=Td)
+    # loss over the two checked views only, so that the fp64 model needs only them
+    gsel = torch.zeros(N, 1, 1, 1, device=DEV)
+    gsel[pick] = 1.0
+    ((images ** 2) * gsel).mean().backward()
+    ndc = rast.transform(meshes, R=Rd, T=Td).detach().cpu().reshape(N, -1, 3)[pick]
+    want = oracle_rasterize(ndc, f, (H, W), 0.0, 1, True, False)
+    F = f.shape[0]
+    got_p2f = frag.pix_to_face[pick].cpu().numpy()
+    base = np.array(pick, dtype=np.int64).reshape(2, 1, 1, 1) * F
+    want_p2f = np.where(want[0] >= 0, want[0] - (np.arange(2).reshape(2, 1, 1, 1) * F) + base, -1)
+    mism = int((got_p2f != want_p2f).sum())
+    assert mism == 0, f"pix_to_face differs at {mism} samples"
+    cover = (want[0] >= 0).mean()
+    assert 0.005 < cover < 0.2, cover          # the headline regime: a few percent of the image is covered
+    for name, a, b in (("zbuf", frag.zbuf, want[1]), ("bary", frag.bary_coords, want[2]), ("dists", frag.dists, want[3])):
+        a = a[pick].detach().cpu().numpy()
+        assert np.allclose(a, b, atol=1e-5, rtol=1e-5), f"{name} max abs diff {np.abs(a - b).max()}"
+    # fp64 model of the two views
+    n = len(pick)
+    v64, c64 = v.double().requires_grad_(True), colors.double().requires_grad_(True)
+    R64, T64 = R[pick].double().requires_grad_(True), T[pick].double().requires_grad_(True)
+    proj = fov_proj(n).double()
+    ndc64 = sref.world_to_ndc(v64, R64, T64, proj[:, 0], proj[:, 1], proj[:, 2], proj[:, 3], True)
+    p2f = torch.from_numpy(want[0])
+    z64, b64, d64 = sref.raster_recompute(ndc64[:, f].reshape(-1, 3, 3), p2f, True, False)
+    ones = lambda *x: torch.tensor([list(x)], dtype=torch.float64).repeat(n, 1)
+    cam = -torch.matmul(T64[:, None, :], torch.linalg.inv(R64))[:, 0, :]
+    ref = sref.shade(p2f, b64, z64, d64, f.repeat(n, 1), v64, sref.vertex_normals(v64, f), c64, shader="soft_phong",
+                     light_kind="point", light_vec=ones(0, 0, -3.0), light_ambient=ones(.5, .5, .5),
+                     light_diffuse=ones(.3, .3, .3), light_specular=ones(.2, .2, .2), mat_ambient=ones(1, 1, 1),
+                     mat_diffuse=ones(1, 1, 1), mat_specular=ones(1, 1, 1),
+                     shininess=torch.full((n,), 64.0, dtype=torch.float64), camera_center=cam)
+    err = (images[pick].detach().cpu().double() - ref).abs().max().item()
+    assert err < 1e-4, f"image error {err}"
+    ((ref ** 2).sum() / (N * H * W * 4)).backward()
+    assert rel_l2(vd.grad.cpu(), v64.grad) < 1e-3
+    assert rel_l2(cd.grad.cpu(), c64.grad) < 1e-3
+    assert rel_l2(Rd.grad[pick].cpu(), R64.grad) < 1e-3
+    assert rel_l2(Td.grad[pick].cpu(), T64.grad) < 1e-3
+    others = [i for i in range(N) if i not in pick]
+    assert float(Rd.grad[others].abs().max()) == 0.0 and float(Td.grad[others].abs().max()) == 0.0

@@ -251,7 +251,12 @@ typedef struct trb_render_config {
   int64_t pair_capacity;
   int32_t scratch_is_zeroed;     /* backward: the caller already zeroed `scratch` (e.g. it lives in the same
                                     zero-filled allocation as the gradient outputs): skip the memset */
-  int32_t reserved;
+  int32_t sparse_fragments;      /* forward: 1 = the caller will not look at the Fragments (MeshRenderer returns the
+                                    image only; upstream's `renderer(meshes)` never exposes them): pix_to_face / zbuf /
+                                    bary / dists are written ONLY for covered pixels -- layers [0, count) plus one -1
+                                    terminator layer when count < K -- which is all the fused backward reads (it walks
+                                    the covered-pixel list).  Background samples are left unwritten.  0 = PyTorch3D's
+                                    dense layout with -1 fill (MeshRasterizer, MeshRendererWithFragments). */
 } trb_render_config;
 
 /* workspace_bytes: scratch for the forward; hit_pixels_len: length of hit_pixels (int32: a count

@@ -1,6 +1,8 @@
 """cProfile of the host side of one config step (profiles/configs.py): python profiles/host_profile.py pose_step"""
 import cProfile, pstats, sys, time
 import torch
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import configs
 name = sys.argv[1]
 dev = torch.device("cuda:0")

@@ -2,6 +2,8 @@
 torch_renderer_b200.build --force).  python profiles/kn_stats.py C5"""
 import ctypes, json, sys
 import torch
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import configs
 from torch_renderer_b200 import _lib
 name = sys.argv[1]
@@ -17,4 +19,9 @@ names = ["busy_tiles", "list_entries", "faces_staged", "walk_iters", "pass_zlo",
          "full_evals", "pass_depth", "insertions", "shift_steps", "early_stops", "pixels_not_full"]
 out = {n: int(buf[i]) for i, n in enumerate(names)}
 out["views"] = info["views"]
+if hasattr(L, "trb_debug_bw_stats"):
+    bw = (ctypes.c_ulonglong * 8)()
+    L.trb_debug_bw_stats(bw)
+    out["backward_scatter"] = {"warp_layer_rounds": int(bw[0]), "lanes_with_sample": int(bw[1]),
+                               "distinct_faces": int(bw[2]), "shuffle_aggregated_rounds": int(bw[3])}
 print(json.dumps(out, indent=1))

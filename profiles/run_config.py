@@ -3,6 +3,8 @@ C-ABI-call event times and the two fused kernels' own durations.  Also the ncu t
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file L.csv python profiles/run_config.py C5 2"""
 import json, sys, time
 import torch
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import configs
 from torch_renderer_b200 import _lib, ops
 

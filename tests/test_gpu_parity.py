@@ -797,3 +797,48 @@ def test_forward_is_bit_reproducible_under_repetition(K, blur):
         assert torch.equal(fr.pix_to_face, fr0.pix_to_face) and torch.equal(fr.zbuf, fr0.zbuf)
         assert torch.equal(fr.bary_coords, fr0.bary_coords) and torch.equal(fr.dists, fr0.dists)
         assert torch.allclose(img, img0, atol=1e-5, rtol=0)  # vertex normals are accumulated with fp32 atomics: order noise ~2e-6
+
+
+@pytest.mark.parametrize("shader_kind,K,blur,size", [
+    ("soft_phong", 1, 0.0, (64, 64)), ("soft_phong", 1, 0.0, (45, 61)), ("hard_phong", 1, 0.0, (96, 96)),
+    ("soft_silhouette", 1, 0.0, (64, 64)), ("soft_phong", 8, 9.21024e-4, (128, 128)), ("soft_phong", 5, 2e-3, (45, 61)),
+    ("soft_silhouette", 50, 9.21024e-4, (96, 96)), ("soft_silhouette", 30, 2e-3, (33, 47)), ("hard_phong", 4, 0.0, (64, 64)),
+])
+def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, size):
+    """``MeshRenderer`` returns the image only, so its kernels write Fragments for covered pixels only
+    (trb_render_config.sparse_fragments); ``MeshRendererWithFragments`` writes PyTorch3D's dense layout.  Same
+    image bit for bit, same gradients (the scatter order of the atomics is the only difference)."""
+    trb = _trb()
+    torch.manual_seed(1)
+    v, f = _scene("teapot")
+    colors = torch.rand(v.shape[0], 3)
+    N = 3
+    R0, T0 = _views(N, seed=5)
+    out = {}
+    for dense in (True, False):
+        vd, cd = v.to(DEV).requires_grad_(True), colors.to(DEV).requires_grad_(True)
+        R, T = R0.to(DEV).requires_grad_(True), T0.to(DEV).requires_grad_(True)
+        cams = trb.FoVPerspectiveCameras(device=DEV)
+        mesh = trb.Meshes(verts=[vd], faces=[f.to(DEV)], textures=trb.TexturesVertex(cd[None])).extend(N)
+        rast = trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=size, blur_radius=blur, faces_per_pixel=K))
+        if shader_kind == "soft_silhouette":
+            shader = trb.SoftSilhouetteShader(trb.BlendParams(1e-4, 1e-4, (0, 0, 0)))
+        else:
+            cls = trb.SoftPhongShader if shader_kind == "soft_phong" else trb.HardPhongShader
+            shader = cls(device=DEV, cameras=cams, lights=trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]]))
+        # a poisoned allocator would show any read of an unwritten background sample as NaN / garbage
+        if dense:
+            img, frag = trb.MeshRendererWithFragments(rast, shader)(mesh, R=R, T=T)
+            assert (frag.pix_to_face >= -1).all()
+        else:
+            junk = torch.full((N * size[0] * size[1] * K * 8,), float("nan"), device=DEV)
+            del junk
+            img = trb.MeshRenderer(rast, shader)(mesh, R=R, T=T)
+        torch.manual_seed(2)
+        w = torch.rand(img.shape, device=DEV)
+        (img * w).sum().backward()
+        out[dense] = (img.detach().clone(), vd.grad.clone(), R.grad.clone(), T.grad.clone(),
+                      cd.grad.clone() if cd.grad is not None else torch.zeros(1, device=DEV))
+    assert torch.equal(out[True][0], out[False][0])
+    for a, b in zip(out[True][1:], out[False][1:]):
+        assert rel_l2(a, b) < 1e-5

@@ -40,7 +40,7 @@ class RenderConfig(ctypes.Structure):
                 ("want_light_grad", _c.c_int32), ("z_clip_value", _f),
                 ("num_world_verts", _c.c_int64), ("num_faces", _c.c_int64),
                 ("num_ndc_verts", _c.c_int64), ("pair_capacity", _c.c_int64),
-                ("scratch_is_zeroed", _c.c_int32), ("reserved", _c.c_int32)]
+                ("scratch_is_zeroed", _c.c_int32), ("sparse_fragments", _c.c_int32)]
 
 
 class UvTexture(ctypes.Structure):

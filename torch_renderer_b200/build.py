@@ -14,8 +14,11 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
-_OBJ = os.path.join(_PKG, "build")
-LIB_PATH = os.path.join(_PKG, "libtrb.so")
+# TRB_BUILD_TAG=<tag> builds a variant beside the product library (libtrb_<tag>.so, objects in build_<tag>/):
+# diagnostic builds (-DTRB_KN_STATS) and same-box A/B of kernel variants, selected at run time with TRB_LIB_PATH
+_TAG = os.environ.get("TRB_BUILD_TAG", "")
+_OBJ = os.path.join(_PKG, "build" + (f"_{_TAG}" if _TAG else ""))
+LIB_PATH = os.path.join(_PKG, f"libtrb_{_TAG}.so" if _TAG else "libtrb.so")
 
 SOURCES = ["api.cu", "raster.cu", "shade.cu", "transform.cu", "render.cu", "render_kn.cu", "render_stages.cu", "allreduce.cu", "points.cu", "clip.cu", "points_render.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -49,12 +49,14 @@ __device__ __forceinline__ void fill_empty_tile(const FineArgs& a, int n, int tb
   const int xi = tbx * 16 + (tid & 15), yi = tby * 16 + (tid >> 4);
   if (xi >= a.W || yi >= a.H) return;
   const size_t pix = ((size_t)n * a.H + yi) * a.W + xi;
-  st_cs(a.p2f + pix, -1ll);
-  st_cs(a.zbuf + pix, -1.0f);
-  st_cs(a.dists + pix, -1.0f);
-  st_cs(a.bary + pix * 3 + 0, -1.0f);
-  st_cs(a.bary + pix * 3 + 1, -1.0f);
-  st_cs(a.bary + pix * 3 + 2, -1.0f);
+  if (!a.sparse) {
+    st_cs(a.p2f + pix, -1ll);
+    st_cs(a.zbuf + pix, -1.0f);
+    st_cs(a.dists + pix, -1.0f);
+    st_cs(a.bary + pix * 3 + 0, -1.0f);
+    st_cs(a.bary + pix * 3 + 1, -1.0f);
+    st_cs(a.bary + pix * 3 + 2, -1.0f);
+  }
   if (SHADER == TRB_SHADER_NONE) return;
   const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
                                                             : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
@@ -70,18 +72,20 @@ __device__ __forceinline__ void fill_empty_tile_v4(const FineArgs& a, int n, int
   const size_t pix0 = ((size_t)n * a.H + tby * 16) * a.W + tbx * 16;  // top-left pixel of the tile
   const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
   const size_t W = a.W;
-  if (tid < 64) {          // zbuf: 16 rows x 4
-    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (tid >> 2) * W) + (tid & 3), m4);
-  } else if (tid < 128) {  // dists
-    const int i = tid - 64;
-    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i >> 2) * W) + (i & 3), m4);
-  } else {                 // pix_to_face: 16 rows x 8 (two int64 per store)
-    const int i = tid - 128;
-    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i >> 3) * W) + (i & 7), make_longlong2(-1ll, -1ll));
-  }
-  if (tid < 192) {         // barycentrics: 16 rows x 12
-    const int r = tid / 12, c = tid - r * 12;
-    st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+  if (!a.sparse) {
+    if (tid < 64) {          // zbuf: 16 rows x 4
+      st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (tid >> 2) * W) + (tid & 3), m4);
+    } else if (tid < 128) {  // dists
+      const int i = tid - 64;
+      st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i >> 2) * W) + (i & 3), m4);
+    } else {                 // pix_to_face: 16 rows x 8 (two int64 per store)
+      const int i = tid - 128;
+      __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i >> 3) * W) + (i & 7), make_longlong2(-1ll, -1ll));
+    }
+    if (tid < 192) {         // barycentrics: 16 rows x 12
+      const int r = tid / 12, c = tid - r * 12;
+      st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+    }
   }
   if (SHADER == TRB_SHADER_NONE) return;
   const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
@@ -99,22 +103,24 @@ __device__ __forceinline__ void fill_empty_strip_v4(const FineArgs& a, int n, in
   const float4 m4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
   constexpr int ZW = kStrip * 4, PW = kStrip * 8, BW = kStrip * 12, IW = kStrip * 16;  // 16-byte words per row
   static_assert(kStrip % 4 == 0, "the strip fill deals whole rounds of 256 stores");
+  if (!a.sparse) {
 #pragma unroll
-  for (int j = 0; j < kStrip / 4; ++j) {       // zbuf, dists: 16 rows x ZW
-    const int i = tid + 256 * j;
-    st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (i / ZW) * W) + (i % ZW), m4);
-    st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i / ZW) * W) + (i % ZW), m4);
-  }
+    for (int j = 0; j < kStrip / 4; ++j) {       // zbuf, dists: 16 rows x ZW
+      const int i = tid + 256 * j;
+      st_cs(reinterpret_cast<float4*>(a.zbuf + pix0 + (i / ZW) * W) + (i % ZW), m4);
+      st_cs(reinterpret_cast<float4*>(a.dists + pix0 + (i / ZW) * W) + (i % ZW), m4);
+    }
 #pragma unroll
-  for (int j = 0; j < kStrip / 2; ++j) {       // pix_to_face: 16 rows x PW
-    const int i = tid + 256 * j;
-    __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i / PW) * W) + (i % PW), make_longlong2(-1ll, -1ll));
-  }
+    for (int j = 0; j < kStrip / 2; ++j) {       // pix_to_face: 16 rows x PW
+      const int i = tid + 256 * j;
+      __stcs(reinterpret_cast<longlong2*>(a.p2f + pix0 + (i / PW) * W) + (i % PW), make_longlong2(-1ll, -1ll));
+    }
 #pragma unroll
-  for (int j = 0; j < kStrip * 3 / 4; ++j) {   // barycentrics: 16 rows x BW
-    const int i = tid + 256 * j;
-    const int r = i / BW, c = i - r * BW;
-    st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+    for (int j = 0; j < kStrip * 3 / 4; ++j) {   // barycentrics: 16 rows x BW
+      const int i = tid + 256 * j;
+      const int r = i / BW, c = i - r * BW;
+      st_cs(reinterpret_cast<float4*>(a.bary + 3 * (pix0 + r * W)) + c, m4);
+    }
   }
   if (SHADER == TRB_SHADER_NONE) return;
   const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
@@ -372,12 +378,14 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     // list of covered pixels for the backward (row-major inside the tile: neighbouring entries, neighbouring pixels)
     if (a.hit_pixels != nullptr) a.hit_pixels[1 + s_hbase + r] = (int)pix;
   } else if (live) {
-    st_cs(a.p2f + pix, -1ll);
-    st_cs(a.zbuf + pix, -1.0f);
-    st_cs(a.dists + pix, -1.0f);
-    st_cs(a.bary + pix * 3 + 0, -1.0f);
-    st_cs(a.bary + pix * 3 + 1, -1.0f);
-    st_cs(a.bary + pix * 3 + 2, -1.0f);
+    if (!a.sparse) {
+      st_cs(a.p2f + pix, -1ll);
+      st_cs(a.zbuf + pix, -1.0f);
+      st_cs(a.dists + pix, -1.0f);
+      st_cs(a.bary + pix * 3 + 0, -1.0f);
+      st_cs(a.bary + pix * 3 + 1, -1.0f);
+      st_cs(a.bary + pix * 3 + 2, -1.0f);
+    }
     if (SHADER != TRB_SHADER_NONE) {
       const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
                                                                 : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
@@ -446,6 +454,12 @@ template <int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
 template <bool K1, int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
+
+// Diagnostic counters of the K > 1 backward scatter (TRB_KN_STATS builds only; trb_debug_bw_stats):
+// [0] warp x layer rounds of the rasteriser-backward scatter, [1] lanes with a sample, [2] distinct faces
+#ifdef TRB_KN_STATS
+__device__ unsigned long long g_bw_stats[8];
+#endif
 
 #ifndef TRB_BWD_CTAS
 #define TRB_BWD_CTAS 4
@@ -857,6 +871,15 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
     {
       // K > 1 with Phong shading is bound by instruction issue, not by the reductions: no run merging there
       const WarpGroups wg = warp_groups(key, !PHONG);
+#ifdef TRB_KN_STATS
+      const unsigned bw_have = __ballot_sync(__activemask(), key >= 0);
+      if ((tid & 31) == 0 && wg.any) {
+        atomicAdd(&g_bw_stats[0], 1ull);
+        atomicAdd(&g_bw_stats[1], (unsigned long long)__popc(bw_have));
+        atomicAdd(&g_bw_stats[2], (unsigned long long)__popc(wg.leaders));
+        atomicAdd(&g_bw_stats[3], wg.aggregate ? 1ull : 0ull);
+      }
+#endif
       warp_groups_add_xyz3(wg, key, gv, a.g_verts_ndc, i0, i1, i2);
     }
   }
@@ -1007,6 +1030,8 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.bg2 = sc.background[2];
   a.uv = {nullptr, nullptr, nullptr, 0, 0};
   if (use_uv) a.uv = {uv->map, uv->verts_uvs, uv->faces_uvs, uv->map_h, uv->map_w};
+  // sparse Fragments need the covered-pixel list (it is what tells the backward which samples exist)
+  a.sparse = (cfg->sparse_fragments && sc.shader != TRB_SHADER_NONE) ? 1 : 0;
   if (g_dbg_events[0]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[0], st));
   rc = launch_render_fine(sc.shader, sc.light_kind, N, st, a);
   if (rc != TRB_OK) return rc;
@@ -1094,3 +1119,13 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   if (rc != TRB_OK) return rc;
   return TRB_OK;
 }
+
+#ifdef TRB_KN_STATS
+// Copies the backward scatter counters to `host_out[8]` and clears them (diagnostic builds only; synchronises).
+extern "C" int trb_debug_bw_stats(unsigned long long* host_out) {
+  unsigned long long zero[8] = {0};
+  if (cudaMemcpyFromSymbol(host_out, trb::g_bw_stats, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  if (cudaMemcpyToSymbol(trb::g_bw_stats, zero, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  return TRB_OK;
+}
+#endif

@@ -16,6 +16,7 @@ struct FineArgs {
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   float sigma, gamma, bg0, bg1, bg2;
   UvTex uv;  // uv.map != nullptr: TexturesUV instead of per-vertex colours
+  int sparse;  // trb_render_config::sparse_fragments: Fragments only for covered pixels (+ a -1 terminator layer)
 };
 
 // Appends the linear indices of the pixels of this CTA that got at least one face to the global

@@ -527,6 +527,8 @@ class _RenderFn(torch.autograd.Function):
         # light / explicit camera-centre gradients are only reduced when the parameter block wants them
         cfg.want_light_grad = int(view_params is not None and view_params.requires_grad)
         cfg.z_clip_value = float(spec.get("z_clip", 0.0) or 0.0)
+        # the caller returns the image only: Fragments are written for covered pixels only (include/trb.h)
+        cfg.sparse_fragments = int(bool(spec.get("sparse", False)) and shader != _lib.SHADER_NONE)
         cfg.num_world_verts, cfg.num_faces = verts.shape[0], (0 if faces is None else faces.shape[0])
         cfg.num_ndc_verts = table.total_ndc_verts
         cfg.pair_capacity = table.poll_capacity()

@@ -270,8 +270,11 @@ class MeshRenderer(nn.Module):
         self.shader.to(device)
         return self
 
-    def _render_fused(self, meshes_world: Meshes, kwargs):
-        """Returns (images, Fragments) through the fused pipeline, or None when it does not apply."""
+    def _render_fused(self, meshes_world: Meshes, kwargs, want_fragments: bool = True):
+        """Returns (images, Fragments) through the fused pipeline, or None when it does not apply.  With
+        ``want_fragments=False`` (``MeshRenderer``: upstream's ``renderer(meshes)`` returns the image and nothing
+        else) the kernels write the Fragments of COVERED pixels only -- what the fused backward reads -- instead
+        of 28*K bytes for every pixel of the image, and the second element is None."""
         from .rasterizer import MeshRasterizer
         rast, shader = self.rasterizer, self.shader
         if type(rast) is not MeshRasterizer:
@@ -345,8 +348,10 @@ class MeshRenderer(nn.Module):
         token = {"consumed": False}
         if uv is not None:
             spec["uv"] = uv
+        # dense Fragments when somebody will look at them: the caller, or the (opt-in) Fragments cache
+        sparse = not want_fragments and not _fragment_cache.enabled
         spec.update(_token=token, shader=kind, light_kind=light_kind, sigma=float(blend_params.sigma),
-                    gamma=float(blend_params.gamma), background=bg, camera_center_from_rt=from_rt)
+                    gamma=float(blend_params.gamma), background=bg, camera_center_from_rt=from_rt, sparse=sparse)
         images, p2f, zbuf, bary, dists = ops.render(
             meshes_world._unique_verts(), colors, R, T, proj, vp, meshes_world.faces_packed_i32(), table, spec,
             tex_map=tex_map)
@@ -354,12 +359,14 @@ class MeshRenderer(nn.Module):
             clipped = rast._clipped_fragments(meshes_world, R, T, proj, spec)
             if clipped is not None:
                 return shader(clipped, meshes_world, **kwargs), clipped
+        if sparse:
+            return images, None
         fragments = Fragments(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
         _fragment_cache.store(key, tensors, fragments, token)
         return images, fragments
 
     def forward(self, meshes_world: Meshes, **kwargs) -> torch.Tensor:
-        fused = self._render_fused(meshes_world, kwargs)
+        fused = self._render_fused(meshes_world, kwargs, want_fragments=False)
         if fused is not None:
             return fused[0]
         fragments = self.rasterizer(meshes_world, **kwargs)

@@ -487,7 +487,32 @@ def measure_other_configs(dev, args, peak):
             _lib.lib().trb_debug_set_events(None, None, None, None)
             calls = ops.stop_event_log()
             gbs = info["bytes"] / ms / 1e6
-            out[name] = {"what": info["what"], "views_per_s": round(info["views"] / ms * 1e3, 2),
+            # the same step replayed from ONE CUDA graph (trb.capture_step: the near-plane flag is checked
+            # asynchronously between replays instead of being waited for)
+            graph = None
+            if name != "C5" and not args.no_graph:
+                try:
+                    cap = trb.capture_step(step)
+                    for _ in range(3):
+                        cap()
+                    greps = []
+                    for _ in range(args.repeats):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(steps):
+                            cap()
+                        e1.record()
+                        torch.cuda.synchronize()
+                        greps.append(e0.elapsed_time(e1) / steps)
+                    cap.check()
+                    gms = statistics.median(greps)
+                    graph = {"ms_per_step": round(gms, 4), "views_per_s": round(info["views"] / gms * 1e3, 2),
+                             "hbm_frac": round(info["bytes"] / gms / 1e6 / peak, 4),
+                             "launch_mode": "cuda-graph (trb.capture_step), near-plane flag checked asynchronously"}
+                    del cap
+                except Exception as e:  # noqa: BLE001
+                    graph = {"error": f"{type(e).__name__}: {e}"[:300]}
+            out[name] = {"what": info["what"], "views_per_s": round(info["views"] / ms * 1e3, 2), "captured": graph,
                          "ms_per_step": round(ms, 4), "ms_per_step_repeats": [round(r, 4) for r in reps],
                          "host_issue_ms_per_step": round(statistics.median(host), 4), "steps": steps,
                          "fine_kernel_ms": round(statistics.median(fine), 4),

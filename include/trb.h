@@ -356,6 +356,10 @@ int trb_allreduce_grid(int64_t capacity_floats);
 int trb_allreduce_sum_f32(float* const* host_segments, const int64_t* host_counts, int num_segments,
                           void* const* host_peer_inbox, int64_t capacity_floats, int rank, int world,
                           uint32_t* epochs, int32_t* error_flag, int device, trb_stream_t stream);
+/* Diagnostics: `device_u64x3` (device memory, zeroed by the caller) accumulates, for every later
+ * trb_allreduce_sum_f32 launch of this process, block 0's push time and wait-and-sum time in %globaltimer
+ * nanoseconds and the call count; NULL switches it off. */
+int trb_allreduce_set_timing(uint64_t* device_u64x3);
 
 /* Measurement hook (bench.py's roofline leg): when non-NULL, the four cudaEvent_t handles are
  * recorded on the call's stream immediately before / after the dominant kernel of

@@ -232,3 +232,60 @@ def test_light_and_material_colour_gradients(kind, K, blur, shader_name):
             assert a is None or float(a.abs().max()) == 0.0
             continue
         assert rel_l2(a, b) < 1e-3, (name, a, b)
+
+
+def test_capture_step_replays_equal_eager_and_flag_the_near_plane():
+    """``trb.capture_step``: a camera_pose_optimizer-style step (quaternion pose -> silhouette + Phong renders ->
+    loss.backward()) replayed from ONE CUDA graph gives the eager step's loss and gradient; moving the camera INTO
+    the mesh between replays trips the asynchronous near-plane flag (``NearPlaneCrossed``)."""
+    import torch_renderer_b200 as trb
+    from helpers import load_mesh, normalize_mesh
+    dev = torch.device("cuda:0")
+    v, f = load_mesh("teapot")
+    v = normalize_mesh(v)
+    torch.manual_seed(0)
+    mesh = trb.Meshes([v.to(dev)], [f.to(dev)], textures=trb.TexturesVertex(torch.rand(1, v.shape[0], 3, device=dev)))
+    cams = trb.FoVPerspectiveCameras(device=dev)
+    settings = trb.RasterizationSettings(image_size=96, blur_radius=9.21024e-4, faces_per_pixel=10)
+    sil = trb.MeshRenderer(trb.MeshRasterizer(cams, settings), trb.SoftSilhouetteShader(trb.BlendParams(1e-4, 1e-4, (0, 0, 0))))
+    phong = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=96)),
+                             trb.SoftPhongShader(device=dev, cameras=cams, lights=trb.PointLights(device=dev, location=[[0.0, 0.0, -3.0]])))
+    R, T = trb.look_at_view_transform(2.7, 20, 40)
+    pose = torch.cat([T, trb.transforms.matrix_to_quaternion(R)], -1).to(dev).requires_grad_(True)
+    target = torch.rand(1, 96, 96, device=dev)
+    loss_out = torch.zeros((), device=dev)
+
+    def step():
+        pose.grad = None
+        Rm = trb.transforms.quaternion_to_matrix(pose[:, 3:])
+        Tm = pose[:, :3]
+        loss = (sil(mesh, R=Rm, T=Tm)[..., 3] - target).abs().mean() + (phong(mesh, R=Rm, T=Tm)[..., :3] ** 2).mean()
+        loss.backward()
+        loss_out.copy_(loss.detach())
+        return loss_out
+
+    step()
+    want_loss, want_grad = float(loss_out), pose.grad.clone()
+    cap = trb.capture_step(step)
+    for _ in range(3):
+        got = cap()
+    cap.check()
+    assert abs(float(got) - want_loss) < 1e-6
+    assert (pose.grad - want_grad).abs().max() < 1e-5 * want_grad.abs().max()
+    # inputs are updated in place between replays: a different pose gives the eager result for that pose
+    with torch.no_grad():
+        pose[:, 2] += 0.3
+    cap()
+    cap.check()
+    g_replay, l_replay = pose.grad.clone(), float(loss_out)
+    step()
+    assert abs(float(loss_out) - l_replay) < 1e-6
+    assert (pose.grad - g_replay).abs().max() < 1e-5 * g_replay.abs().max()
+    # camera moved into the mesh: vertices behind z_clip = znear / 2 -> the flag trips, check() raises
+    with torch.no_grad():
+        pose[:, :3] = torch.tensor([[0.0, 0.0, 0.2]], device=dev)
+    cap()
+    with pytest.raises(trb.NearPlaneCrossed):
+        cap.check()
+    with pytest.raises(trb.NearPlaneCrossed):
+        cap()

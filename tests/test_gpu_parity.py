@@ -807,7 +807,9 @@ def test_forward_is_bit_reproducible_under_repetition(K, blur):
 def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, size):
     """``MeshRenderer`` returns the image only, so its kernels write Fragments for covered pixels only
     (trb_render_config.sparse_fragments); ``MeshRendererWithFragments`` writes PyTorch3D's dense layout.  Same
-    image bit for bit, same gradients (the scatter order of the atomics is the only difference)."""
+    image (bit for bit where no atomically accumulated vertex normal enters), same gradients (the scatter order of
+    the atomics is the only difference).  The allocator is poisoned with NaNs before the sparse render, so a read of
+    an unwritten background sample would show."""
     trb = _trb()
     torch.manual_seed(1)
     v, f = _scene("teapot")
@@ -839,6 +841,11 @@ def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, 
         (img * w).sum().backward()
         out[dense] = (img.detach().clone(), vd.grad.clone(), R.grad.clone(), T.grad.clone(),
                       cd.grad.clone() if cd.grad is not None else torch.zeros(1, device=DEV))
-    assert torch.equal(out[True][0], out[False][0])
+    if shader_kind == "soft_silhouette":
+        assert torch.equal(out[True][0], out[False][0])
+    else:
+        # vertex normals are accumulated with atomics (order of the float sums differs from run to run): ulps
+        assert torch.equal(out[True][0][..., 3], out[False][0][..., 3])
+        assert (out[True][0] - out[False][0]).abs().max() < 2e-6
     for a, b in zip(out[True][1:], out[False][1:]):
         assert rel_l2(a, b) < 1e-5

@@ -8,6 +8,7 @@ from .structures import Meshes, Pointclouds, join_meshes_as_batch, join_pointclo
 from .io import load_obj, load_objs_as_meshes, save_obj  # noqa: F401
 from .utils import ico_sphere  # noqa: F401
 from .ops import interpolate_face_attributes  # noqa: F401
+from .capture import CapturedStep, NearPlaneCrossed, capture_step  # noqa: F401
 
 __version__ = "0.1.0"
 from .loss import (  # noqa: F401

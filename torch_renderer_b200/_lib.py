@@ -78,6 +78,7 @@ _SIGNATURES = {
     "trb_nn_forward": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "trb_nn_backward": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "trb_allreduce_grid": [_i64],
+    "trb_allreduce_set_timing": [_vp],
     "trb_allreduce_sum_f32": [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _vp],
 }
 

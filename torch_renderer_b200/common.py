@@ -58,11 +58,14 @@ def named_tensors(obj) -> Dict[str, torch.Tensor]:
     under ``_parameters`` / ``_buffers`` (``lights.location = nn.Parameter(...)``).  The memoised parameter blocks
     (shader / rasteriser) key on these, so none may be skipped."""
     d = obj.__dict__
-    out = {k: v for k, v in d.items() if torch.is_tensor(v)}
-    for store in ("_parameters", "_buffers"):
-        for k, v in (d.get(store) or {}).items():
-            if v is not None:
-                out[k] = v
+    Tensor = torch.Tensor
+    out = {k: v for k, v in d.items() if isinstance(v, Tensor)}
+    store = d.get("_parameters")
+    if store:
+        out.update((k, v) for k, v in store.items() if v is not None)
+    store = d.get("_buffers")
+    if store:
+        out.update((k, v) for k, v in store.items() if v is not None)
     return out
 
 

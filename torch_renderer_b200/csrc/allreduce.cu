@@ -15,8 +15,19 @@
 // reading.  Block b always owns elements [b*1024, (b+1)*1024) and keeps its own epoch counter in device
 // memory, so the kernel can be replayed from a CUDA graph and the segment layout may change between calls.
 #include "trb_internal.cuh"
+#include "stages.cuh"   // pdl_wait
 
 namespace trb {
+
+// Optional device-side timing of the protocol (trb_allreduce_set_timing): block 0 accumulates, in nanoseconds of
+// %globaltimer, [0] push time, [1] wait-and-sum time (rank skew + one NVLink one-way latency), [2] call count.
+static unsigned long long* g_ar_timing = nullptr;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int kMaxSegments = 4;
 constexpr int kMaxPeers = 16;
@@ -44,8 +55,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_b64(const unsigned 
 
 __global__ void __launch_bounds__(256)
 allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world, long long capacity,
-                      unsigned* epochs, int* error) {
+                      unsigned* epochs, int* error, unsigned long long* timing) {
   constexpr int PER = kArChunk / 256;
+  // launched as a programmatic dependent launch: resident while the producer of the gradients drains
+  pdl_wait();
+  const bool timed = timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t0 = timed ? global_ns() : 0ull;
   const unsigned epoch = epochs[blockIdx.x] + 1u;
   const long long total = seg.start[seg.count];
   const size_t parity_off = (size_t)(epoch & 1u) * world * capacity;
@@ -68,6 +83,7 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
                              ((unsigned long long)epoch << 32) | __float_as_uint(v[u]));
     }
   }
+  const unsigned long long t1 = timed ? global_ns() : 0ull;
   // ---- 2. collect the peers' values from my inbox, sum in rank order
   const unsigned long long* mine = p.inbox[rank] + parity_off;
 #pragma unroll
@@ -93,6 +109,10 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
   }
   __syncthreads();
   if (threadIdx.x == 0) epochs[blockIdx.x] = epoch;
+  if (timed) {
+    const unsigned long long t2 = global_ns();
+    timing[0] += t1 - t0; timing[1] += t2 - t1; timing[2] += 1ull;
+  }
 }
 
 }  // namespace trb
@@ -133,8 +153,15 @@ extern "C" int trb_allreduce_sum_f32(float* const* host_segments, const int64_t*
   }
   TRB_ENTER(device);
   const int grid = (int)((total + kArChunk - 1) / kArChunk);
-  allreduce_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg, p, rank, world, (long long)capacity_floats,
-                                                                epochs, error_flag);
+  TRB_CUDA_TRY(launch_pdl(allreduce_push_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, seg, p, rank, world,
+                          (long long)capacity_floats, (unsigned*)epochs, (int*)error_flag, g_ar_timing));
   TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
+/* diagnostics: `device_u64x3` (zeroed by the caller) accumulates block 0's push / wait-and-sum nanoseconds and the
+ * call count of every later trb_allreduce_sum_f32 launch; NULL switches it off.  Process-wide. */
+extern "C" int trb_allreduce_set_timing(uint64_t* device_u64x3) {
+  g_ar_timing = (unsigned long long*)device_u64x3;
   return TRB_OK;
 }

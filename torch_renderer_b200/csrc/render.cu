@@ -146,25 +146,28 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t);
 #define TRB_K1_CTAS 4   // 64 registers: 4 x 256 threads per SM (same-box A/B: 3 -> 4 CTAs: fine 0.160 -> 0.147 ms)
 #endif
 
-template <int SHADER, int LIGHT>
+// STRIP = kStrip for batches (the streaming fill wants long rows per CTA), 1 for grids too small to fill the GPU
+// that way: one 512^2 view is 1,024 tiles = 128 strips of 8 for 148 SMs, and a 256^2 view 32 -- its ~150 busy tiles
+// were rasterised five deep by 32 CTAs (C1: 0.042 ms of fine kernel for 0.4 M pixels).
+template <int SHADER, int LIGHT, int STRIP>
 __global__ void __launch_bounds__(256, TRB_K1_CTAS)
 render_fine_k1_kernel(const FineArgs a) {
   pdl_wait();
-  const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * kStrip;
+  const int n = blockIdx.z, tby = blockIdx.y, tbx0 = blockIdx.x * STRIP;
   const int* counts = a.tile_count + (size_t)(n * a.tg.tiles_y + tby) * a.tg.tiles_x;
-  int cnt[kStrip];
+  int cnt[STRIP];
 #pragma unroll
-  for (int s = 0; s < kStrip; ++s) cnt[s] = (tbx0 + s < a.tg.tiles_x) ? __ldg(counts + tbx0 + s) : -1;
+  for (int s = 0; s < STRIP; ++s) cnt[s] = (tbx0 + s < a.tg.tiles_x) ? __ldg(counts + tbx0 + s) : -1;
   const int nbusy = __ldg(a.ws_header + 4);
   const bool rows_inside = (tby + 1) * 16 <= a.H && (a.W & 3) == 0;
   bool all_empty = true;
 #pragma unroll
-  for (int s = 0; s < kStrip; ++s) all_empty = all_empty && cnt[s] == 0;
-  if (all_empty && rows_inside && (tbx0 + kStrip) * 16 <= a.W) {
+  for (int s = 0; s < STRIP; ++s) all_empty = all_empty && cnt[s] == 0;
+  if (STRIP == kStrip && all_empty && rows_inside && (tbx0 + STRIP) * 16 <= a.W) {
     fill_empty_strip_v4<SHADER>(a, n, tbx0, tby);
   } else {
 #pragma unroll
-    for (int s = 0; s < kStrip; ++s)
+    for (int s = 0; s < STRIP; ++s)
       if (cnt[s] == 0) {
         if (rows_inside && (tbx0 + s + 1) * 16 <= a.W) fill_empty_tile_v4<SHADER>(a, n, tbx0 + s, tby);
         else fill_empty_tile<SHADER>(a, n, tbx0 + s, tby);
@@ -464,8 +467,11 @@ __device__ unsigned long long g_bw_stats[8];
 #ifndef TRB_BWD_CTAS
 #define TRB_BWD_CTAS 4
 #endif
+#ifndef TRB_BWD_KN_CTAS
+#define TRB_BWD_KN_CTAS 1
+#endif
 template <bool K1, int SHADER, int LIGHT>
-__global__ void __launch_bounds__(128, K1 ? TRB_BWD_CTAS : 1)
+__global__ void __launch_bounds__(128, K1 ? TRB_BWD_CTAS : TRB_BWD_KN_CTAS)
 render_backward_kernel(const BwdArgs a) {
   pdl_wait();
   extern __shared__ float4 s_park[];  // K>1 Phong: (g_bary from shading, g . colour_k) per [k][tid]
@@ -907,8 +913,16 @@ static inline bool is_phong(int shader) {
   return shader == TRB_SHADER_SOFT_PHONG || shader == TRB_SHADER_HARD_PHONG;
 }
 
-static int launch_render_fine_k1(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
-#define TRB_RF1(SH, L) TRB_CUDA_TRY(launch_pdl(render_fine_k1_kernel<SH, L>, grid, dim3(256), 0, st, a))
+static int launch_render_fine_k1(int shader, int light, int N, cudaStream_t st, const FineArgs& a) {
+  // strips of kStrip tiles once that still leaves two full waves of CTAs (148 SMs x TRB_K1_CTAS resident)
+  const long long tiles = (long long)a.tg.tiles_x * a.tg.tiles_y * N;
+  const bool strips = tiles >= 2ll * kStrip * kNumSMs * TRB_K1_CTAS;
+  const dim3 grid(strips ? ceil_div(a.tg.tiles_x, kStrip) : a.tg.tiles_x, a.tg.tiles_y, N);
+#define TRB_RF1(SH, L)                                                                                   \
+  do {                                                                                                   \
+    if (strips) TRB_CUDA_TRY(launch_pdl(render_fine_k1_kernel<SH, L, kStrip>, grid, dim3(256), 0, st, a)); \
+    else TRB_CUDA_TRY(launch_pdl(render_fine_k1_kernel<SH, L, 1>, grid, dim3(256), 0, st, a));           \
+  } while (0)
   if (shader == TRB_SHADER_NONE) TRB_RF1(TRB_SHADER_NONE, 0);
   else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RF1(TRB_SHADER_SOFT_SILHOUETTE, 0);
   else if (shader == TRB_SHADER_SOFT_PHONG) {
@@ -949,7 +963,7 @@ static int launch_render_backward(int shader, int light, dim3 grid, int nt, size
 
 int launch_render_fine(int shader, int light, int N, cudaStream_t st, const FineArgs& a) {
   if (a.K == 1)
-    return launch_render_fine_k1(shader, light, dim3(ceil_div(a.tg.tiles_x, kStrip), a.tg.tiles_y, N), st, a);
+    return launch_render_fine_k1(shader, light, N, st, a);
   return launch_render_fine_kn(shader, light, N, st, a);
 }
 

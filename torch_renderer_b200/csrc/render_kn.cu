@@ -22,17 +22,11 @@
 
 namespace trb {
 
-// Depth buckets of the tile-list ordering.  The key -> bucket map is piecewise linear: a first, coarse
-// histogram (kCoarse uniform buckets over the list's key range) finds the key below which the nearest
-// ~kNearTarget entries lie; that near segment then gets kNearBuckets buckets of its own and the rest of the
-// range the remaining ones.  A single uniform map spends its resolution on the empty gap between the front
-// and the back side of a closed surface: on the 1M-face sphere all ~2,000 front faces of a tile fell into 1-13
-// of 256 buckets, arrived in effectively random order, and every pixel took ~50 insertions (and ~100 exact
-// evaluations) to settle its 8 layers.
-constexpr int kBuckets = 512;
-constexpr int kCoarse = 256;
-constexpr int kNearBuckets = 384;
-constexpr int kNearTarget = 1536;
+// 256 uniform depth buckets over a tile list's key range.  (A two-level, piecewise-linear map that gave the
+// nearest ~1,500 entries 384 buckets of their own was measured on the 1M-face sphere and changed nothing --
+// 40.65 M insertions either way: that mesh's per-vertex radial noise makes every face span a depth range far wider
+// than the spacing of its neighbours' keys, so the order of min-vertex depths is not the order of sample depths.)
+constexpr int kBuckets = 256;
 
 // Diagnostic counters of the K > 1 walk (build with TRB_EXTRA_NVCC_FLAGS=-DTRB_KN_STATS; read with
 // trb_debug_kn_stats).  Not compiled into the product library.
@@ -42,13 +36,6 @@ __device__ unsigned long long g_kn_stats[16];
 #else
 #define KN_STAT(i, v) ((void)0)
 #endif
-
-// Piecewise-linear key -> bucket map (see kBuckets).  ANY map is correct -- the stop test uses the exact suffix
-// minima of the buckets -- a monotone one makes the staging order front to back.
-__device__ __forceinline__ int bucket_of(float z, float lo, float split, float near_scale, float far_scale) {
-  if (z < split) return min(kNearBuckets - 1, (int)((z - lo) * near_scale));
-  return kNearBuckets + min(kBuckets - kNearBuckets - 1, (int)((z - split) * far_scale));
-}
 
 // Block-wide maximum of a small non-negative int; contains __syncthreads (every thread must call it).
 template <int NT>
@@ -66,7 +53,13 @@ __device__ __forceinline__ int block_max_sync(int v) {
 template <int LT>
 struct KnCfg {
   static constexpr int TX = 1 << LT, NT = TX * TX;
-  static constexpr int LOGKG = (LT == 4) ? 3 : 4;  // layers parked per output pass: 8 (16x16) / 16 (8x8)
+#ifndef TRB_KN_LOGKG16
+#define TRB_KN_LOGKG16 3
+#endif
+#ifndef TRB_KN_LOGKG8
+#define TRB_KN_LOGKG8 4
+#endif
+  static constexpr int LOGKG = (LT == 4) ? TRB_KN_LOGKG16 : TRB_KN_LOGKG8;  // layers parked per output pass
   static constexpr int KG = 1 << LOGKG;
   static constexpr int ROT = 5 - LOGKG;             // slot rotation: (kk + (p >> ROT)) & (KG - 1)
   static constexpr int STAGE_BYTES = NT * 64;       // bb, va, vb (float4) + vc (float2) + zlo + id
@@ -130,7 +123,10 @@ __device__ __forceinline__ void fill_tile_kn(const FineArgs& a, int n, int x0, i
 }
 
 template <int LT, int SHADER, int LIGHT>
-__global__ void __launch_bounds__((1 << LT) * (1 << LT), LT == 4 ? 3 : 8)
+#ifndef TRB_KN_CTAS16
+#define TRB_KN_CTAS16 3
+#endif
+__global__ void __launch_bounds__((1 << LT) * (1 << LT), LT == 4 ? TRB_KN_CTAS16 : 8)
 render_fine_kn_kernel(const FineArgs a) {
   using C = KnCfg<LT>;
   constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
@@ -158,7 +154,7 @@ render_fine_kn_kernel(const FineArgs a) {
   __shared__ unsigned s_bmin[kBuckets];
   __shared__ float s_bound[kBuckets];  // min depth key over this bucket and every later one
   __shared__ float s_red[2 * (NT / 32)];
-  __shared__ unsigned short s_chunk_bucket[8192 / NT + 1];  // bucket of the first entry of every staging chunk
+  __shared__ unsigned char s_chunk_bucket[8192 / NT + 1];  // bucket of the first entry of every staging chunk
 
   const int n = blockIdx.z;
   const trb_view vd = a.views[n];
@@ -200,7 +196,7 @@ render_fine_kn_kernel(const FineArgs a) {
     const int m = min(CAP, nlist - sbase);
     const bool ordered = !overflow && can_bound && m > NT;
     if (ordered) {
-      float key_lo, key_split, near_scale, far_scale;
+      float key_lo, key_scale;
       const int2* lst = a.pairs + (size_t)off + sbase;
       // ---- 1. range of the depth keys
       float lo = 3.0e38f, hi = -3.0e38f;
@@ -219,50 +215,11 @@ render_fine_kn_kernel(const FineArgs a) {
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, s_red[2 * w]); hi = fmaxf(hi, s_red[2 * w + 1]); }
       key_lo = lo;
-      const float coarse_scale = (hi > lo) ? (float)kCoarse / (hi - lo) : 0.0f;
-      // ---- 2a. coarse histogram -> the key that closes the near segment
+      key_scale = (hi > lo) ? (float)kBuckets / (hi - lo) : 0.0f;
+      // ---- 2. histogram + exact minimum of every bucket (keys are positive: uint order == float order)
       for (int i = tid; i < m; i += NT) {
         const float z = __int_as_float(__ldg(&lst[i].y));
-        atomicAdd(&s_hist[min(kCoarse - 1, (int)((z - key_lo) * coarse_scale))], 1);
-      }
-      __syncthreads();
-      if (warp == 0) {
-        constexpr int PER = kCoarse / 32;
-        int sum = 0;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) sum += s_hist[lane * PER + q];
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        // first coarse bucket at which the running count reaches the target (the last one if it never does)
-        const int target = min(m, kNearTarget);
-        int run = incl - sum, found = kCoarse - 1;
-        bool got = false;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-          run += s_hist[lane * PER + q];
-          if (!got && run >= target) { found = lane * PER + q; got = true; }
-        }
-        const unsigned who = __ballot_sync(0xffffffffu, got);
-        const int src = who ? __ffs(who) - 1 : 31;
-        found = __shfl_sync(0xffffffffu, found, src);
-        if (lane == 0) s_red[0] = (found + 1 >= kCoarse || coarse_scale == 0.0f)
-                                      ? hi : key_lo + (float)(found + 1) / coarse_scale;
-      }
-      __syncthreads();
-      key_split = s_red[0];
-      __syncthreads();
-      for (int i = tid; i < kCoarse; i += NT) s_hist[i] = 0;
-      near_scale = (key_split > key_lo) ? (float)kNearBuckets / (key_split - key_lo) : 0.0f;
-      far_scale = (hi > key_split) ? (float)(kBuckets - kNearBuckets) / (hi - key_split) : 0.0f;
-      __syncthreads();
-      // ---- 2b. histogram + exact minimum of every bucket (keys are positive: uint order == float order)
-      for (int i = tid; i < m; i += NT) {
-        const float z = __int_as_float(__ldg(&lst[i].y));
-        const int b = bucket_of(z, key_lo, key_split, near_scale, far_scale);
+        const int b = min(kBuckets - 1, (int)((z - key_lo) * key_scale));
         atomicAdd(&s_hist[b], 1);
         atomicMin(&s_bmin[b], __float_as_uint(z));
       }
@@ -299,10 +256,10 @@ render_fine_kn_kernel(const FineArgs a) {
       for (int i = tid; i < m; i += NT) {
         const int2 e = __ldg(&lst[i]);
         const float z = __int_as_float(e.y);
-        const int b = bucket_of(z, key_lo, key_split, near_scale, far_scale);
+        const int b = min(kBuckets - 1, (int)((z - key_lo) * key_scale));
         const int pos = atomicAdd(&s_hist[b], 1);
         ord_id[pos] = e.x;
-        if ((pos & (NT - 1)) == 0) s_chunk_bucket[pos / NT] = (unsigned short)b;
+        if ((pos & (NT - 1)) == 0) s_chunk_bucket[pos / NT] = (unsigned char)b;
       }
       __syncthreads();
     }

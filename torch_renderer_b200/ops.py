@@ -7,7 +7,7 @@ boundary (SURVEY.md layer L3); the reference reaches it through ``MeshRasterizer
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Optional
 
 import torch
@@ -84,6 +84,16 @@ def _stream(device: torch.device) -> int:
     return torch._C._cuda_getCurrentRawStream(device.index)
 
 
+_EMPTY_F32 = {}
+
+
+def _empty_f32(dev: torch.device) -> torch.Tensor:
+    t = _EMPTY_F32.get(dev)
+    if t is None:
+        t = _EMPTY_F32[dev] = torch.empty((0,), dtype=torch.float32, device=dev)
+    return t
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -104,6 +114,27 @@ class ViewTable:
     shared_mesh: bool
     pair_capacity: int = 0
     _pending: object = None      # (pinned stats, event) of the last forward
+    _plans: dict = field(default_factory=dict)   # _RenderFn: static config / sizes / buffer layout per settings
+    _stats_host: object = None   # pinned int32[4], allocated once
+    _stats_event: object = None
+    _calls: int = 0
+
+    def want_stats(self) -> bool:
+        """Whether this forward should report its bin statistics (pair-list demand) back to the host: the first
+        calls (capacity is an estimate until then), afterwards one call in 16 -- an overflowing tile only costs
+        speed (it falls back to a whole-mesh scan), never faces."""
+        if self._pending is not None or torch.cuda.is_current_stream_capturing():
+            return False
+        self._calls += 1
+        return self._calls <= 4 or (self._calls & 15) == 0
+
+    def arm_stats(self, stats_dev: torch.Tensor, device: torch.device) -> None:
+        if self._stats_host is None:
+            self._stats_host = torch.empty((4,), dtype=torch.int32, pin_memory=True)
+            self._stats_event = torch.cuda.Event()
+        self._stats_host.copy_(stats_dev, non_blocking=True)
+        self._stats_event.record(torch.cuda.current_stream(device))
+        self._pending = (self._stats_host, self._stats_event)
 
     @staticmethod
     def build(face_start, face_count, p2f_base, world_vert_start, vert_count, device, shared_mesh):
@@ -226,12 +257,8 @@ class _RasterizeFn(torch.autograd.Function):
                         _ptr(nbr), N, H, W, K, float(blur_radius), int(flags), _ptr(p2f), _ptr(zbuf), _ptr(bary),
                         _ptr(dists), 0, dev.index, _stream(dev)), "rasterize_meshes (clipped faces)")
                 _bump(1)
-        if table._pending is None and not torch.cuda.is_current_stream_capturing():
-            host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
-            host_stats.copy_(stats, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            table._pending = (host_stats, ev)
+        if table.want_stats():
+            table.arm_stats(stats, dev)
         ctx.save_for_backward(verts_ndc, faces, p2f)
         ctx.table, ctx.dims, ctx.flags = table, (H, W, K), flags
         ctx.mark_non_differentiable(p2f)
@@ -305,6 +332,57 @@ def any_vertex_behind_async(verts_world, R, T, table: ViewTable, z_plane: float)
         # then the answer errs towards True, which only sends the caller to clip_faces (exact) for nothing
         return st.host_word.value >= epoch
     return answer
+
+
+class NearPlaneWatch:
+    """The near-plane question for renders that cannot wait for the answer (CUDA-graph capture, ``capture.py``):
+    the same test kernel raises a STICKY device flag (epoch 1, never lowered) and the stream -- or the captured
+    graph -- copies it into a pinned host word after every test; ``tripped()`` reads that word without
+    synchronising."""
+
+    def __init__(self, dev: torch.device):
+        self.device = dev
+        self.flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.host_word = ctypes.c_int32.from_address(self.host.data_ptr())
+
+    def enqueue(self, verts_world, R, T, table: ViewTable, z_plane: float) -> None:
+        _require_cuda(verts_world, "near-plane test")
+        dev = verts_world.device
+        verts_world, R, T = _f32c(verts_world), _f32c(R), _f32c(T)
+        check(_lib.lib().trb_any_vertex_behind(_ptr(verts_world), _ptr(R), _ptr(T), _ptr(table.views), table.N,
+                                               table.max_vert_count, float(z_plane), 1, _ptr(self.flag),
+                                               self.host.data_ptr(), None, dev.index, _stream(dev)),
+              "near-plane test")
+        _bump(1)
+
+    def tripped(self) -> bool:
+        return self.host_word.value >= 1
+
+
+_active_watch = None     # set by capture.CapturedStep while it warms up / captures a step
+
+
+class near_plane_watch:
+    """Context manager: renders inside ask the near-plane question through ``watch`` (no host wait) instead of
+    the blocking / skipped forms."""
+
+    def __init__(self, watch: NearPlaneWatch):
+        self.watch = watch
+
+    def __enter__(self):
+        global _active_watch
+        self.prev, _active_watch = _active_watch, self.watch
+        return self.watch
+
+    def __exit__(self, *exc):
+        global _active_watch
+        _active_watch = self.prev
+        return False
+
+
+def active_near_plane_watch():
+    return _active_watch
 
 
 def any_vertex_behind(verts_world, R, T, table: ViewTable, z_plane: float) -> bool:
@@ -508,78 +586,102 @@ class _RenderFn(torch.autograd.Function):
         vp = None if view_params is None else _f32c(view_params).clone()
         N, (H, W), K = table.N, spec["image_size"], spec["K"]
         shader = spec["shader"]
-        cfg = _lib.RenderConfig()
-        sc = cfg.shade
-        sc.N, sc.H, sc.W, sc.K = N, H, W, K
-        sc.shader, sc.light_kind = shader, spec["light_kind"]
-        sc.texture_mode = _lib.TEX_UV if tex_map is not None else _lib.TEX_VERTEX
+        phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
+        want_light_grad = int(view_params is not None and view_params.requires_grad)
+        sparse = int(bool(spec.get("sparse", False)) and shader != _lib.SHADER_NONE)
+        cap = table.poll_capacity()
+        # The config record, the workspace sizes and the layout of the internal buffer depend only on static things:
+        # memoised on the view table (one render call used to spend ~25 us of host time rebuilding them).
+        plan_key = (shader, spec["light_kind"], tex_map is not None, H, W, K, spec["sigma"], spec["gamma"],
+                    spec["background"], spec["blur_radius"], spec["flags"], spec["perspective"],
+                    spec["camera_center_from_rt"], want_light_grad, spec.get("z_clip", 0.0) or 0.0, verts.shape[0],
+                    0 if faces is None else faces.shape[0], sparse, cap)
+        plan = table._plans.get(plan_key)
+        if plan is None:
+            cfg = _lib.RenderConfig()
+            sc = cfg.shade
+            sc.N, sc.H, sc.W, sc.K = N, H, W, K
+            sc.shader, sc.light_kind = shader, spec["light_kind"]
+            sc.texture_mode = _lib.TEX_UV if tex_map is not None else _lib.TEX_VERTEX
+            sc.sigma, sc.gamma = spec["sigma"], spec["gamma"]
+            sc.background[0], sc.background[1], sc.background[2] = spec["background"]
+            cfg.blur_radius, cfg.raster_flags = spec["blur_radius"], spec["flags"]
+            cfg.perspective = int(spec["perspective"])
+            cfg.max_face_count, cfg.max_vert_count = table.max_face_count, table.max_vert_count
+            cfg.camera_center_from_rt = int(spec["camera_center_from_rt"])
+            # light / explicit camera-centre gradients are only reduced when the parameter block wants them
+            cfg.want_light_grad = want_light_grad
+            cfg.z_clip_value = float(spec.get("z_clip", 0.0) or 0.0)
+            # the caller returns the image only: Fragments are written for covered pixels only (include/trb.h)
+            cfg.sparse_fragments = sparse
+            cfg.num_world_verts, cfg.num_faces = verts.shape[0], (0 if faces is None else faces.shape[0])
+            cfg.num_ndc_verts = table.total_ndc_verts
+            cfg.pair_capacity = cap
+            cfg.scratch_is_zeroed = 1     # the backward zero-fills scratch with the gradient outputs (one torch.zeros)
+            ws_bytes, n_tiles, n_scratch = ctypes.c_size_t(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            check(L.trb_render_sizes(ctypes.byref(cfg), ctypes.byref(ws_bytes), ctypes.byref(n_tiles),
+                                     ctypes.byref(n_scratch)), "render")
+            # One allocation for everything the caller never sees -- workspace, NDC vertices, vertex normals, the
+            # covered-pixel list, bin statistics, and (sparse mode) the Fragments themselves -- addressed by offset
+            # (each torch.empty costs ~4 us of host time).
+            V3 = verts.shape[0] * 12
+            P = N * H * W * K
+            sizes = (ws_bytes.value, table.total_ndc_verts * 12, V3 if phong else 0, V3 if phong else 0,
+                     max(n_tiles.value, 1) * 4, 16,
+                     8 * P if sparse else 0, 4 * P if sparse else 0, 12 * P if sparse else 0, 4 * P if sparse else 0)
+            offs, total = [], 0
+            for nb in sizes:
+                offs.append(total)
+                total += (nb + 255) & ~255
+            plan = table._plans[plan_key] = (cfg, ws_bytes.value, n_scratch.value, tuple(offs), max(total, 256))
+            if len(table._plans) > 64:      # settings that change every call must not grow the memo without bound
+                table._plans.pop(next(iter(table._plans)))
+        cfg, ws_nbytes, n_scratch, offs, total = plan
         uv = None
         if tex_map is not None:
             verts_uvs, faces_uvs = spec["uv"]
             uv = _lib.UvTexture(tex_map.data_ptr(), verts_uvs.data_ptr(), faces_uvs.data_ptr(), 0,
                                 tex_map.shape[0], tex_map.shape[1])
-        sc.sigma, sc.gamma = spec["sigma"], spec["gamma"]
-        sc.background[0], sc.background[1], sc.background[2] = spec["background"]
-        cfg.blur_radius, cfg.raster_flags = spec["blur_radius"], spec["flags"]
-        cfg.perspective = int(spec["perspective"])
-        cfg.max_face_count, cfg.max_vert_count = table.max_face_count, table.max_vert_count
-        cfg.camera_center_from_rt = int(spec["camera_center_from_rt"])
-        # light / explicit camera-centre gradients are only reduced when the parameter block wants them
-        cfg.want_light_grad = int(view_params is not None and view_params.requires_grad)
-        cfg.z_clip_value = float(spec.get("z_clip", 0.0) or 0.0)
-        # the caller returns the image only: Fragments are written for covered pixels only (include/trb.h)
-        cfg.sparse_fragments = int(bool(spec.get("sparse", False)) and shader != _lib.SHADER_NONE)
-        cfg.num_world_verts, cfg.num_faces = verts.shape[0], (0 if faces is None else faces.shape[0])
-        cfg.num_ndc_verts = table.total_ndc_verts
-        cfg.pair_capacity = table.poll_capacity()
-        ws_bytes, n_tiles, n_scratch = ctypes.c_size_t(0), ctypes.c_int64(0), ctypes.c_int64(0)
-        check(L.trb_render_sizes(ctypes.byref(cfg), ctypes.byref(ws_bytes), ctypes.byref(n_tiles),
-                                 ctypes.byref(n_scratch)), "render")
-        phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
-        # One allocation for everything the caller never sees -- workspace, NDC vertices, vertex normals, the
-        # covered-pixel list, bin statistics -- addressed by offset (each torch.empty costs ~4 us of host time).
-        want_stats = table._pending is None and not torch.cuda.is_current_stream_capturing()
-        V3 = verts.shape[0] * 12
-        sizes = (ws_bytes.value, table.total_ndc_verts * 12, V3 if phong else 0, V3 if phong else 0,
-                 max(n_tiles.value, 1) * 4, 16 if want_stats else 0)
-        offs, total = [], 0
-        for nb in sizes:
-            offs.append(total)
-            total += (nb + 255) & ~255
-        aux = torch.empty((max(total, 256),), dtype=torch.uint8, device=dev)
+        want_stats = table.want_stats()
+        aux = torch.empty((total,), dtype=torch.uint8, device=dev)
         base = aux.data_ptr()
-        p_ws, p_ndc, p_nraw, p_nrm, p_hit, p_stats = (base + o for o in offs)
+        p_ws, p_ndc, p_nraw, p_nrm, p_hit, p_stats = (base + o for o in offs[:6])
         if not phong:
             p_nraw = p_nrm = 0
         if not want_stats:
             p_stats = 0
-        p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
-        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
-        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        if sparse:
+            # internal Fragments (covered pixels only): views of the same buffer, never shown to the caller
+            p2f = zbuf = bary = dists = None
+            p_p2f, p_zbuf, p_bary, p_dists = (base + o for o in offs[6:10])
+        else:
+            p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+            bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+            dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+            p_p2f, p_zbuf, p_bary, p_dists = p2f.data_ptr(), zbuf.data_ptr(), bary.data_ptr(), dists.data_ptr()
         images = (torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if shader != _lib.SHADER_NONE
-                  else torch.empty((0,), dtype=torch.float32, device=dev))
+                  else _empty_f32(dev))
         with _timed("render_forward", dev):
             check(L.trb_render_forward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
-                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, _ptr(p2f), _ptr(zbuf),
-                _ptr(bary), _ptr(dists), _ptr(images if shader != _lib.SHADER_NONE else None), p_hit,
-                p_ws, ws_bytes.value, p_stats, None if uv is None else ctypes.byref(uv), dev.index,
+                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, p_p2f, p_zbuf,
+                p_bary, p_dists, _ptr(images if shader != _lib.SHADER_NONE else None), p_hit,
+                p_ws, ws_nbytes, p_stats, None if uv is None else ctypes.byref(uv), dev.index,
                 _stream(dev)), "render")
         _bump(5 + (1 if want_stats else 0))  # prep, count, alloc, fill, fine (+ stats)
         if want_stats:
-            host_stats = torch.empty((4,), dtype=torch.int32, pin_memory=True)
-            host_stats.copy_(aux[offs[5]:offs[5] + 16].view(torch.int32), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            table._pending = (host_stats, ev)
+            table.arm_stats(aux[offs[5]:offs[5] + 16].view(torch.int32), dev)
         ctx.save_for_backward(verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists, tex_map,
                               *(spec["uv"] if tex_map is not None else ()))
         ctx.aux_offsets = (offs[1], offs[2], offs[3], offs[4], phong)
-        ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch.value
+        ctx.frag_offsets = tuple(offs[6:10]) if sparse else None
+        ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch
         ctx.token = spec.get("_token")   # Fragments cache: set once a backward has consumed this graph
-        ctx.mark_non_differentiable(p2f)
         ctx.set_materialize_grads(False)
+        if sparse:
+            return images, None, None, None, None
+        ctx.mark_non_differentiable(p2f)
         return images, p2f, zbuf, bary, dists
 
     @staticmethod
@@ -589,6 +691,10 @@ class _RenderFn(torch.autograd.Function):
         base = aux.data_ptr()
         p_ndc, p_hit = base + o_ndc, base + o_hit
         p_nraw, p_nrm = (base + o_nraw, base + o_nrm) if phong else (0, 0)
+        if ctx.frag_offsets is not None:
+            p_p2f, p_zbuf, p_bary, p_dists = (base + o for o in ctx.frag_offsets)
+        else:
+            p_p2f, p_zbuf, p_bary, p_dists = p2f.data_ptr(), zbuf.data_ptr(), bary.data_ptr(), dists.data_ptr()
         table, cfg = ctx.table, ctx.cfg
         if ctx.token is not None:
             ctx.token["consumed"] = True
@@ -607,7 +713,6 @@ class _RenderFn(torch.autograd.Function):
         flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
         parts = list(flat.split(sizes))
         scratch, g_verts, g_cols, g_R, g_T, g_proj, g_vp, g_tex = parts
-        cfg.scratch_is_zeroed = 1
         uv = None
         if tex_map is not None:
             verts_uvs, faces_uvs = ctx.saved_tensors[13:15]
@@ -618,8 +723,8 @@ class _RenderFn(torch.autograd.Function):
         with _timed("render_backward", dev):
             check(_lib.lib().trb_render_backward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
-                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, _ptr(p2f), _ptr(zbuf),
-                _ptr(bary), _ptr(dists), p_hit, _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
+                _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, p_p2f, p_zbuf,
+                p_bary, p_dists, p_hit, _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
                 _ptr(f32(g_zbuf)), _ptr(f32(g_bary)), _ptr(f32(g_dists)),
                 _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
                 _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),

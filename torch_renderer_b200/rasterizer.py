@@ -353,6 +353,15 @@ class MeshRasterizer(nn.Module):
         z_clip, cull = spec["z_clip_value"], spec["cull_to_frustum"]
         if cull and _clipping_mode == "off":
             raise ValueError("cull_to_frustum needs set_near_plane_clipping('exact')")
+        watch = ops.active_near_plane_watch()
+        if watch is not None:
+            # capture_step: the step is (about to be) replayed from a CUDA graph and cannot read an answer; the
+            # test raises a sticky flag the CapturedStep looks at between replays (capture.py)
+            if cull:
+                raise ValueError("cull_to_frustum cuts faces on the host's say-so and cannot run inside capture_step")
+            if z_clip is not None and _clipping_mode != "off":
+                watch.enqueue(meshes_world._unique_verts(), R, T, meshes_world.view_table(), z_clip)
+            return None
         if (z_clip is None and not cull) or _clipping_mode == "off" or torch.cuda.is_current_stream_capturing():
             return None
         if cull:

@@ -271,11 +271,26 @@ def run_ours(args):
     l0 = ops.launch_count()
     step_device()
     launches_per_step = ops.launch_count() - l0
-    core_run, mode_device = graphed(core_device)
+    # world > 1: the all-reduce of the shared gradients is part of the captured step (the peer-memory kernel keeps
+    # its epochs in device memory, so it replays); its block 0 accumulates push / wait nanoseconds (diagnostics)
+    ar_timing = None
+    if world > 1:
+        ar_timing = torch.zeros(3, dtype=torch.int64, device=dev)
+        from torch_renderer_b200 import _lib as _l
+        _l.lib().trb_allreduce_set_timing(ar_timing.data_ptr())
+        step_run, mode_device = graphed(step_device)
+        if mode_device != "cuda-graph":
+            core_run, mode_device = graphed(core_device)
 
-    def run_device():
-        core_run()
-        allreduce_shared_grads([verts.grad, cols.grad])
+            def step_run():
+                core_run()
+                allreduce_shared_grads([verts.grad, cols.grad])
+            mode_device += " + eager all-reduce"
+        else:
+            mode_device = "cuda-graph (all-reduce captured)"
+        run_device = step_run
+    else:
+        run_device, mode_device = graphed(core_device)
 
     for _ in range(args.warmup):
         run_device()
@@ -286,7 +301,22 @@ def run_ours(args):
     # a fixed step count so that every rank issues the same number of all-reduces
     for _ in range(1500):
         run_device()
+    if ar_timing is not None:
+        torch.cuda.synchronize()
+        ar_timing.zero_()
     ms_total, ms_repeats = timed(run_device, args.steps)
+    ar_report = None
+    if ar_timing is not None:
+        t = ar_timing.clone()
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        calls = max(int(t[2].item()), 1)
+        ar_report = {"what": "block 0 of the peer all-reduce kernel, %globaltimer ns averaged over the timed steps, per rank",
+                     "push_us": [round(float(r[0]) / max(int(r[2]), 1) / 1e3, 2) for r in per_rank],
+                     "wait_and_sum_us": [round(float(r[1]) / max(int(r[2]), 1) / 1e3, 2) for r in per_rank],
+                     "calls": calls,
+                     "reading": "wait_and_sum = rank skew (the slowest rank's backward) + one NVLink one-way latency; "
+                                "push = issuing the remote stores"}
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -432,6 +462,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if collective_check is not None:
             line["collective_check"] = collective_check
+        if ar_report is not None:
+            line["collective_timing"] = ar_report
         if other is not None:
             line["other_configs"] = other
         if c5 is not None:

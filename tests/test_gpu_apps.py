@@ -241,6 +241,13 @@ def test_capture_step_replays_equal_eager_and_flag_the_near_plane():
     import torch_renderer_b200 as trb
     from helpers import load_mesh, normalize_mesh
     dev = torch.device("cuda:0")
+    # torch's rule for whole-step capture: leaves that take part must not have been used on the legacy default
+    # stream (their gradient accumulation would be bound to it) -- the step lives on a side stream from the start
+    with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+        _capture_step_body(trb, dev, load_mesh, normalize_mesh)
+
+
+def _capture_step_body(trb, dev, load_mesh, normalize_mesh):
     v, f = load_mesh("teapot")
     v = normalize_mesh(v)
     torch.manual_seed(0)

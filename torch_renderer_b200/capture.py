@@ -19,7 +19,9 @@ waiting) and by ``check()`` (waiting).  A raised flag means some replay drew fac
 ``"raise"`` (default) raises ``NearPlaneCrossed``, ``"ignore"`` carries on.
 
 Rules for ``fn`` (those of ``torch.cuda.graphs``): fixed shapes, no host reads (``.item()``, prints of tensors),
-optimisers constructed with ``capturable=True`` where torch requires it, inputs updated IN PLACE between replays.
+optimisers constructed with ``capturable=True`` where torch requires it, inputs updated IN PLACE between replays,
+and the program's tensors living on a side stream from the start (``torch.cuda.set_stream(torch.cuda.Stream())``:
+a leaf whose gradient was first accumulated on the legacy default stream cannot take part in a capture).
 """
 from __future__ import annotations
 
@@ -58,8 +60,18 @@ class CapturedStep:
             torch.cuda.synchronize(self.device)
             self._raise_if_tripped("during warm-up")
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.outputs = fn()
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.outputs = fn()
+            except Exception as e:  # noqa: BLE001
+                if "legacy stream" in str(e) or "StreamCapture" in str(e):
+                    raise RuntimeError(
+                        "capture_step: CUDA refused the capture because part of the step is bound to the legacy "
+                        "default stream -- typically a leaf tensor whose gradient was first accumulated there.  "
+                        "Create the parameters and run the loop under a side stream "
+                        "(`torch.cuda.set_stream(torch.cuda.Stream())` at start-up), as torch's whole-network "
+                        "capture recipe asks.") from e
+                raise
         torch.cuda.synchronize(self.device)
 
     def _raise_if_tripped(self, when: str) -> None:

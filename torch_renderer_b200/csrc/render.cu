@@ -467,8 +467,10 @@ __device__ unsigned long long g_bw_stats[8];
 #ifndef TRB_BWD_CTAS
 #define TRB_BWD_CTAS 4
 #endif
+// K > 1 backward: capped at 128 registers (4 CTAs = 16 warps per SM instead of 3 at 167 registers; a few spills).
+// Same-box A/B on the 1M-face sphere: 4.02 -> 3.04 ms (5 CTAs / 96 registers: 3.38 ms).
 #ifndef TRB_BWD_KN_CTAS
-#define TRB_BWD_KN_CTAS 1
+#define TRB_BWD_KN_CTAS 4
 #endif
 template <bool K1, int SHADER, int LIGHT>
 __global__ void __launch_bounds__(128, K1 ? TRB_BWD_CTAS : TRB_BWD_KN_CTAS)

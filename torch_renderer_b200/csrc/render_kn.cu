@@ -53,8 +53,10 @@ __device__ __forceinline__ int block_max_sync(int v) {
 template <int LT>
 struct KnCfg {
   static constexpr int TX = 1 << LT, NT = TX * TX;
+// 16x16 tiles park 4 layers per output pass: 28.7 KB instead of 57 KB of shared memory, which is what lets THREE
+// CTAs (24 warps) share an SM instead of two (same-box A/B on the 1M-face sphere: fine kernel 6.04 -> 4.71 ms)
 #ifndef TRB_KN_LOGKG16
-#define TRB_KN_LOGKG16 3
+#define TRB_KN_LOGKG16 2
 #endif
 #ifndef TRB_KN_LOGKG8
 #define TRB_KN_LOGKG8 4

@@ -143,7 +143,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG") in ("VERSION", "WARN") else None  # "NCCL version ..." goes to stdout at those levels: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     # Everything runs on a non-default stream: autograd binds each leaf's gradient accumulator to the
     # stream that was current when the leaf was first used, and work bound to the legacy default stream

@@ -893,6 +893,85 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   }
 }
 
+// ---- soft silhouette, faces_per_pixel > 1: FOUR lanes per covered pixel -------------------------------------
+// camera_pose_optimizer.py:116-121 (K = 50): one thread per pixel walked up to 50 layers one after the other, each
+// step a chain of dependent loads (face -> vertices) -- 41 k covered pixels are 1,300 warps of long serial loops
+// (C3: 0.125 ms at 8 % occupancy).  Here lane j of a pixel's quad takes layers j, j+4, ...; the only cross-layer
+// quantity of sigmoid_alpha_blend, prod_k (1 - p_k), is a two-step shuffle product over the quad.
+template <int DUMMY>
+__global__ void __launch_bounds__(128, 6)
+silhouette_backward_kn_kernel(const BwdArgs a) {
+  pdl_wait();
+  const int count = a.hit_pixels[0];
+  const int H = a.H, W = a.W, K = a.K, HW = H * W;
+  const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
+  const long long items_up = (((long long)count * 4) + 31) & ~31ll;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float inv_sigma = 1.0f / a.sigma;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items_up; it += stride) {
+    const int hi = (int)(it >> 2), sub = (int)(it & 3);
+    const bool live = hi < count;
+    const int pixi = live ? a.hit_pixels[1 + hi] : 0;
+    const int n = pixi / HW;
+    const int prem = pixi - n * HW;
+    const int yi = prem / W, xi = prem - yi * W;
+    const trb_view vd = a.views[n];
+    const float px = pix_to_ndc_fast(W - 1 - xi, W, H), py = pix_to_ndc_fast(H - 1 - yi, H, W);
+    const size_t s0 = (size_t)pixi * K;
+    // ---- pass A: my layers' factors of the product (layers are a contiguous prefix: stop at the first -1)
+    int mine = 0, zeros = 0;
+    float prod_nz = 1.0f;
+    if (live) {
+      for (int k = sub; k < K && a.p2f[s0 + k] >= 0; k += 4) {
+        const float q = 1.0f - sigmoidf(-a.dists[s0 + k] * inv_sigma);
+        if (q == 0.0f) ++zeros; else prod_nz *= q;
+        ++mine;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      prod_nz *= __shfl_xor_sync(0xffffffffu, prod_nz, o);
+      zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    }
+    const float gw = live ? __ldg(a.g_images + 4 * (size_t)pixi + 3) : 0.0f;
+    // ---- pass C: per layer blend backward -> rasteriser backward -> scatter
+    const int nloop = __reduce_max_sync(0xffffffffu, mine);
+    for (int r = 0; r < nloop; ++r) {
+      const bool on = r < mine;
+      int key = -1, i0 = 0, i1 = 0, i2 = 0;
+      float gv[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) gv[i] = 0.0f;
+      if (on) {
+        const size_t s = s0 + sub + 4 * r;
+        const long long f = a.p2f[s];
+        const float d = a.dists[s];
+        const float p = sigmoidf(-d * inv_sigma), q = 1.0f - p;
+        const float others = zeros == 0 ? prod_nz / q : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
+        float gd = gw * others * p * q * (-inv_sigma);
+        float gz = 0.0f, gb0 = 0.0f, gb1 = 0.0f, gb2 = 0.0f;
+        if (a.g_zbuf) gz = a.g_zbuf[s];
+        if (a.g_dists) gd += a.g_dists[s];
+        if (a.g_bary) { gb0 = a.g_bary[s * 3]; gb1 = a.g_bary[s * 3 + 1]; gb2 = a.g_bary[s * 3 + 2]; }
+        const int lf = (int)(f - vd.p2f_base);
+        const size_t row = (size_t)(vd.face_start + lf);
+        if (a.faces != nullptr) {
+          i0 = __ldg(a.faces + 3 * row) + vd.vert_delta;
+          i1 = __ldg(a.faces + 3 * row + 1) + vd.vert_delta;
+          i2 = __ldg(a.faces + 3 * row + 2) + vd.vert_delta;
+        } else {
+          i0 = 3 * (int)row; i1 = i0 + 1; i2 = i0 + 2;
+        }
+        const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, lf);
+        sample_backward_fast(v, px, py, persp, clip, signbit(d), gz, gb0, gb1, gb2, gd, gv);
+        key = (int)f;
+      }
+      const WarpGroups wg = warp_groups(key, true);
+      warp_groups_add_xyz3(wg, key, gv, a.g_verts_ndc, i0, i1, i2);
+    }
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 static int check_render_cfg(const trb_render_config* c) {
   if (!c) return TRB_ERR_BAD_ARG;
@@ -1123,6 +1202,10 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   const dim3 grid(kNumSMs * (K == 1 ? TRB_BWD_CTAS : 512 / nt));
   if (g_dbg_events[2]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[2], st));
   if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
+  else if (sc.shader == TRB_SHADER_SOFT_SILHOUETTE && K >= 4 && a.g_verts_ndc != nullptr) {
+    TRB_CUDA_TRY(launch_pdl(silhouette_backward_kn_kernel<0>, dim3(kNumSMs * 6), dim3(128), 0, st, a));
+    TRB_LAUNCH_CHECK();
+  }
   else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, dyn, st, a);
   if (rc != TRB_OK) return rc;
   if (g_dbg_events[3]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[3], st));

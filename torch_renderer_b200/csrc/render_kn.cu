@@ -58,8 +58,11 @@ struct KnCfg {
 #ifndef TRB_KN_LOGKG16
 #define TRB_KN_LOGKG16 2
 #endif
+// 8x8 tiles (K > 24) park 4 layers per pass as well: at K = 50 the per-pixel lists already take 25.6 KB of a
+// 64-thread CTA; 28.7 KB of parking on top left 3 CTAs = 6 warps per SM for a kernel that stalls 38 % on
+// fixed-latency dependencies
 #ifndef TRB_KN_LOGKG8
-#define TRB_KN_LOGKG8 4
+#define TRB_KN_LOGKG8 2
 #endif
   static constexpr int LOGKG = (LT == 4) ? TRB_KN_LOGKG16 : TRB_KN_LOGKG8;  // layers parked per output pass
   static constexpr int KG = 1 << LOGKG;

@@ -278,7 +278,9 @@ int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes,
                      int64_t* backward_scratch_floats);
 /* view_params f32[N,20] is in/out (camera centre filled in when camera_center_from_rt).
  * Outputs: verts_ndc f32[num_ndc_verts,3]; normals_raw, normals f32[num_world_verts,3] (Phong only);
- * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); hit_pixels i32[hit_pixels_len]. */
+ * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); hit_pixels i32[hit_pixels_len]: [0] = number of
+ * covered pixels C, [1 .. 1+C) their linear pixel ids (tile by tile), and for faces_per_pixel > 1
+ * [1+N*H*W .. 1+N*H*W+C) the number of layers each of them got -- the list the fused backward walks. */
 int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        const float* verts_world, const int32_t* faces, const float* vert_colors,
                        const float* R, const float* T, const float* proj, float* view_params,

@@ -443,7 +443,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
 // ---- fused backward ----------------------------------------------------------------------------
 struct BwdArgs {
   const float* verts_ndc; const int* faces; const trb_view* views;
-  int H, W, K; unsigned flags; const int* hit_pixels;
+  int H, W, K; unsigned flags; const int* hit_pixels; const int* hit_counts;
   const long long* p2f; const float* zbuf; const float* bary; const float* dists;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   const float* g_images; const float* g_zbuf; const float* g_bary; const float* g_dists;
@@ -456,7 +456,7 @@ struct BwdArgs {
 template <int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
 template <bool K1, int SHADER, int LIGHT>
-__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park);
+__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, int nk, float4* s_park);
 
 // Diagnostic counters of the K > 1 backward scatter (TRB_KN_STATS builds only; trb_debug_bw_stats):
 // [0] warp x layer rounds of the rasteriser-backward scatter, [1] lanes with a sample, [2] distinct faces
@@ -484,7 +484,7 @@ render_backward_kernel(const BwdArgs a) {
     const bool live = i < count;
     const int pixi = live ? a.hit_pixels[1 + i] : 0;
     if (K1) render_backward_pixel_k1<SHADER, LIGHT>(a, live, pixi);
-    else render_backward_pixel<false, SHADER, LIGHT>(a, live, pixi, s_park);
+    else render_backward_pixel<false, SHADER, LIGHT>(a, live, pixi, live ? a.hit_counts[i] : 0, s_park);
   }
 }
 
@@ -651,7 +651,7 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
 }
 
 template <bool K1, int SHADER, int LIGHT>
-__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, float4* s_park) {
+__device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool live, int pixi, int nk, float4* s_park) {
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W;
@@ -669,10 +669,7 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   constexpr bool SOFT = (SHADER == TRB_SHADER_SOFT_PHONG);
   constexpr bool SIL = (SHADER == TRB_SHADER_SOFT_SILHOUETTE);
 
-  int nk = 0;
-  if (live) {
-    while (nk < K && a.p2f[s0 + nk] >= 0) ++nk;
-  }
+  // nk: layers of this pixel, written next to the covered-pixel list by the forward (no scan for the first -1)
   float4 g = make_float4(0, 0, 0, 0);
   if (SHADER != TRB_SHADER_NONE && nk > 0) g = __ldg(reinterpret_cast<const float4*>(a.g_images) + pix);
 
@@ -893,48 +890,51 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   }
 }
 
-// ---- soft silhouette, faces_per_pixel > 1: FOUR lanes per covered pixel -------------------------------------
+// ---- soft silhouette, faces_per_pixel > 1: FOUR warps per group of 32 covered pixels -------------------------
 // camera_pose_optimizer.py:116-121 (K = 50): one thread per pixel walked up to 50 layers one after the other, each
 // step a chain of dependent loads (face -> vertices) -- 41 k covered pixels are 1,300 warps of long serial loops
-// (C3: 0.125 ms at 8 % occupancy).  Here lane j of a pixel's quad takes layers j, j+4, ...; the only cross-layer
-// quantity of sigmoid_alpha_blend, prod_k (1 - p_k), is a two-step shuffle product over the quad.
-template <int DUMMY>
+// (C3: 0.125 ms at 8 % occupancy).  Here a 128-thread CTA takes 32 consecutive covered pixels; warp w handles
+// layers w, w+4, ... of all 32, so a warp still sees NEIGHBOURING PIXELS AT THE SAME LAYER (runs of one face merge
+// into one reduction, as in the one-warp version) while the serial chain is a quarter as long and four times as
+// many warps are in flight.  The only cross-layer quantity of sigmoid_alpha_blend, prod_k (1 - p_k), goes through
+// shared memory once.
 __global__ void __launch_bounds__(128, 6)
 silhouette_backward_kn_kernel(const BwdArgs a) {
   pdl_wait();
+  __shared__ float s_prod[4][32];
+  __shared__ int s_zero[4][32];
   const int count = a.hit_pixels[0];
   const int H = a.H, W = a.W, K = a.K, HW = H * W;
   const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
-  const long long items_up = (((long long)count * 4) + 31) & ~31ll;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
   const float inv_sigma = 1.0f / a.sigma;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items_up; it += stride) {
-    const int hi = (int)(it >> 2), sub = (int)(it & 3);
+  const int groups = (count + 31) >> 5;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int hi = grp * 32 + lane;
     const bool live = hi < count;
     const int pixi = live ? a.hit_pixels[1 + hi] : 0;
+    const int nk = live ? a.hit_counts[hi] : 0;
     const int n = pixi / HW;
     const int prem = pixi - n * HW;
     const int yi = prem / W, xi = prem - yi * W;
     const trb_view vd = a.views[n];
     const float px = pix_to_ndc_fast(W - 1 - xi, W, H), py = pix_to_ndc_fast(H - 1 - yi, H, W);
     const size_t s0 = (size_t)pixi * K;
-    // ---- pass A: my layers' factors of the product (layers are a contiguous prefix: stop at the first -1)
-    int mine = 0, zeros = 0;
+    // ---- pass A: this warp's factors of the product
+    int zeros = 0;
     float prod_nz = 1.0f;
-    if (live) {
-      for (int k = sub; k < K && a.p2f[s0 + k] >= 0; k += 4) {
-        const float q = 1.0f - sigmoidf(-a.dists[s0 + k] * inv_sigma);
-        if (q == 0.0f) ++zeros; else prod_nz *= q;
-        ++mine;
-      }
+    for (int k = sub; k < nk; k += 4) {
+      const float q = 1.0f - sigmoidf(-a.dists[s0 + k] * inv_sigma);
+      if (q == 0.0f) ++zeros; else prod_nz *= q;
     }
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-      prod_nz *= __shfl_xor_sync(0xffffffffu, prod_nz, o);
-      zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
-    }
+    s_prod[sub][lane] = prod_nz; s_zero[sub][lane] = zeros;
+    __syncthreads();
+    prod_nz = s_prod[0][lane] * s_prod[1][lane] * s_prod[2][lane] * s_prod[3][lane];
+    zeros = s_zero[0][lane] + s_zero[1][lane] + s_zero[2][lane] + s_zero[3][lane];
+    __syncthreads();   // the next group overwrites s_prod / s_zero
     const float gw = live ? __ldg(a.g_images + 4 * (size_t)pixi + 3) : 0.0f;
     // ---- pass C: per layer blend backward -> rasteriser backward -> scatter
+    const int mine = nk > sub ? (nk - sub + 3) >> 2 : 0;
     const int nloop = __reduce_max_sync(0xffffffffu, mine);
     for (int r = 0; r < nloop; ++r) {
       const bool on = r < mine;
@@ -1067,8 +1067,8 @@ extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_
   const trb_shade_config& s = cfg->shade;
   const TileGrid tg = make_tile_grid(s.H, s.W, s.K);
   if (workspace_bytes) *workspace_bytes = make_ws_layout(s.N, tg, cfg->pair_capacity).total;
-  // hit_pixels = [count, pixel ids...]
-  if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W + 1;
+  // hit_pixels = [count, pixel ids ... (N*H*W slots), layer counts ... (N*H*W slots, faces_per_pixel > 1 only)]
+  if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W * (s.K > 1 ? 2 : 1) + 1;
   // backward scratch: float4 accumulators for grad NDC verts [num_ndc_verts], world verts, colours and
   // normals [V each], then grad of the raw normals [V,3]
   if (backward_scratch_floats) *backward_scratch_floats = 4 * cfg->num_ndc_verts + 15 * cfg->num_world_verts;
@@ -1120,6 +1120,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.ws_header = (const int*)(wsb + ws.header); a.busy_tiles = (const int*)(wsb + ws.busy);
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
   a.hit_pixels = tile_hit;
+  a.hit_counts = K > 1 ? tile_hit + 1 + (size_t)N * H * W : nullptr;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];
@@ -1181,6 +1182,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   BwdArgs a;
   a.verts_ndc = verts_ndc; a.faces = faces; a.views = views; a.H = H; a.W = W; a.K = K;
   a.flags = cfg->raster_flags; a.hit_pixels = tile_hit;
+  a.hit_counts = K > 1 ? tile_hit + 1 + (size_t)N * H * W : nullptr;
   a.p2f = (const long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.g_images = grad_images; a.g_zbuf = grad_zbuf; a.g_bary = grad_bary; a.g_dists = grad_dists;
@@ -1203,7 +1205,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   if (g_dbg_events[2]) TRB_CUDA_TRY(cudaEventRecord(g_dbg_events[2], st));
   if (K == 1) rc = launch_render_backward<true>(sc.shader, sc.light_kind, grid, nt, 0, st, a);
   else if (sc.shader == TRB_SHADER_SOFT_SILHOUETTE && K >= 4 && a.g_verts_ndc != nullptr) {
-    TRB_CUDA_TRY(launch_pdl(silhouette_backward_kn_kernel<0>, dim3(kNumSMs * 6), dim3(128), 0, st, a));
+    TRB_CUDA_TRY(launch_pdl(silhouette_backward_kn_kernel, dim3(kNumSMs * 6), dim3(128), 0, st, a));
     TRB_LAUNCH_CHECK();
   }
   else rc = launch_render_backward<false>(sc.shader, sc.light_kind, grid, nt, dyn, st, a);

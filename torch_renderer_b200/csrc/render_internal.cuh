@@ -12,6 +12,7 @@ struct FineArgs {
   int H, W, K; float blur_radius, sqrt_blur, z_cull; unsigned flags; TileGrid tg;
   const int* tile_count; const int* tile_offset; const int2* pairs;  // (face, bits of min vertex z)
   long long* p2f; float* zbuf; float* bary; float* dists; float* images; int* hit_pixels;
+  int* hit_counts;  // K > 1: layers of each covered pixel, parallel to hit_pixels[1..] (the backward's loop bounds)
   const int* ws_header; const int* busy_tiles;
   const float* view_params; const float* verts_world; const float* normals; const float* colors;
   float sigma, gamma, bg0, bg1, bg2;
@@ -24,7 +25,8 @@ struct FineArgs {
 // that neighbouring lanes of the backward still see neighbouring pixels).  Must be reached by every
 // thread of the CTA.
 template <int NT>
-__device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int pix) {
+__device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int pix, int* hit_counts = nullptr,
+                                                  int cnt = 0) {
   __shared__ int s_wcnt[NT / 32];
   __shared__ int s_base;
   if (hit_pixels == nullptr) return;  // stand-alone rasteriser: no fused backward follows
@@ -39,7 +41,11 @@ __device__ __forceinline__ void append_hit_pixels(int* hit_pixels, bool hit, int
     s_base = tot > 0 ? atomicAdd(hit_pixels, tot) : 0;
   }
   __syncthreads();
-  if (hit) hit_pixels[1 + s_base + s_wcnt[warp] + __popc(ball & ((1u << lane) - 1u))] = pix;
+  if (hit) {
+    const int at = s_base + s_wcnt[warp] + __popc(ball & ((1u << lane) - 1u));
+    hit_pixels[1 + at] = pix;
+    if (hit_counts != nullptr) hit_counts[at] = cnt;
+  }
 }
 
 struct ShadeIn {

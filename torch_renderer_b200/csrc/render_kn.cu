@@ -430,7 +430,7 @@ render_fine_kn_kernel(const FineArgs a) {
 #endif
   const bool hit = live && cnt > 0;
   const size_t pix = ((size_t)n * H + yi) * W + xi;
-  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix);
+  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix, a.hit_counts, cnt);
   // Sparse Fragments (the caller only wants the image): covered pixels write layers [0, cnt) and one -1
   // terminator layer when cnt < K; nothing else is written, and the layer loop ends at the tile's deepest pixel.
   // s_wr[p] = number of layers pixel p writes (K for every pixel of the image in the dense layout).

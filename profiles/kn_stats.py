@@ -18,6 +18,7 @@ L.trb_debug_kn_stats(buf)
 names = ["busy_tiles", "list_entries", "faces_staged", "walk_iters", "pass_zlo", "pass_bbox", "npos1_shortcut", "npos2_pass",
          "full_evals", "pass_depth", "insertions", "shift_steps", "early_stops", "pixels_not_full"]
 out = {n: int(buf[i]) for i, n in enumerate(names)}
+out["max_list_entries"] = int(buf[14]); out["max_walk_cycles"] = int(buf[15])
 out["views"] = info["views"]
 if hasattr(L, "trb_debug_bw_stats"):
     bw = (ctypes.c_ulonglong * 8)()

@@ -52,7 +52,16 @@ __device__ __forceinline__ int block_max_sync(int v) {
 
 template <int LT>
 struct KnCfg {
-  static constexpr int TX = 1 << LT, NT = TX * TX;
+  static constexpr int TX = 1 << LT, NT = TX * TX;   // NT: pixels of the tile
+  // 8x8 tiles (K > 24, e.g. the K = 50 soft silhouette of camera_pose_optimizer.py:116-121) put TWO threads on
+  // every pixel: thread s of a pixel walks every second staged face into its own top-K list and the epilogue merges
+  // the two lists on the fly.  The busiest tile of the teapot at 512^2 (296 faces) kept one thread walking for
+  // 467 k cycles = 243 us of a 318 us kernel: that kernel is as long as its longest serial chain, not its work.
+#ifndef TRB_KN_SPLIT8
+#define TRB_KN_SPLIT8 2
+#endif
+  static constexpr int SPLIT = (LT == 4) ? 1 : TRB_KN_SPLIT8;
+  static constexpr int NTH = NT * SPLIT;              // threads of the CTA
 // 16x16 tiles park 4 layers per output pass: 28.7 KB instead of 57 KB of shared memory, which is what lets THREE
 // CTAs (24 warps) share an SM instead of two (same-box A/B on the 1M-face sphere: fine kernel 6.04 -> 4.71 ms)
 #ifndef TRB_KN_LOGKG16
@@ -67,7 +76,7 @@ struct KnCfg {
   static constexpr int LOGKG = (LT == 4) ? TRB_KN_LOGKG16 : TRB_KN_LOGKG8;  // layers parked per output pass
   static constexpr int KG = 1 << LOGKG;
   static constexpr int ROT = 5 - LOGKG;             // slot rotation: (kk + (p >> ROT)) & (KG - 1)
-  static constexpr int STAGE_BYTES = NT * 64;       // bb, va, vb (float4) + vc (float2) + zlo + id
+  static constexpr int STAGE_BYTES = NTH * 64;      // bb, va, vb (float4) + vc (float2) + zlo + id, one face per thread
   static constexpr int OUT_BYTES = NT * KG * 28;    // p2f (8) + zbuf (4) + dists (4) + bary (12)
   // list entries ordered per super-chunk (face ids, 4 B each)
   __host__ __device__ static constexpr int cap(int K) {
@@ -84,7 +93,7 @@ struct KnCfg {
 // alignment ((W*K) % 4 == 0) -- for K = 50 at 512^2 the scalar version was 35% of all instructions of the kernel.
 template <int LT, int SHADER>
 __device__ __forceinline__ void fill_tile_kn(const FineArgs& a, int n, int x0, int y0) {
-  constexpr int TX = 1 << LT, NT = TX * TX;
+  constexpr int TX = 1 << LT, NP = TX * TX, NT = KnCfg<LT>::NTH;   // NT: threads (the store loops' stride)
   const int tid = threadIdx.x;
   const int K = a.K, H = a.H, W = a.W;
   const int rows = min(TX, H - y0), cols = min(TX, W - x0);
@@ -120,7 +129,7 @@ __device__ __forceinline__ void fill_tile_kn(const FineArgs& a, int n, int x0, i
   }
   if (SHADER == TRB_SHADER_NONE) return;
   const int lx = tid & (TX - 1), ly = tid >> LT;
-  if (lx < cols && ly < rows) {
+  if (tid < NP && lx < cols && ly < rows) {
     const float4 bgv = (SHADER == TRB_SHADER_SOFT_SILHOUETTE) ? make_float4(1.0f, 1.0f, 1.0f, 0.0f)
                                                               : make_float4(a.bg0, a.bg1, a.bg2, 0.0f);
     st_cs(reinterpret_cast<float4*>(a.images) + ((size_t)(n * H + y0 + ly) * W + x0 + lx), bgv);
@@ -131,10 +140,11 @@ template <int LT, int SHADER, int LIGHT>
 #ifndef TRB_KN_CTAS16
 #define TRB_KN_CTAS16 3
 #endif
-__global__ void __launch_bounds__((1 << LT) * (1 << LT), LT == 4 ? TRB_KN_CTAS16 : 8)
+__global__ void __launch_bounds__(KnCfg<LT>::NTH, LT == 4 ? TRB_KN_CTAS16 : (KnCfg<LT>::SPLIT == 2 ? 3 : 8))
 render_fine_kn_kernel(const FineArgs a) {
   using C = KnCfg<LT>;
-  constexpr int TX = C::TX, NT = C::NT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
+  // NP: pixels of the tile; NT: threads of the CTA (= NP * SPLIT); thread tid works on pixel tid % NP
+  constexpr int TX = C::TX, NP = C::NT, NT = C::NTH, SPLIT = C::SPLIT, KG = C::KG, LOGKG = C::LOGKG, ROT = C::ROT;
   pdl_wait();
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int K = a.K;
@@ -151,10 +161,10 @@ render_fine_kn_kernel(const FineArgs a) {
   int* s_id = reinterpret_cast<int*>(s_zlo + NT);
   int* ord_id = reinterpret_cast<int*>(s_un + C::STAGE_BYTES);  // [CAP] face ids in depth-bucket order
   // (b) epilogue: KG layers of the tile parked for the coalesced write-out
-  long long* o_p2f = reinterpret_cast<long long*>(s_un);  // [NT][KG]
-  float* o_z = reinterpret_cast<float*>(o_p2f + NT * KG);
-  float* o_d = o_z + NT * KG;
-  float* o_b = o_d + NT * KG;                              // [NT][KG][3]
+  long long* o_p2f = reinterpret_cast<long long*>(s_un);  // [NP][KG]
+  float* o_z = reinterpret_cast<float*>(o_p2f + NP * KG);
+  float* o_d = o_z + NP * KG;
+  float* o_b = o_d + NP * KG;                              // [NP][KG][3]
   __shared__ int s_hist[kBuckets];
   __shared__ unsigned s_bmin[kBuckets];
   __shared__ float s_bound[kBuckets];  // min depth key over this bucket and every later one
@@ -166,8 +176,10 @@ render_fine_kn_kernel(const FineArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = a.H, W = a.W;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TX;
-  const int xi = x0 + (tid & (TX - 1));
-  const int yi = y0 + (tid >> LT);
+  const int p = tid & (NP - 1);      // pixel of the tile
+  const int slice = tid / NP;        // which share of the staged faces this thread walks (0 when SPLIT == 1)
+  const int xi = x0 + (p & (TX - 1));
+  const int yi = y0 + (p >> LT);
   const bool live = (xi < W) && (yi < H);
 
   const int t = (n * a.tg.tiles_y + blockIdx.y) * a.tg.tiles_x + blockIdx.x;
@@ -194,6 +206,8 @@ render_fine_kn_kernel(const FineArgs a) {
 #ifdef TRB_KN_STATS
   unsigned kn_st[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (tid == 0) { KN_STAT(0, 1); KN_STAT(1, nlist); }
+  const long long kn_t0 = clock64();
+  if (tid == 0) atomicMax(&g_kn_stats[14], (unsigned long long)nlist);
 #endif
   int cnt = 0;
   float kth = 3.0e38f;  // depth of the pixel's K-th layer once the list is full (register copy of kz[K-1])
@@ -306,7 +320,7 @@ render_fine_kn_kernel(const FineArgs a) {
       const int mm = min(NT, m - base);
       if (tid == 0) KN_STAT(2, mm);
       if (live) {
-        for (int q = 0; q < mm; ++q) {
+        for (int q = slice; q < mm; q += SPLIT) {
           KN_STAT(3, 1);
           // cheapest test first: once the K-th layer has settled it rejects ~90% of a depth-ordered list
           if (s_zlo[q] > kth) continue;
@@ -421,24 +435,36 @@ render_fine_kn_kernel(const FineArgs a) {
 
 #ifdef TRB_KN_STATS
   if (live && cnt < K) KN_STAT(13, 1);
+  atomicMax(&g_kn_stats[15], (unsigned long long)(clock64() - kn_t0));   // longest list walk of any thread (cycles)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 14; ++i) {
     unsigned v = kn_st[i];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0 && v) atomicAdd(&g_kn_stats[i], (unsigned long long)v);
   }
 #endif
-  const bool hit = live && cnt > 0;
+  // ---- SPLIT == 2: the two threads of a pixel hold two sorted lists A (slice 0) and B (slice 1); the pixel's
+  // layers are their merge, produced on the fly by both threads (same sequence), each evaluating every second layer
+  int cntA = cnt, cntB = 0, total = cnt;
+  const int colA = (SPLIT == 2) ? p : tid, colB = p + NP;
+  if (SPLIT == 2) {
+    __shared__ int s_cnt2[NT];
+    s_cnt2[tid] = cnt;
+    __syncthreads();
+    cntA = s_cnt2[colA]; cntB = s_cnt2[colB];
+    total = min(K, cntA + cntB);
+  }
+  const bool hit = live && slice == 0 && total > 0;
   const size_t pix = ((size_t)n * H + yi) * W + xi;
-  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix, a.hit_counts, cnt);
-  // Sparse Fragments (the caller only wants the image): covered pixels write layers [0, cnt) and one -1
-  // terminator layer when cnt < K; nothing else is written, and the layer loop ends at the tile's deepest pixel.
+  append_hit_pixels<NT>(a.hit_pixels, hit, (int)pix, a.hit_counts, total);
+  // Sparse Fragments (the caller only wants the image): covered pixels write layers [0, total) and one -1
+  // terminator layer when total < K; nothing else is written, and the layer loop ends at the tile's deepest pixel.
   // s_wr[p] = number of layers pixel p writes (K for every pixel of the image in the dense layout).
-  __shared__ int s_wr[NT];
+  __shared__ int s_wr[NP];
   const bool sparse = a.sparse != 0;
-  const int n_write = !live ? 0 : (sparse ? (cnt > 0 ? min(cnt + 1, K) : 0) : K);
-  s_wr[tid] = n_write;
-  const int k_end = sparse ? block_max_sync<NT>(n_write) : K;   // barrier: also publishes s_wr
+  const int n_write = (!live || slice != 0) ? 0 : (sparse ? (total > 0 ? min(total + 1, K) : 0) : K);
+  if (slice == 0) s_wr[p] = n_write;
+  const int k_end = sparse ? block_max_sync<NT>(n_write) : K;   // s_wr is published by the barrier after parking
 
   ViewParams vp;
   const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces, a.uv};
@@ -450,69 +476,99 @@ render_fine_kn_kernel(const FineArgs a) {
   F3 hard_c = {a.bg0, a.bg1, a.bg2};
   if (SHADER == TRB_SHADER_SOFT_PHONG) {
     zrange = vp.zfar - vp.znear;
-    if (cnt > 0) zmax = fmaxf(eps, (vp.zfar - kz[tid]) / zrange);
+    if (total > 0) {
+      float z_first = cntA > 0 ? kz[colA] : 3.0e38f;
+      if (SPLIT == 2 && cntB > 0 && (cntA == 0 || cand_less(kz[colB], kf[colB], kz[colA], kf[colA]))) z_first = kz[colB];
+      zmax = fmaxf(eps, (vp.zfar - z_first) / zrange);
+    }
   }
-  const int rot = tid >> ROT;
+  const int rot = p >> ROT;
+  int ia = 0, ib = 0;   // merge cursors
   for (int k0 = 0; k0 < k_end; k0 += KG) {
     const int kg = min(KG, k_end - k0);
     for (int kk = 0; kk < kg; ++kk) {
       const int k = k0 + kk;
+      const bool mine = (SPLIT == 1) || ((k & 1) == slice);
       Sample s = {-1.0f, -1.0f, -1.0f, -1.0f, -1.0f};
       long long pf = -1;
-      if (k < cnt) {
-        const int f = kf[k * NT + tid];
-        const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
-        eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
-        pf = (long long)vd.p2f_base + f;
-        if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
-          alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
-        } else if (SHADER == TRB_SHADER_HARD_PHONG) {
-          if (k == 0) hard_c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
-        } else if (SHADER == TRB_SHADER_SOFT_PHONG) {
-          const float prob = sigmoidf(-s.d / a.sigma);
-          alpha *= 1.0f - prob;
-          const float zinv = (vp.zfar - s.z) / zrange;
-          const float w = prob * expf((zinv - zmax) / a.gamma);
-          const F3 c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
-          wsum += w;
-          acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
+      if (k < total) {
+        bool take_a = true;
+        if (SPLIT == 2)
+          take_a = ib >= cntB || (ia < cntA && cand_less(kz[ia * NT + colA], kf[ia * NT + colA],
+                                                         kz[ib * NT + colB], kf[ib * NT + colB]));
+        const int f = take_a ? kf[ia * NT + colA] : kf[ib * NT + colB];
+        if (take_a) ++ia; else ++ib;
+        if (mine) {
+          const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
+          eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
+          pf = (long long)vd.p2f_base + f;
+          if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+            alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
+          } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+            if (k == 0) hard_c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+          } else if (SHADER == TRB_SHADER_SOFT_PHONG) {
+            const float prob = sigmoidf(-s.d / a.sigma);
+            alpha *= 1.0f - prob;
+            const float zinv = (vp.zfar - s.z) / zrange;
+            const float w = prob * expf((zinv - zmax) / a.gamma);
+            const F3 c = shade_sample<LIGHT>(sin, vd, vp, f, s.c0, s.c1, s.c2);
+            wsum += w;
+            acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
+          }
         }
       }
-      const int slot = tid * KG + ((kk + rot) & (KG - 1));
-      o_p2f[slot] = pf; o_z[slot] = s.z; o_d[slot] = s.d;
-      o_b[3 * slot] = s.c0; o_b[3 * slot + 1] = s.c1; o_b[3 * slot + 2] = s.c2;
+      if (mine) {
+        const int slot = p * KG + ((kk + rot) & (KG - 1));
+        o_p2f[slot] = pf; o_z[slot] = s.z; o_d[slot] = s.d;
+        o_b[3 * slot] = s.c0; o_b[3 * slot + 1] = s.c1; o_b[3 * slot + 2] = s.c2;
+      }
     }
     __syncthreads();
     // ---- the CTA writes the parked layers out as contiguous runs
-    for (int idx = tid; idx < NT * KG; idx += NT) {
-      const int p = idx >> LOGKG;
-      const int kk = ((idx & (KG - 1)) - (p >> ROT)) & (KG - 1);
-      const int gx = x0 + (p & (TX - 1)), gy = y0 + (p >> LT);
-      if (kk < kg && k0 + kk < s_wr[p]) {
+    for (int idx = tid; idx < NP * KG; idx += NT) {
+      const int pp = idx >> LOGKG;
+      const int kk = ((idx & (KG - 1)) - (pp >> ROT)) & (KG - 1);
+      const int gx = x0 + (pp & (TX - 1)), gy = y0 + (pp >> LT);
+      if (kk < kg && k0 + kk < s_wr[pp]) {
         const size_t g = ((size_t)(n * H + gy) * W + gx) * K + k0 + kk;
         st_cs(a.p2f + g, o_p2f[idx]);
         st_cs(a.zbuf + g, o_z[idx]);
         st_cs(a.dists + g, o_d[idx]);
       }
     }
-    for (int idx = tid; idx < NT * KG * 3; idx += NT) {
+    for (int idx = tid; idx < NP * KG * 3; idx += NT) {
       const int e = idx / 3, c = idx - 3 * e;
-      const int p = e >> LOGKG;
-      const int kk = ((e & (KG - 1)) - (p >> ROT)) & (KG - 1);
-      const int gx = x0 + (p & (TX - 1)), gy = y0 + (p >> LT);
-      if (kk < kg && k0 + kk < s_wr[p]) {
+      const int pp = e >> LOGKG;
+      const int kk = ((e & (KG - 1)) - (pp >> ROT)) & (KG - 1);
+      const int gx = x0 + (pp & (TX - 1)), gy = y0 + (pp >> LT);
+      if (kk < kg && k0 + kk < s_wr[pp]) {
         const size_t g = ((size_t)(n * H + gy) * W + gx) * K + k0 + kk;
         st_cs(a.bary + 3 * g + c, o_b[idx]);
       }
     }
     __syncthreads();
   }
-  if (SHADER == TRB_SHADER_NONE || !live) return;
+  if (SHADER == TRB_SHADER_NONE) return;
+  if (SPLIT == 2 && SHADER != TRB_SHADER_HARD_PHONG) {
+    // slice 1 hands its share of the blend sums to slice 0 (the parking area is free again)
+    float* s_part = reinterpret_cast<float*>(s_un);   // [NP][5]
+    if (slice == 1) {
+      s_part[5 * p] = alpha; s_part[5 * p + 1] = wsum;
+      s_part[5 * p + 2] = acc.x; s_part[5 * p + 3] = acc.y; s_part[5 * p + 4] = acc.z;
+    }
+    __syncthreads();
+    if (slice == 0) {
+      alpha *= s_part[5 * p]; wsum += s_part[5 * p + 1];
+      acc.x += s_part[5 * p + 2]; acc.y += s_part[5 * p + 3]; acc.z += s_part[5 * p + 4];
+    }
+  }
+  const int cnt_total = total;
+  if (!live || slice != 0) return;
   float4 out;
   if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
     out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
   } else if (SHADER == TRB_SHADER_HARD_PHONG) {
-    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt > 0 ? 1.0f : 0.0f);
+    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt_total > 0 ? 1.0f : 0.0f);
   } else {
     const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
     const float inv = 1.0f / (wsum + delta);
@@ -525,12 +581,12 @@ render_fine_kn_kernel(const FineArgs a) {
 template <int LT>
 static int launch_kn(int shader, int light, dim3 grid, cudaStream_t st, const FineArgs& a) {
   using C = KnCfg<LT>;
-  const size_t dyn = (size_t)a.K * C::NT * 8 + C::union_bytes(a.K);
+  const size_t dyn = (size_t)a.K * C::NTH * 8 + C::union_bytes(a.K);
 #define TRB_RKN(SH, L)                                                                              \
   do {                                                                                              \
     auto kern = render_fine_kn_kernel<LT, SH, L>;                                                   \
     TRB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-    TRB_CUDA_TRY(launch_pdl(kern, grid, dim3(C::NT), dyn, st, a));                                  \
+    TRB_CUDA_TRY(launch_pdl(kern, grid, dim3(C::NTH), dyn, st, a));                                 \
   } while (0)
   if (shader == TRB_SHADER_NONE) TRB_RKN(TRB_SHADER_NONE, 0);
   else if (shader == TRB_SHADER_SOFT_SILHOUETTE) TRB_RKN(TRB_SHADER_SOFT_SILHOUETTE, 0);

@@ -482,7 +482,8 @@ def measure_other_configs(dev, args, peak):
     import bench_workloads as wl
     from torch_renderer_b200 import _lib, ops
     out = {}
-    plan = (("C1", 20), ("C3", 20), ("C3cow", 20), ("C4", 20), ("pose_step", 20), ("pose_step_cached", 20), ("C5", 3))
+    plan = (("C1", 20), ("C3", 20), ("C3cow", 20), ("C4", 20), ("pose_step", 20), ("pose_step_cached", 20),
+            ("clipped", 20), ("C5", 3))
     for name, steps in plan:
         trb.set_fragment_cache(False)
         trb.set_near_plane_clipping("exact")     # the defaults a drop-in script gets
@@ -513,8 +514,9 @@ def measure_other_configs(dev, args, peak):
             for _ in range(min(steps, 10)):
                 step()
                 torch.cuda.synchronize()
-                fine.append(evs[0].elapsed_time(evs[1]))
-                if name != "C1":
+                if name != "clipped":      # the clipped route runs the stand-alone kernels (see calls_ms)
+                    fine.append(evs[0].elapsed_time(evs[1]))
+                if name not in ("C1", "clipped"):
                     bwd.append(evs[2].elapsed_time(evs[3]))
             _lib.lib().trb_debug_set_events(None, None, None, None)
             calls = ops.stop_event_log()
@@ -522,7 +524,7 @@ def measure_other_configs(dev, args, peak):
             # the same step replayed from ONE CUDA graph (trb.capture_step: the near-plane flag is checked
             # asynchronously between replays instead of being waited for)
             graph = None
-            if name != "C5" and not args.no_graph:
+            if name not in ("C5", "clipped") and not args.no_graph:   # clipped: cutting faces needs the host's answer
                 try:
                     cap = trb.capture_step(step)
                     for _ in range(3):
@@ -547,7 +549,7 @@ def measure_other_configs(dev, args, peak):
             out[name] = {"what": info["what"], "views_per_s": round(info["views"] / ms * 1e3, 2), "captured": graph,
                          "ms_per_step": round(ms, 4), "ms_per_step_repeats": [round(r, 4) for r in reps],
                          "host_issue_ms_per_step": round(statistics.median(host), 4), "steps": steps,
-                         "fine_kernel_ms": round(statistics.median(fine), 4),
+                         "fine_kernel_ms": round(statistics.median(fine), 4) if fine else None,
                          "backward_kernel_ms": round(statistics.median(bwd), 4) if bwd else None,
                          "calls_ms": {k: round(t / n, 4) for k, (n, t) in sorted(calls.items())},
                          "algorithmic_bytes_per_step": int(info["bytes"]), "algorithmic_GBps": round(gbs, 1),

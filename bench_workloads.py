@@ -184,7 +184,30 @@ def pose_step(dev, cache):
                            + (" (Fragments cache on)" if cache else ""))
 
 
+def clipped(dev, size=256):
+    """The near-plane route: teapot with the FoV camera 1.25 units from its centre, so part of the mesh
+    lies behind z_clip = znear / 2 = 0.5 -- every render goes through clip_faces (faces cut, stand-alone
+    rasteriser, clip_resequence, stand-alone shader), forward + backward to the vertices."""
+    v, f = load_mesh("teapot"); v = normalize_mesh(v)
+    vd = v.to(dev).requires_grad_(True)
+    cols = torch.rand(1, v.shape[0], 3, generator=torch.Generator().manual_seed(0)).to(dev)
+    R, T = trb.look_at_view_transform(1.25, 10, 20)
+    cams = trb.FoVPerspectiveCameras(device=dev, R=R.to(dev), T=T.to(dev))
+    rend = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=size)),
+                            trb.SoftPhongShader(device=dev, cameras=cams,
+                                                lights=trb.PointLights(device=dev, location=[[0, 0, -3.0]])))
+    fd = f.to(dev)
+
+    def step():
+        vd.grad = None
+        m = trb.Meshes([vd], [fd], textures=trb.TexturesVertex(cols))
+        (rend(m)[..., :3] ** 2).mean().backward()
+    return step, dict(views=1, bytes=bview(1, size, size, v.shape[0], f.shape[0]),
+                      what=f"teapot {size}^2 K=1 SoftPhong fwd+bwd with vertices behind the near plane (clip_faces route)")
+
+
 BUILDERS = {
+    "clipped": clipped,
     "pose_step": lambda dev: pose_step(dev, False),
     "pose_step_cached": lambda dev: pose_step(dev, True),
     "C1": c1,

@@ -318,6 +318,16 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
 int trb_points_raster_forward(const float* points_ndc, const float* radius, const trb_view* views, int N, int H,
                               int W, int K, int32_t* idx, float* zbuf, float* dists, int device,
                               trb_stream_t stream);
+/* The same rasteriser with per-tile point lists (count -> allocate -> fill; points are their own bounding discs):
+ * a tile only sees the points whose disc can reach it instead of streaming the whole cloud.  `workspace` (caller
+ * allocated, trb_points_raster_workspace_bytes; contents need not be initialised) holds the tile counters and
+ * `entry_capacity` list entries; tiles whose list does not fit fall back to the whole-cloud scan, so the result
+ * never depends on the capacity.  `max_points` = largest point count of a view.  Same outputs, bit for bit. */
+int trb_points_raster_workspace_bytes(int N, int H, int W, int64_t entry_capacity, size_t* bytes);
+int trb_points_raster_forward_binned(const float* points_ndc, const float* radius, const trb_view* views, int N,
+                                     int max_points, int H, int W, int K, int64_t entry_capacity, void* workspace,
+                                     size_t workspace_bytes, int32_t* idx, float* zbuf, float* dists, int device,
+                                     trb_stream_t stream);
 int trb_points_raster_backward(const float* points_ndc, const int32_t* idx, const float* grad_zbuf,
                                const float* grad_dists, int N, int H, int W, int K, float* grad_points, int device,
                                trb_stream_t stream);

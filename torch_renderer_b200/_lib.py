@@ -72,6 +72,8 @@ _SIGNATURES = {
     "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture), _i, _vp],
     "trb_debug_set_events": [_vp, _vp, _vp, _vp],
     "trb_points_raster_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "trb_points_raster_workspace_bytes": [_i, _i, _i, _i64, _c.POINTER(_sz)],
+    "trb_points_raster_forward_binned": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _sz, _vp, _vp, _vp, _i, _vp],
     "trb_points_raster_backward": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "trb_points_composite_forward": [_i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp],
     "trb_points_composite_backward": [_i, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _i, _vp],

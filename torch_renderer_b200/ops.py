@@ -751,19 +751,28 @@ def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec
 # Point clouds (csrc/points_render.cu)
 class _RasterizePointsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points_ndc, radius, table: ViewTable, H, W, K):
+    def forward(ctx, points_ndc, radius, table: ViewTable, H, W, K, tiles_per_point):
         _require_cuda(points_ndc, "rasterize_points")
         points_ndc, radius = _f32c(points_ndc), _f32c(radius)
         dev = points_ndc.device
         N = table.N
+        L = _lib.lib()
         idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
         zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        # per-tile point lists: every point enters the tiles its disc can reach (a known scalar radius bounds that
+        # number; per-point radii get 8 entries per point -- tiles that do not fit scan the whole cloud instead)
+        total_points = points_ndc.shape[0]
+        capacity = int(min(total_points * max(int(tiles_per_point), 1) + 1024, (1 << 31) - 1))
+        nbytes = ctypes.c_size_t(0)
+        check(L.trb_points_raster_workspace_bytes(N, H, W, capacity, ctypes.byref(nbytes)), "rasterize_points")
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
         with _timed("points_raster_forward", dev):
-            check(_lib.lib().trb_points_raster_forward(_ptr(points_ndc), _ptr(radius), _ptr(table.views), N, H, W, K,
-                                                       _ptr(idx), _ptr(zbuf), _ptr(dists), dev.index, _stream(dev)),
+            check(L.trb_points_raster_forward_binned(_ptr(points_ndc), _ptr(radius), _ptr(table.views), N,
+                                                     table.max_face_count, H, W, K, capacity, _ptr(ws), nbytes.value,
+                                                     _ptr(idx), _ptr(zbuf), _ptr(dists), dev.index, _stream(dev)),
                   "rasterize_points")
-        _bump(1)
+        _bump(5)
         ctx.save_for_backward(points_ndc, idx)
         ctx.dims = (N, H, W, K)
         ctx.mark_non_differentiable(idx)
@@ -774,12 +783,12 @@ class _RasterizePointsFn(torch.autograd.Function):
     def backward(ctx, _g_idx, g_zbuf, g_dists):
         points_ndc, idx = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
-            return (None,) * 6
+            return (None,) * 7
         N, H, W, K = ctx.dims
         dev = points_ndc.device
         g_points = torch.zeros_like(points_ndc)
         if (g_zbuf is None and g_dists is None) or points_ndc.numel() == 0:
-            return (g_points,) + (None,) * 5
+            return (g_points,) + (None,) * 6
         g_zbuf = None if g_zbuf is None else _f32c(g_zbuf)
         g_dists = None if g_dists is None else _f32c(g_dists)
         with _timed("points_raster_backward", dev):
@@ -787,15 +796,20 @@ class _RasterizePointsFn(torch.autograd.Function):
                                                         W, K, _ptr(g_points), dev.index, _stream(dev)),
                   "rasterize_points backward")
         _bump(1)
-        return (g_points,) + (None,) * 5
+        return (g_points,) + (None,) * 6
 
 
-def rasterize_points_ndc(points_ndc, radius, table: ViewTable, image_size, points_per_pixel):
-    """points_ndc f32 (P, 3) packed, radius f32 (P,), one view per cloud -> (idx i32 (N,H,W,K), zbuf, dists)."""
+def rasterize_points_ndc(points_ndc, radius, table: ViewTable, image_size, points_per_pixel, max_radius=None):
+    """points_ndc f32 (P, 3) packed, radius f32 (P,), one view per cloud -> (idx i32 (N,H,W,K), zbuf, dists).
+    ``max_radius`` (a host float, when the settings hold a scalar radius) sizes the per-tile lists exactly."""
     H, W = image_size
     if points_per_pixel > _lib.MAX_FACES_PER_PIXEL:
         raise ValueError(f"Must have points_per_pixel <= {_lib.MAX_FACES_PER_PIXEL}")
-    return _RasterizePointsFn.apply(points_ndc, radius, table, int(H), int(W), int(points_per_pixel))
+    tiles_per_point = 8
+    if max_radius is not None and max_radius == max_radius and max_radius >= 0:
+        r_px = float(max_radius) * 1.0001 * min(H, W) / 2.0 + 0.6      # NDC -> pixels (the short side spans 2)
+        tiles_per_point = min((int(2.0 * r_px / 16.0) + 2) ** 2, 4096)
+    return _RasterizePointsFn.apply(points_ndc, radius, table, int(H), int(W), int(points_per_pixel), tiles_per_point)
 
 
 COMPOSITE_ALPHA, COMPOSITE_NORM_WEIGHTED = 0, 1

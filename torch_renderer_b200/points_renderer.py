@@ -61,7 +61,8 @@ def rasterize_points(pointclouds: Pointclouds, image_size=256, radius=0.01, poin
     H, W = _parse_image_size(image_size)
     _check_bin_size(bin_size, H, W)
     return ops.rasterize_points_ndc(pointclouds.points_packed(), _packed_radius(radius, pointclouds),
-                                    pointclouds.view_table(), (H, W), points_per_pixel)
+                                    pointclouds.view_table(), (H, W), points_per_pixel,
+                                    max_radius=None if torch.is_tensor(radius) else float(radius))
 
 
 class PointsRasterizer(nn.Module):
@@ -99,8 +100,10 @@ class PointsRasterizer(nn.Module):
         H, W = _parse_image_size(settings.image_size)
         _check_bin_size(settings.bin_size, H, W)
         points_ndc = self.transform(point_clouds, **kwargs)
-        idx, zbuf, dists = ops.rasterize_points_ndc(points_ndc, _packed_radius(settings.radius, point_clouds),
-                                                    point_clouds.view_table(), (H, W), settings.points_per_pixel)
+        idx, zbuf, dists = ops.rasterize_points_ndc(
+            points_ndc, _packed_radius(settings.radius, point_clouds), point_clouds.view_table(), (H, W),
+            settings.points_per_pixel,
+            max_radius=None if torch.is_tensor(settings.radius) else float(settings.radius))
         return PointFragments(idx=idx, zbuf=zbuf, dists=dists)
 
 

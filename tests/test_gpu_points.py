@@ -179,7 +179,7 @@ def test_binned_point_rasteriser_reference_settings_and_list_overflow():
     want = pr.rasterize_points(cloud.numpy(), np.array([0]), np.array([n]), np.full((n,), 0.003, np.float32), (256, 256), 10)
     pc = trb.Pointclouds([cloud.to(DEV)])
     idx, zbuf, dists = trb.rasterize_points(pc, 256, 0.003, 10)
-    assert (want[0] >= 0).sum() > 20000
+    assert (want[0] >= 0).sum() > 5000
     assert int((idx.cpu().numpy() != want[0]).sum()) == 0
     assert np.allclose(zbuf.cpu().numpy(), want[1], **TOL) and np.allclose(dists.cpu().numpy(), want[2], **TOL)
     # (b) big discs, capacity sized for tiny ones: most tiles overflow

@@ -235,6 +235,30 @@ points_raster_binned_kernel(const float* __restrict__ points, const float* __res
       }
     }
   }
+  if (SMEM_Q) {
+    // Coalesced write-out: layer k of pixel p lives at (p*K + k), so a thread-per-pixel store touches one word in
+    // each of 32 sectors; here the CTA walks the tile's rows as contiguous runs of 16*K words instead.
+    __shared__ int s_qn[kPtsThreads];
+    s_qn[tid] = qn;
+    __syncthreads();
+    const int rows = min(kPtsTile, H - ty * kPtsTile), cols = min(kPtsTile, W - tx * kPtsTile);
+    const int run = cols * K;
+    const float* gz = s_q;
+    const float* gd = s_q + (size_t)K * kPtsThreads;
+    const int* gi = reinterpret_cast<const int*>(s_q + 2 * (size_t)K * kPtsThreads);
+    for (int r = 0; r < rows; ++r) {
+      const size_t o = (((size_t)n * H + ty * kPtsTile + r) * W + tx * kPtsTile) * K;
+      for (int i = tid; i < run; i += kPtsThreads) {
+        const int c = i / K, k = i - c * K;
+        const int pp = r * kPtsTile + c;
+        const bool hit = k < s_qn[pp];
+        idx[o + i] = hit ? gi[k * kPtsThreads + pp] : -1;
+        zbuf[o + i] = hit ? gz[k * kPtsThreads + pp] : -1.0f;
+        dists[o + i] = hit ? gd[k * kPtsThreads + pp] : -1.0f;
+      }
+    }
+    return;
+  }
   if (!live) return;
   const size_t o = (((size_t)n * H + yi) * W + xi) * K;
   for (int k = 0; k < K; ++k) {

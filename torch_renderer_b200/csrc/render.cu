@@ -453,6 +453,20 @@ struct BwdArgs {
   UvTex uv; float* g_tex_map;  // TexturesUV: texture lookup instead of vertex colours; gradient of the map
 };
 
+// The K > 1 backward stalls 32 % of its samples on instruction fetch (82 KB of SASS, ncu r02h): its four scatters
+// share ONE out-of-line copy of the warp-aggregated reduction instead of four inlined ones.
+#ifndef TRB_BWD_SCATTER_INLINE
+__device__ __noinline__ void scatter_xyz3_outlined(unsigned leaders, bool any, bool aggregate, int key, float v0,
+                                                   float v1, float v2, float v3, float v4, float v5, float v6,
+                                                   float v7, float v8, float4* base, int i0, int i1, int i2) {
+  WarpGroups wg;
+  wg.leaders = leaders; wg.any = any; wg.aggregate = aggregate;
+  wg.runs = false; wg.run_head = false; wg.run_end = 0; wg.run_steps = 0;
+  const float v[9] = {v0, v1, v2, v3, v4, v5, v6, v7, v8};
+  warp_groups_add_xyz3(wg, key, v, base, i0, i1, i2);
+}
+#endif
+
 template <int SHADER, int LIGHT>
 __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool live, int pixi);
 template <bool K1, int SHADER, int LIGHT>
@@ -774,9 +788,14 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
       {
         const WarpGroups wg = warp_groups(key);  // one grouping for the three scatters of this layer
         auto scatter = [&](float4* base, F3 gv) {
+#ifndef TRB_BWD_SCATTER_INLINE
+          scatter_xyz3_outlined(wg.leaders, wg.any, wg.aggregate, key, b0 * gv.x, b0 * gv.y, b0 * gv.z, b1 * gv.x,
+                                b1 * gv.y, b1 * gv.z, b2 * gv.x, b2 * gv.y, b2 * gv.z, base, i0, i1, i2);
+#else
           const float v[9] = {b0 * gv.x, b0 * gv.y, b0 * gv.z, b1 * gv.x, b1 * gv.y, b1 * gv.z,
                               b2 * gv.x, b2 * gv.y, b2 * gv.z};
           warp_groups_add_xyz3(wg, key, v, base, i0, i1, i2);
+#endif
         };
         if (a.g_colors && a.uv.map == nullptr) scatter(a.g_colors, gT);
         if (LIGHT != TRB_LIGHT_AMBIENT) {
@@ -874,8 +893,15 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
       key = (int)f;
     }
     {
-      // K > 1 with Phong shading is bound by instruction issue, not by the reductions: no run merging there
+      // K > 1 with Phong shading is bound by instruction issue / fetch, not by the reductions: no run merging there
       const WarpGroups wg = warp_groups(key, !PHONG);
+#ifndef TRB_BWD_SCATTER_INLINE
+      if (PHONG) {
+        scatter_xyz3_outlined(wg.leaders, wg.any, wg.aggregate, key, gv[0], gv[1], gv[2], gv[3], gv[4], gv[5], gv[6],
+                              gv[7], gv[8], a.g_verts_ndc, i0, i1, i2);
+        continue;
+      }
+#endif
 #ifdef TRB_KN_STATS
       const unsigned bw_have = __ballot_sync(__activemask(), key >= 0);
       if ((tid & 31) == 0 && wg.any) {

@@ -158,15 +158,18 @@ class ViewTable:
                          max_vert_count=max(vert_count, default=0), total_ndc_verts=ndc_start,
                          total_faces_packed=total_faces, shared_mesh=shared_mesh)
 
-    def default_pair_capacity(self) -> int:
+    def default_pair_capacity(self, tiles_per_face: int = 8) -> int:
         total_fv = int(self.host[:, 1].sum())
-        return int(min(max(8 * total_fv, 1 << 16), 1 << 28))
+        return int(min(max(max(8, tiles_per_face) * total_fv, 1 << 16), 1 << 28))
 
-    def poll_capacity(self) -> int:
+    def poll_capacity(self, tiles_per_face: int = 8) -> int:
         """Non-blocking: grows the (tile, face) pair capacity when an earlier forward reported
-        that some tiles had to fall back to a whole-mesh scan.  Never synchronises."""
+        that some tiles had to fall back to a whole-mesh scan.  Never synchronises.  ``tiles_per_face``: how many
+        tiles the blur-inflated box of a small face touches (the first estimate; a 15-pixel blur band makes every
+        face of a fine mesh touch ~16 tiles, and a tile without room scans the whole mesh -- correct, but the
+        first render of the 1M-face sphere took 0.8 s that way)."""
         if self.pair_capacity == 0:
-            self.pair_capacity = self.default_pair_capacity()
+            self.pair_capacity = self.default_pair_capacity(tiles_per_face)
         if self._pending is not None and not torch.cuda.is_current_stream_capturing():
             stats, event = self._pending
             if event.query():
@@ -589,7 +592,9 @@ class _RenderFn(torch.autograd.Function):
         phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
         want_light_grad = int(view_params is not None and view_params.requires_grad)
         sparse = int(bool(spec.get("sparse", False)) and shader != _lib.SHADER_NONE)
-        cap = table.poll_capacity()
+        tile = 16 if K <= 24 else 8
+        blur_px = (spec["blur_radius"] ** 0.5) * min(H, W) / 2.0
+        cap = table.poll_capacity((int(2.0 * blur_px / tile) + 3) ** 2 if blur_px > 0 else 8)
         # The config record, the workspace sizes and the layout of the internal buffer depend only on static things:
         # memoised on the view table (one render call used to spend ~25 us of host time rebuilding them).
         plan_key = (shader, spec["light_kind"], tex_map is not None, H, W, K, spec["sigma"], spec["gamma"],

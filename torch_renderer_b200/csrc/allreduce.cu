@@ -84,7 +84,9 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
     }
   }
   const unsigned long long t1 = timed ? global_ns() : 0ull;
-  // ---- 2. collect the peers' values from my inbox, sum in rank order
+  // ---- 2. collect the peers' values from my inbox, sum in rank order.  All peers' words of an element are
+  // requested BEFORE the first one is looked at: the system-scope loads are then in flight together (polling the
+  // peers one after the other cost ~1.5 us each -- 11 us of wait at 8 GPUs with every contribution already there).
   const unsigned long long* mine = p.inbox[rank] + parity_off;
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
@@ -92,16 +94,26 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
     const long long i = (long long)blockIdx.x * kArChunk + u * 256 + threadIdx.x;
     float acc = 0.0f;
     bool ok = true;
-    for (int r = 0; r < world && ok; ++r) {
-      if (r == rank) { acc += v[u]; continue; }
-      const unsigned long long* src = mine + (size_t)r * capacity + i;
-      unsigned long long w = ld_relaxed_sys_b64(src);
-      unsigned spins = 0;
-      while ((unsigned)(w >> 32) != epoch) {
-        if (++spins > (1u << 26)) { atomicExch(error, 1); ok = false; break; }
-        w = ld_relaxed_sys_b64(src);
+    for (int r0 = 0; r0 < world && ok; r0 += 8) {   // peers in groups of 8 (one group on an 8-GPU box)
+      unsigned long long w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + j;
+        if (r < world && r != rank) w[j] = ld_relaxed_sys_b64(mine + (size_t)r * capacity + i);
       }
-      acc += __uint_as_float((unsigned)w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + j;
+        if (r >= world || !ok) continue;
+        if (r == rank) { acc += v[u]; continue; }
+        const unsigned long long* src = mine + (size_t)r * capacity + i;
+        unsigned spins = 0;
+        while ((unsigned)(w[j] >> 32) != epoch) {
+          if (++spins > (1u << 26)) { atomicExch(error, 1); ok = false; break; }
+          w[j] = ld_relaxed_sys_b64(src);
+        }
+        acc += __uint_as_float((unsigned)w[j]);
+      }
     }
     // a peer that never arrived: the partial sum is NOT written (the local gradient stays as it was and the
     // error flag tells the host -- PeerAllReduce.check())

@@ -40,7 +40,6 @@ __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
 #define TRB_K1_STRIP 8
 #endif
 constexpr int kStrip = TRB_K1_STRIP;  // tiles per CTA strip
-constexpr int kK1Queue = 2048;        // survivors of the edge tests queued per staging chunk (K = 1, blur 0)
 
 // Background of one tile whose face list is empty: a pure streaming store of -1 Fragments and
 // the background colour.
@@ -221,10 +220,6 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   __shared__ int s_rng[NT];        // c0 - tile_x0 | (r0 - tile_y0) << 4 | (bbox width - 1) << 8
   __shared__ int s_start[NT + 1];  // exclusive prefix sum of bbox pixel counts
   __shared__ int s_wtot[NT / 32];
-#ifndef TRB_K1_ONE_PHASE
-  __shared__ unsigned short s_queue[kK1Queue];  // (staged face << 8 | pixel) pairs that passed the edge tests
-  __shared__ int s_qn;
-#endif
 
   const trb_view vd = a.views[n];
   const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
@@ -238,9 +233,6 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
 
   __syncthreads();  // a CTA may rasterise several tiles: the previous one's epilogue still reads these arrays
   s_key[tid] = ~0ull;
-#ifndef TRB_K1_ONE_PHASE
-  if (tid == 0) s_qn = 0;
-#endif
   if (tid < TX) s_px[tid] = pix_to_ndc(W - 1 - (tile_x0 + tid), W, H);
   else if (tid < TX + TY) s_py[tid - TX] = pix_to_ndc(H - 1 - (tile_y0 + tid - TX), H, W);
   // last pixel column / row of the tile that exists in the image
@@ -347,13 +339,6 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
             if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
                             : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
               continue;
-#ifndef TRB_K1_ONE_PHASE
-            // TWO PHASES.  Only ~1 lane in 6 gets here (ncu r02h: 5-8 of 32 lanes active through the six IEEE
-            // divisions below, 36 % of the kernel's instructions): the survivor is queued as (staged face, pixel)
-            // and evaluated after the barrier with all lanes busy.  A full queue evaluates in place.
-            const int at = atomicAdd(&s_qn, 1);
-            if (at < kK1Queue) { s_queue[at] = (unsigned short)((fj << 8) | (lr * TX + lc)); continue; }
-#endif
           }
           float pz, b0, b1, b2;
           bool inside;
@@ -370,32 +355,6 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
         k = 0;
       }
     }
-#ifndef TRB_K1_ONE_PHASE
-    if (hard_edges) {
-      __syncthreads();
-      const int nq = min(s_qn, kK1Queue);
-      for (int i = tid; i < nq; i += NT) {
-        const unsigned e = s_queue[i];
-        const int fj = e >> 8, pixl = e & 255;
-        const float4 va = s_va[fj], vb = s_vb[fj];
-        const float2 vc = s_vc[fj];
-        FaceXYZ v;
-        v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
-        v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
-        const float qx = s_px[pixl & (TX - 1)], qy = s_py[pixl >> 4];
-        const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
-        const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
-        const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
-        float pz, b0, b1, b2;
-        bool inside;
-        if (!eval_from_edges(v, vc.y, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
-        if (!inside) continue;
-        atomicMin(&s_key[pixl], pack_key(pz, s_id[fj]));
-      }
-      __syncthreads();
-      if (tid == 0) s_qn = 0;
-    }
-#endif
     __syncthreads();  // staging arrays are rewritten by the next chunk
   }
   // ---- epilogue.  Only the covered pixels (a third of a busy tile of the cow batch) need the division-heavy

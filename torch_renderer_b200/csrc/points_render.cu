@@ -199,10 +199,17 @@ points_raster_binned_kernel(const float* __restrict__ points, const float* __res
   int qn = 0;
   float kth = 3.0e38f;
 
+  // NDC y extent of the two pixel rows this warp owns (y decreases with the row index)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int row0 = ty * kPtsTile + 2 * warp;
+  const float wy_hi = pix_to_ndc(H - 1 - min(row0, H - 1), H, W), wy_lo = pix_to_ndc(H - 1 - min(row0 + 1, H - 1), H, W);
+  __shared__ float s_rad[kPtsThreads];
+  __shared__ unsigned char s_wlist[kPtsThreads / 32][kPtsThreads];   // per warp: staged points that reach its rows
+
   for (int base = 0; base < nlist; base += kPtsThreads) {
     __syncthreads();   // the previous chunk's readers are done
     const int j = base + tid;
-    float r2 = -1.0f;   // empty slot: fails every d2 < r2 test
+    float r2 = -1.0f, rad = -1.0f;   // empty slot: fails every d2 < r2 test
     if (j < nlist) {
       const int lp = overflow ? j : ws.entries[(size_t)off + j];
       const size_t row = (size_t)(vd.face_start + lp);
@@ -210,13 +217,30 @@ points_raster_binned_kernel(const float* __restrict__ points, const float* __res
       const float r = __ldg(radius + row);
       s_x[tid] = __ldg(points + 3 * row); s_y[tid] = __ldg(points + 3 * row + 1); s_z[tid] = pz;
       s_id[tid] = vd.p2f_base + lp;
-      if (pz >= 0.0f) r2 = fmul(r, r);
+      if (pz >= 0.0f && r >= 0.0f) { r2 = fmul(r, r); rad = r * 1.0001f + 1e-6f; }
     }
-    s_r2[tid] = r2;
+    s_r2[tid] = r2; s_rad[tid] = rad;
     __syncthreads();
     const int m = min(kPtsThreads, nlist - base);
+    // Sub-tile culling: a disc of the reference's radius (0.003 NDC = 0.8 px at 512^2) reaches one or two of a tile's
+    // sixteen rows, so each warp first compacts the staged points that can reach ITS two rows (one ballot per 32
+    // points) and its pixels test only those -- 280 staged points per tile became ~50 per warp.
+    int wn = 0;
+    for (int q0 = 0; q0 < m; q0 += 32) {
+      const int q = q0 + lane;
+      bool ov = false;
+      if (q < m) {
+        const float rq = s_rad[q], yq = s_y[q];
+        ov = rq >= 0.0f && yq + rq >= wy_lo && yq - rq <= wy_hi;
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, ov);
+      if (ov) s_wlist[warp][wn + __popc(b & ((1u << lane) - 1u))] = (unsigned char)q;
+      wn += __popc(b);
+    }
+    __syncwarp();
     if (live) {
-      for (int q = 0; q < m; ++q) {
+      for (int jj = 0; jj < wn; ++jj) {
+        const int q = s_wlist[warp][jj];
         const float dx = fsub(xf, s_x[q]), dy = fsub(yf, s_y[q]);
         const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
         if (!(d2 < s_r2[q])) continue;

@@ -39,6 +39,15 @@ __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
 #ifndef TRB_K1_STRIP
 #define TRB_K1_STRIP 8
 #endif
+// Diagnostic (TRB_KN_STATS builds): clock64 cycles of thread 0 spent in the phases of a busy K=1 tile, summed over
+// tiles: [0] tiles, [1] header + staging (to the first barrier), [2] prefix sums, [3] (face, pixel) items,
+// [4] covered-pixel compaction incl. the list atomic, [5] finishing the covered pixels (exact sample + shading)
+#ifdef TRB_KN_STATS
+__device__ unsigned long long g_k1_phase[8];
+#define K1_T(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_k1_phase[i], (unsigned long long)(now_ - k1_t_)); k1_t_ = now_; } } while (0)
+#else
+#define K1_T(i) ((void)0)
+#endif
 constexpr int kStrip = TRB_K1_STRIP;  // tiles per CTA strip
 
 // Background of one tile whose face list is empty: a pure streaming store of -1 Fragments and
@@ -231,6 +240,10 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   const bool overflow = off < 0;
   if (overflow) nlist = vd.face_count;
 
+#ifdef TRB_KN_STATS
+  long long k1_t_ = clock64();
+  if (tid == 0) atomicAdd(&g_k1_phase[0], 1ull);
+#endif
   __syncthreads();  // a CTA may rasterise several tiles: the previous one's epilogue still reads these arrays
   s_key[tid] = ~0ull;
   if (tid < TX) s_px[tid] = pix_to_ndc(W - 1 - (tile_x0 + tid), W, H);
@@ -275,6 +288,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     }
     if (lane == 31) s_wtot[warp] = incl;
     __syncthreads();  // also publishes s_key / s_px / s_py on the first pass and the staging arrays
+    K1_T(1);
     int wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < NT / 32; ++w) {
@@ -285,6 +299,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     s_start[tid] = wbase + incl - npx;
     if (tid == 0) s_start[NT] = total;
     __syncthreads();
+    K1_T(2);
 
     // ---- deal the (face, pixel) pairs out in equal contiguous runs
     const int m = min(NT, nlist - base);  // staged faces
@@ -356,6 +371,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
       }
     }
     __syncthreads();  // staging arrays are rewritten by the next chunk
+    K1_T(3);
   }
   // ---- epilogue.  Only the covered pixels (a third of a busy tile of the cow batch) need the division-heavy
   // sample evaluation and the shading: they are compacted over the CTA, so that ceil(covered / 32) warps run that
@@ -396,6 +412,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     }
   }
   __syncthreads();
+  K1_T(4);
   if (tid >= s_nhit) return;
   const int hp = s_hitlist[tid];           // pixel of the tile this thread finishes
   const int hx = hp & (TX - 1), hy = hp >> 4;
@@ -438,6 +455,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     }
   }
   st_cs(reinterpret_cast<float4*>(a.images) + hpix, out);
+  K1_T(5);
 }
 
 // ---- fused backward ----------------------------------------------------------------------------
@@ -1248,6 +1266,12 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
 }
 
 #ifdef TRB_KN_STATS
+extern "C" int trb_debug_k1_phases(unsigned long long* host_out) {
+  unsigned long long zero[8] = {0};
+  if (cudaMemcpyFromSymbol(host_out, trb::g_k1_phase, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  if (cudaMemcpyToSymbol(trb::g_k1_phase, zero, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  return TRB_OK;
+}
 // Copies the backward scatter counters to `host_out[8]` and clears them (diagnostic builds only; synchronises).
 extern "C" int trb_debug_bw_stats(unsigned long long* host_out) {
   unsigned long long zero[8] = {0};

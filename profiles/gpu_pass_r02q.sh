@@ -1,0 +1,15 @@
+tag=r02q
+out=gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > $out/tests_$tag.log 2>&1; echo "pytest rc=$?" >> $out/tests_$tag.log
+tail -3 $out/tests_$tag.log
+for lib in base prev; do
+  p=$PWD/torch_renderer_b200/libtrb_$lib.so; [ $lib = base ] && p=$PWD/torch_renderer_b200/libtrb.so
+  for c in C3 C3cow; do
+    TRB_LIB_PATH=$p timeout 300 python profiles/run_config.py $c 20 > $out/ab_${lib}_${c}_$tag.json 2>> $out/ab_$tag.err
+    python -c "
+import json
+try:
+    d = json.load(open('$out/ab_${lib}_${c}_$tag.json')); print('$lib $c', 'step', d['ms_per_step_device'], 'fine', d['fine_kernel_ms'], 'bwd', d['backward_kernel_ms'])
+except Exception as e: print('$lib $c failed', e)"
+  done
+done

@@ -30,5 +30,7 @@ names = ["tiles", "header+staging", "prefix sums", "items", "hit compaction + li
 out = {"busy_tiles": tiles}
 for i in range(1, 6):
     out[names[i] + " (cycles/tile)"] = round(int(buf[i]) / tiles, 1)
+out["(face, pixel) items per tile"] = round(int(buf[6]) / tiles, 1)
+out["staged faces per tile"] = round(int(buf[7]) / tiles, 1)
 out["sum (cycles/tile)"] = round(sum(int(buf[i]) for i in range(1, 6)) / tiles, 1)
 print(json.dumps(out, indent=1))

@@ -803,6 +803,7 @@ def test_forward_is_bit_reproducible_under_repetition(K, blur):
     ("soft_phong", 1, 0.0, (64, 64)), ("soft_phong", 1, 0.0, (45, 61)), ("hard_phong", 1, 0.0, (96, 96)),
     ("soft_silhouette", 1, 0.0, (64, 64)), ("soft_phong", 8, 9.21024e-4, (128, 128)), ("soft_phong", 5, 2e-3, (45, 61)),
     ("soft_silhouette", 50, 9.21024e-4, (96, 96)), ("soft_silhouette", 30, 2e-3, (33, 47)), ("hard_phong", 4, 0.0, (64, 64)),
+    ("soft_silhouette", 10, 9.21024e-4, (128, 128)), ("soft_silhouette", 3, 1e-3, (45, 61)),
 ])
 def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, size):
     """``MeshRenderer`` returns the image only, so its kernels write Fragments for covered pixels only

@@ -405,3 +405,33 @@ def test_memoised_parameter_blocks_see_parameters_and_grad_flags():
     T = torch.tensor([[0.0, 0.0, 5.0]])
     cams.get_camera_center(R=R, T=T)
     assert cams.R is R and cams.T is T
+
+
+def test_round2_host_pieces_without_gpu():
+    """capture_step needs CUDA and says so; the bench workload builders import without the oracle and build the
+    BASELINE configs[4] mesh at the stated size; the C5-at-spec sharding covers every view exactly once."""
+    import importlib
+    import sys as _sys
+    from torch_renderer_b200.parallel import chunk_views, shard_views
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            trb.capture_step(lambda: None)
+    assert issubclass(trb.NearPlaneCrossed, RuntimeError)
+    _sys.path.insert(0, ROOT)
+    wl = importlib.import_module("bench_workloads")
+    assert "oracle" not in wl.__dict__ and set(wl.BUILDERS) >= {"C1", "C3", "C3cow", "C4", "C5", "pose_step", "clipped"}
+    v, f = wl.grid_sphere(11, 20)
+    assert f.shape[0] == 2 * 11 * 20 - 2 * 20 and v.shape[0] == (11 - 1) * 20 + 2 and int(f.max()) == v.shape[0] - 1
+    # 501 x 1000 quads -> exactly 1,000,000 triangles and 500,002 vertices (the C5 mesh), by the same closed form
+    assert 2 * 501 * 1000 - 2 * 1000 == 1_000_000 and (501 - 1) * 1000 + 2 == 500_002
+    assert wl.bview(8, 1024, 1024, 500_002, 1_000_000) == 599_316_672
+    seen = []
+    for r in range(8):
+        lo, hi = shard_views(1024, r, 8)
+        for s0, s1 in chunk_views(hi - lo, 32):
+            seen.extend(range(lo + s0, lo + s1))
+    assert seen == list(range(1024))
+    # tile-list capacity estimate of the point rasteriser: a scalar radius bounds the tiles a disc can reach
+    from torch_renderer_b200 import ops
+    import inspect
+    assert "max_radius" in inspect.signature(ops.rasterize_points_ndc).parameters

@@ -300,6 +300,9 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     if (tid == 0) s_start[NT] = total;
     __syncthreads();
     K1_T(2);
+#ifdef TRB_KN_STATS
+    if (tid == 0) { atomicAdd(&g_k1_phase[6], (unsigned long long)total); atomicAdd(&g_k1_phase[7], (unsigned long long)min(NT, nlist - base)); }
+#endif
 
     // ---- deal the (face, pixel) pairs out in equal contiguous runs
     const int m = min(NT, nlist - base);  // staged faces

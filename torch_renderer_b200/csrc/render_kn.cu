@@ -27,6 +27,9 @@ namespace trb {
 // 40.65 M insertions either way: that mesh's per-vertex radial noise makes every face span a depth range far wider
 // than the spacing of its neighbours' keys, so the order of min-vertex depths is not the order of sample depths.)
 constexpr int kBuckets = 256;
+// bit 31 of a top-K list entry's face id: the sample lies inside its face (decided during the walk)
+constexpr int kFaceMask = 0x7fffffff;
+constexpr int kInsideBit = (int)0x80000000u;
 
 // Diagnostic counters of the K > 1 walk (build with TRB_EXTRA_NVCC_FLAGS=-DTRB_KN_STATS; read with
 // trb_debug_kn_stats).  Not compiled into the product library.
@@ -401,7 +404,7 @@ render_fine_kn_kernel(const FineArgs a) {
             if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, c0, c1, c2, inside)) continue;
           }
           // the depth is known before the (three more divisions of the) distance: losers leave here
-          if (cnt == K && !cand_less(pz, f, kth, kf[(K - 1) * NT + tid])) continue;
+          if (cnt == K && !cand_less(pz, f, kth, kf[(K - 1) * NT + tid] & kFaceMask)) continue;
           KN_STAT(9, 1);
           if (!inside) {
             if (hard_edges) continue;
@@ -409,13 +412,13 @@ render_fine_kn_kernel(const FineArgs a) {
           }
           KN_STAT(10, 1);
           int pos = cnt < K ? cnt : K - 1;
-          while (pos > 0 && cand_less(pz, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid])) {
+          while (pos > 0 && cand_less(pz, f, kz[(pos - 1) * NT + tid], kf[(pos - 1) * NT + tid] & kFaceMask)) {
             kz[pos * NT + tid] = kz[(pos - 1) * NT + tid];
             kf[pos * NT + tid] = kf[(pos - 1) * NT + tid];
             --pos;
             KN_STAT(11, 1);
           }
-          kz[pos * NT + tid] = pz; kf[pos * NT + tid] = f;
+          kz[pos * NT + tid] = pz; kf[pos * NT + tid] = inside ? (f | kInsideBit) : f;
           if (cnt < K) ++cnt;
           if (cnt == K) kth = kz[(K - 1) * NT + tid];
         }
@@ -478,11 +481,15 @@ render_fine_kn_kernel(const FineArgs a) {
     zrange = vp.zfar - vp.znear;
     if (total > 0) {
       float z_first = cntA > 0 ? kz[colA] : 3.0e38f;
-      if (SPLIT == 2 && cntB > 0 && (cntA == 0 || cand_less(kz[colB], kf[colB], kz[colA], kf[colA]))) z_first = kz[colB];
+      if (SPLIT == 2 && cntB > 0 && (cntA == 0 || cand_less(kz[colB], kf[colB] & kFaceMask, kz[colA], kf[colA] & kFaceMask)))
+        z_first = kz[colB];
       zmax = fmaxf(eps, (vp.zfar - z_first) / zrange);
     }
   }
   const int rot = p >> ROT;
+  // sparse Fragments of a soft-silhouette render: zbuf and barycentrics are never read again (sigmoid_alpha_blend and
+  // its backward use the distances only), so the epilogue skips the nine IEEE divisions per layer that produce them
+  const bool dist_only = sparse && SHADER == TRB_SHADER_SOFT_SILHOUETTE;
   int ia = 0, ib = 0;   // merge cursors
   for (int k0 = 0; k0 < k_end; k0 += KG) {
     const int kg = min(KG, k_end - k0);
@@ -494,13 +501,21 @@ render_fine_kn_kernel(const FineArgs a) {
       if (k < total) {
         bool take_a = true;
         if (SPLIT == 2)
-          take_a = ib >= cntB || (ia < cntA && cand_less(kz[ia * NT + colA], kf[ia * NT + colA],
-                                                         kz[ib * NT + colB], kf[ib * NT + colB]));
-        const int f = take_a ? kf[ia * NT + colA] : kf[ib * NT + colB];
+          take_a = ib >= cntB || (ia < cntA && cand_less(kz[ia * NT + colA], kf[ia * NT + colA] & kFaceMask,
+                                                         kz[ib * NT + colB], kf[ib * NT + colB] & kFaceMask));
+        const int f_raw = take_a ? kf[ia * NT + colA] : kf[ib * NT + colB];
+        const int f = f_raw & kFaceMask;
         if (take_a) ++ia; else ++ib;
         if (mine) {
           const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
-          eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
+          if (dist_only) {
+            // image-only soft silhouette: the blend and the backward read the signed distance and nothing else;
+            // `inside` was decided when the candidate entered the list (same arithmetic as eval_pixel_face_rt)
+            const float d2 = triangle_d2(v, px, py);
+            s.d = (f_raw & kInsideBit) ? -d2 : d2;
+          } else {
+            eval_pixel_face_rt(v, px, py, persp, clip, blur, s);
+          }
           pf = (long long)vd.p2f_base + f;
           if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
             alpha *= 1.0f - sigmoidf(-s.d / a.sigma);
@@ -532,11 +547,11 @@ render_fine_kn_kernel(const FineArgs a) {
       if (kk < kg && k0 + kk < s_wr[pp]) {
         const size_t g = ((size_t)(n * H + gy) * W + gx) * K + k0 + kk;
         st_cs(a.p2f + g, o_p2f[idx]);
-        st_cs(a.zbuf + g, o_z[idx]);
+        if (!dist_only) st_cs(a.zbuf + g, o_z[idx]);
         st_cs(a.dists + g, o_d[idx]);
       }
     }
-    for (int idx = tid; idx < NP * KG * 3; idx += NT) {
+    for (int idx = tid; idx < (dist_only ? 0 : NP * KG * 3); idx += NT) {
       const int e = idx / 3, c = idx - 3 * e;
       const int pp = e >> LOGKG;
       const int kk = ((e & (KG - 1)) - (pp >> ROT)) & (KG - 1);

@@ -768,7 +768,8 @@ class _RasterizePointsFn(torch.autograd.Function):
         # per-tile point lists: every point enters the tiles its disc can reach (a known scalar radius bounds that
         # number; per-point radii get 8 entries per point -- tiles that do not fit scan the whole cloud instead)
         total_points = points_ndc.shape[0]
-        capacity = int(min(total_points * max(int(tiles_per_point), 1) + 1024, (1 << 31) - 1))
+        # (capped at 64 M entries = 256 MB: huge discs then overflow into the whole-cloud scan, which is what they need)
+        capacity = int(min(total_points * max(int(tiles_per_point), 1) + 1024, 1 << 26))
         nbytes = ctypes.c_size_t(0)
         check(L.trb_points_raster_workspace_bytes(N, H, W, capacity, ctypes.byref(nbytes)), "rasterize_points")
         ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)

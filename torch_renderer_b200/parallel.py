@@ -73,6 +73,7 @@ class PeerAllReduce:
         self.peer_inbox = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         self.epochs = torch.zeros(_lib.lib().trb_allreduce_grid(self.capacity), dtype=torch.int32, device=device)
+        self.calls = 0     # allreduce_shared_grads reads the error flag every _CHECK_EVERY calls
 
     def __call__(self, grads: Sequence[torch.Tensor]) -> None:
         ctypes, _lib = self._ctypes, self._lib
@@ -119,7 +120,6 @@ def _get_peer_allreduce(n_floats: int, device: torch.device, group):
         if int(ok.item()) == 0:
             _peer_allreduce[key] = False
             return None
-        cur.calls = 0
         _peer_allreduce[key] = cur
     return cur
 

@@ -849,4 +849,4 @@ def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, 
         assert torch.equal(out[True][0][..., 3], out[False][0][..., 3])
         assert (out[True][0] - out[False][0]).abs().max() < 1e-5
     for a, b in zip(out[True][1:], out[False][1:]):
-        assert rel_l2(a, b) < 1e-5
+        assert rel_l2(a, b) < 1e-4      # two runs of the same kernels: atomics order + the normals' ulps through the blend

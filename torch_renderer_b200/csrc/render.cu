@@ -712,6 +712,8 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   if (PHONG) vp = load_view_params(a.view_params, n);
   const float eps = 1e-10f;
   const float zrange = PHONG ? vp.zfar - vp.znear : 1.0f;
+  // fast-math throughout: gradients are held to 1e-3 against fp64; the forward image came from the precise kernels
+  const float inv_zrange = __frcp_rn(zrange), inv_sigma = __frcp_rn(a.sigma), inv_gamma = __frcp_rn(a.gamma);
 
   // ---- pass A: blend bookkeeping (no colours yet)
   float zmax = eps; int kmax = -1;
@@ -719,23 +721,23 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
   float wsum = 0.0f, delta = 0.0f, den = 1.0f;
   if (SOFT || SIL) {
     for (int k = 0; k < nk; ++k) {
-      const float q = 1.0f - sigmoidf(-a.dists[s0 + k] / a.sigma);
+      const float q = 1.0f - sigmoid_fast(-a.dists[s0 + k] * inv_sigma);
       if (q == 0.0f) ++zeros; else prod_nz *= q;
       if (SOFT) {
-        const float zinv = (vp.zfar - a.zbuf[s0 + k]) / zrange;
+        const float zinv = (vp.zfar - a.zbuf[s0 + k]) * inv_zrange;
         if (zinv > zmax) { zmax = zinv; kmax = k; }
       }
     }
   }
   if (SOFT) {
     for (int k = 0; k < nk; ++k) {
-      const float zinv = (vp.zfar - a.zbuf[s0 + k]) / zrange;
-      wsum += sigmoidf(-a.dists[s0 + k] / a.sigma) * expf((zinv - zmax) / a.gamma);
+      const float zinv = (vp.zfar - a.zbuf[s0 + k]) * inv_zrange;
+      wsum += sigmoid_fast(-a.dists[s0 + k] * inv_sigma) * __expf((zinv - zmax) * inv_gamma);
     }
-    delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+    delta = fmaxf(__expf((eps - zmax) * inv_gamma), eps);
     den = wsum + delta;
   }
-  const float inv_den = 1.0f / den;
+  const float inv_den = __frcp_rn(den);
 
   // ---- pass B: lighting model forward + backward, vertex-attribute scatters
   const int nshade = (SHADER == TRB_SHADER_HARD_PHONG) ? min(nk, 1) : (PHONG ? nk : 0);
@@ -777,19 +779,19 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
           nr = interp3(b0, b1, b2, N0, N1, N2);
         }
         Lit lit;
-        const F3 c = phong_color<LIGHT>(vp, P, nr, tex, lit);
+        const F3 c = phong_color<LIGHT, true>(vp, P, nr, tex, lit);
         float wn = 1.0f;
         float gdotc = 0.0f;
         if (SOFT) {
-          const float zinv = (vp.zfar - a.zbuf[s]) / zrange;
-          const float w = sigmoidf(-a.dists[s] / a.sigma) * expf((zinv - zmax) / a.gamma);
+          const float zinv = (vp.zfar - a.zbuf[s]) * inv_zrange;
+          const float w = sigmoid_fast(-a.dists[s] * inv_sigma) * __expf((zinv - zmax) * inv_gamma);
           acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z;
           gdotc = g.x * c.x + g.y * c.y + g.z * c.z;
           wn = w * inv_den;
         }
         const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
         F3 g_lv, g_cam;
-        phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
+        phong_color_bwd<LIGHT, true>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
         g_lv_acc.x += g_lv.x; g_lv_acc.y += g_lv.y; g_lv_acc.z += g_lv.z;
         g_cam_acc.x += g_cam.x; g_cam_acc.y += g_cam.y; g_cam_acc.z += g_cam.z;
         float gb0, gb1, gb2;
@@ -853,8 +855,8 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
                     (acc.z + delta * a.bg2) * inv_den};
     g_rgb = g.x * rgb.x + g.y * rgb.y + g.z * rgb.z;
     const float g_delta = ((g.x * a.bg0 + g.y * a.bg1 + g.z * a.bg2) - g_rgb) * inv_den;
-    const bool delta_clamped = !(expf((eps - zmax) / a.gamma) > eps);
-    g_zmax = delta_clamped ? 0.0f : -g_delta * delta / a.gamma;
+    const bool delta_clamped = !(__expf((eps - zmax) * inv_gamma) > eps);
+    g_zmax = delta_clamped ? 0.0f : -g_delta * delta * inv_gamma;
   }
   const int nloop = __reduce_max_sync(0xffffffffu, nk);
   for (int k = 0; k <= nloop; ++k) {
@@ -872,24 +874,24 @@ __device__ __forceinline__ void render_backward_pixel(const BwdArgs& a, bool liv
       const long long f = a.p2f[s];
       float gz = 0.0f, gd = 0.0f, gb0 = 0.0f, gb1 = 0.0f, gb2 = 0.0f;
       if (tail) {
-        gz = -g_zmax / zrange;
+        gz = -g_zmax * inv_zrange;
       } else {
         if (SOFT || SIL) {
-          const float p = sigmoidf(-a.dists[s] / a.sigma);
+          const float p = sigmoid_fast(-a.dists[s] * inv_sigma);
           const float q = 1.0f - p;
-          const float others = zeros == 0 ? prod_nz / q : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
+          const float others = zeros == 0 ? prod_nz * __frcp_rn(q) : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
           float g_p = g.w * others;
           if (SOFT) {
-            const float zinv = (vp.zfar - a.zbuf[s]) / zrange;
-            const float E = expf((zinv - zmax) / a.gamma);
+            const float zinv = (vp.zfar - a.zbuf[s]) * inv_zrange;
+            const float E = __expf((zinv - zmax) * inv_gamma);
             const float4 pk = K1 ? park1 : s_park[k * NT + tid];
             const float g_w = (pk.w - g_rgb) * inv_den;
             g_p += g_w * E;
-            const float g_zinv = g_w * (p * E) / a.gamma;
+            const float g_zinv = g_w * (p * E) * inv_gamma;
             g_zmax -= g_zinv;
-            gz = -g_zinv / zrange;
+            gz = -g_zinv * inv_zrange;
           }
-          gd = g_p * p * q * (-1.0f / a.sigma);
+          gd = g_p * p * q * (-inv_sigma);
         }
         if (PHONG && k < nshade) {
           const float4 pk = K1 ? park1 : s_park[k * NT + tid];
@@ -971,7 +973,7 @@ silhouette_backward_kn_kernel(const BwdArgs a) {
     int zeros = 0;
     float prod_nz = 1.0f;
     for (int k = sub; k < nk; k += 4) {
-      const float q = 1.0f - sigmoidf(-a.dists[s0 + k] * inv_sigma);
+      const float q = 1.0f - sigmoid_fast(-a.dists[s0 + k] * inv_sigma);
       if (q == 0.0f) ++zeros; else prod_nz *= q;
     }
     s_prod[sub][lane] = prod_nz; s_zero[sub][lane] = zeros;
@@ -993,8 +995,8 @@ silhouette_backward_kn_kernel(const BwdArgs a) {
         const size_t s = s0 + sub + 4 * r;
         const long long f = a.p2f[s];
         const float d = a.dists[s];
-        const float p = sigmoidf(-d * inv_sigma), q = 1.0f - p;
-        const float others = zeros == 0 ? prod_nz / q : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
+        const float p = sigmoid_fast(-d * inv_sigma), q = 1.0f - p;
+        const float others = zeros == 0 ? prod_nz * __frcp_rn(q) : (zeros == 1 && q == 0.0f ? prod_nz : 0.0f);
         float gd = gw * others * p * q * (-inv_sigma);
         float gz = 0.0f, gb0 = 0.0f, gb1 = 0.0f, gb2 = 0.0f;
         if (a.g_zbuf) gz = a.g_zbuf[s];

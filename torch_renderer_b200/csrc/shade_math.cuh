@@ -59,7 +59,9 @@ struct Lit {
 };
 
 // colour = (amb + dif*relu(cos)) * tex + spec * a^shin        (A6)
-template <int LIGHT>
+// FAST (backward passes only: the image was produced by the precise version, gradients are held to 1e-3): the
+// specular power goes through the SFU (__powf) instead of the ~70-instruction powf.
+template <int LIGHT, bool FAST = false>
 __device__ __forceinline__ F3 phong_color(const ViewParams& vp, F3 P, F3 nrm, F3 tex, Lit& s) {
   if (LIGHT == TRB_LIGHT_AMBIENT) return {vp.amb[0] * tex.x, vp.amb[1] * tex.y, vp.amb[2] * tex.z};
   s.nh = normalize3(nrm, s.nlen, s.nclamp);
@@ -75,14 +77,14 @@ __device__ __forceinline__ F3 phong_color(const ViewParams& vp, F3 P, F3 nrm, F3
             -s.lh.z + 2.0f * s.cosv * s.nh.z};
   s.dotvr = dot3(s.vh, s.refl);
   s.a = (s.cosv > 0.0f) ? fmaxf(s.dotvr, 0.0f) : 0.0f;
-  s.pw = (s.a > 0.0f) ? powf(s.a, vp.shin) : (vp.shin == 0.0f ? 1.0f : 0.0f);
+  s.pw = (s.a > 0.0f) ? (FAST ? __powf(s.a, vp.shin) : powf(s.a, vp.shin)) : (vp.shin == 0.0f ? 1.0f : 0.0f);
   return {(vp.amb[0] + vp.dif[0] * s.diffuse_s) * tex.x + vp.spec[0] * s.pw,
           (vp.amb[1] + vp.dif[1] * s.diffuse_s) * tex.y + vp.spec[1] * s.pw,
           (vp.amb[2] + vp.dif[2] * s.diffuse_s) * tex.z + vp.spec[2] * s.pw};
 }
 
 // Backward of phong_color: g = dL/dcolour -> g_tex, g_P, g_nrm, g_light_vec, g_cam.
-template <int LIGHT>
+template <int LIGHT, bool FAST = false>
 __device__ __forceinline__ void phong_color_bwd(const ViewParams& vp, F3 tex, const Lit& s, F3 g,
                                                 F3& g_tex, F3& g_P, F3& g_nrm, F3& g_lv, F3& g_cam) {
   g_P = {0, 0, 0}; g_nrm = {0, 0, 0}; g_lv = {0, 0, 0}; g_cam = {0, 0, 0};
@@ -96,7 +98,9 @@ __device__ __forceinline__ void phong_color_bwd(const ViewParams& vp, F3 tex, co
   float g_cos = (s.cosv > 0.0f) ? g_diff : 0.0f;
   const float g_pw = g.x * vp.spec[0] + g.y * vp.spec[1] + g.z * vp.spec[2];
   float g_dot = 0.0f;
-  if (s.a > 0.0f && s.dotvr > 0.0f && s.cosv > 0.0f) g_dot = g_pw * vp.shin * powf(s.a, vp.shin - 1.0f);
+  // d a^shin / d a = shin a^(shin-1); FAST: = shin * (a^shin) / a with the forward's power (no second pow)
+  if (s.a > 0.0f && s.dotvr > 0.0f && s.cosv > 0.0f)
+    g_dot = g_pw * vp.shin * (FAST ? s.pw * __frcp_rn(s.a) : powf(s.a, vp.shin - 1.0f));
   F3 g_vh = {g_dot * s.refl.x, g_dot * s.refl.y, g_dot * s.refl.z};
   const F3 g_refl = {g_dot * s.vh.x, g_dot * s.vh.y, g_dot * s.vh.z};
   F3 g_lh = {-g_refl.x, -g_refl.y, -g_refl.z};
@@ -196,6 +200,8 @@ __device__ __forceinline__ F2 ld2(const float* __restrict__ p, int i) {
 }
 
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+// backward passes: SFU exponential and reciprocal (~2e-7 relative)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 struct FaceIds {
   int i0, i1, i2;

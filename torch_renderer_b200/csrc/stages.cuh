@@ -226,6 +226,39 @@ __device__ __forceinline__ void bin_face(const float* __restrict__ verts, const 
   const int cnt = nx * ny;
   const int steps = __reduce_max_sync(0xffffffffu, cnt);  // warp-uniform trip count
   const int tbase = n * tg.tiles_x * tg.tiles_y;
+  // Neighbouring faces of a mesh cover nearly the same tiles, but lane by lane they reach a given tile at different
+  // steps of their own row-major walk, so grouping lanes per step (below) merges few of them.  When the UNION of the
+  // warp's tile boxes is small the warp walks that union instead: one ballot and ONE atomic per tile for all lanes
+  // that cover it (1M-face sphere with a 15-pixel blur band: ~16 tiles per face, ~25 in the union of 32 faces).
+  {
+    const int ux0 = __reduce_min_sync(0xffffffffu, cnt > 0 ? tx0 : (1 << 30));
+    const int ux1 = __reduce_max_sync(0xffffffffu, cnt > 0 ? tx0 + nx - 1 : -1);
+    const int uy0 = __reduce_min_sync(0xffffffffu, cnt > 0 ? ty0 : (1 << 30));
+    const int uy1 = __reduce_max_sync(0xffffffffu, cnt > 0 ? ty0 + ny - 1 : -1);
+    if (ux1 < ux0) return;   // no lane has a tile
+    const int uarea = (ux1 - ux0 + 1) * (uy1 - uy0 + 1);
+    if (uarea <= 2 * steps + 8) {
+      for (int ty = uy0; ty <= uy1; ++ty)
+        for (int tx = ux0; tx <= ux1; ++tx) {
+          const bool in = cnt > 0 && tx >= tx0 && tx < tx0 + nx && ty >= ty0 && ty < ty0 + ny;
+          const unsigned b = __ballot_sync(0xffffffffu, in);
+          if (b == 0) continue;
+          const int t = tbase + ty * tg.tiles_x + tx;
+          const int leader = __ffs(b) - 1, npeers = __popc(b);
+          if (!FILL) {
+            if (lane == leader) atomicAdd(tile_count + t, npeers);
+          } else {
+            const int off = tile_offset[t];
+            int base = 0;
+            if (lane == leader && off >= 0) base = atomicAdd(tile_fill + t, npeers);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (in && off >= 0)
+              pairs[(size_t)off + base + __popc(b & ((1u << lane) - 1u))] = make_int2(lf, __float_as_int(zmin));
+          }
+        }
+      return;
+    }
+  }
   int ix = 0, iy = 0;
   for (int i = 0; i < steps; ++i) {
     const bool have = i < cnt;

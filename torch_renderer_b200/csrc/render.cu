@@ -515,11 +515,19 @@ render_backward_kernel(const BwdArgs a) {
   const int count = a.hit_pixels[0];
   const int count_up = (count + 31) & ~31;
   const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count_up; i += stride) {
+  // the next iteration's list entry is requested before this one's pixel is processed (one of the four dependent
+  // round trips of an iteration: list entry -> Fragments -> face -> vertices)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int pixi = i < count ? a.hit_pixels[1 + i] : 0;
+  int nk = (!K1 && i < count) ? a.hit_counts[i] : 0;
+  for (; i < count_up; i += stride) {
     const bool live = i < count;
-    const int pixi = live ? a.hit_pixels[1 + i] : 0;
+    const int inext = i + stride;
+    const int pixi_next = inext < count ? a.hit_pixels[1 + inext] : 0;
+    const int nk_next = (!K1 && inext < count) ? a.hit_counts[inext] : 0;
     if (K1) render_backward_pixel_k1<SHADER, LIGHT>(a, live, pixi);
-    else render_backward_pixel<false, SHADER, LIGHT>(a, live, pixi, live ? a.hit_counts[i] : 0, s_park);
+    else render_backward_pixel<false, SHADER, LIGHT>(a, live, pixi, nk, s_park);
+    pixi = pixi_next; nk = nk_next;
   }
 }
 
@@ -594,7 +602,7 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
       const F3 P = interp3(b0, b1, b2, X0, X1, X2);
       const F3 nr = interp3(b0, b1, b2, N0, N1, N2);
       Lit lit;
-      const F3 c = phong_color<LIGHT>(vp, P, nr, tex, lit);
+      const F3 c = phong_color<LIGHT, true>(vp, P, nr, tex, lit);
       float wn = 1.0f;
       if (SOFT) {
         const float eps = 1e-10f;
@@ -622,7 +630,7 @@ __device__ __forceinline__ void render_backward_pixel_k1(const BwdArgs& a, bool 
       }
       const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
       F3 gT, gP, gN, g_lv, g_cam;
-      phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
+      phong_color_bwd<LIGHT, true>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
       if (use_uv) {
         const float gu = dot3(gT, dtu), gvv = dot3(gT, dtv);
         gb0 += gu * t0.x + gvv * t0.y; gb1 += gu * t1.x + gvv * t1.y; gb2 += gu * t2.x + gvv * t2.y;

@@ -207,7 +207,7 @@ shade_backward_kernel(trb_shade_config cfg, const trb_view* __restrict__ views,
         tex = {texels[s * 3], texels[s * 3 + 1], texels[s * 3 + 2]};
       }
       Lit lit;
-      const F3 c = phong_color<LIGHT>(vp, P, nr, tex, lit);
+      const F3 c = phong_color<LIGHT, true>(vp, P, nr, tex, lit);
       float w = 1.0f;  // d rgb / d colour_k
       if (!hard) {
         const float zinv = (vp.zfar - zbuf[s]) / zrange;
@@ -218,7 +218,7 @@ shade_backward_kernel(trb_shade_config cfg, const trb_view* __restrict__ views,
       const float wn = hard ? 1.0f : w * inv_den;
       const F3 gc = {g.x * wn, g.y * wn, g.z * wn};
       F3 g_lv, g_cam;
-      phong_color_bwd<LIGHT>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
+      phong_color_bwd<LIGHT, true>(vp, tex, lit, gc, gT, gP, gN, g_lv, g_cam);
       g_lv_acc.x += g_lv.x; g_lv_acc.y += g_lv.y; g_lv_acc.z += g_lv.z;
       g_cam_acc.x += g_cam.x; g_cam_acc.y += g_cam.y; g_cam_acc.z += g_cam.z;
       if (grad_bary) {

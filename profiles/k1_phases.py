@@ -18,7 +18,7 @@ rend = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image
                         trb.SoftPhongShader(device=dev, cameras=cams, lights=trb.PointLights(device=dev, location=[[0, 0, -3.0]])))
 trb.set_near_plane_clipping("off")
 L = _lib.lib()
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 16)()
 for _ in range(3):
     rend(mesh)
 torch.cuda.synchronize()
@@ -32,5 +32,7 @@ for i in range(1, 6):
     out[names[i] + " (cycles/tile)"] = round(int(buf[i]) / tiles, 1)
 out["(face, pixel) items per tile"] = round(int(buf[6]) / tiles, 1)
 out["staged faces per tile"] = round(int(buf[7]) / tiles, 1)
+out["items: slowest thread (cycles/tile)"] = round(int(buf[8]) / tiles, 1)
+out["items: mean thread (cycles/tile)"] = round(int(buf[9]) / tiles, 1)
 out["sum (cycles/tile)"] = round(sum(int(buf[i]) for i in range(1, 6)) / tiles, 1)
 print(json.dumps(out, indent=1))

@@ -43,12 +43,13 @@ __device__ __forceinline__ unsigned long long pack_key(float z, int f) {
 // tiles: [0] tiles, [1] header + staging (to the first barrier), [2] prefix sums, [3] (face, pixel) items,
 // [4] covered-pixel compaction incl. the list atomic, [5] finishing the covered pixels (exact sample + shading)
 #ifdef TRB_KN_STATS
-__device__ unsigned long long g_k1_phase[8];
+__device__ unsigned long long g_k1_phase[16];
 #define K1_T(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_k1_phase[i], (unsigned long long)(now_ - k1_t_)); k1_t_ = now_; } } while (0)
 #else
 #define K1_T(i) ((void)0)
 #endif
 constexpr int kStrip = TRB_K1_STRIP;  // tiles per CTA strip
+constexpr int kK1ItemTable = 4096;    // (face, pixel) items of a staging chunk with a face lookup entry (else: search)
 
 // Background of one tile whose face list is empty: a pure streaming store of -1 Fragments and
 // the background colour.
@@ -229,6 +230,9 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   __shared__ int s_rng[NT];        // c0 - tile_x0 | (r0 - tile_y0) << 4 | (bbox width - 1) << 8
   __shared__ int s_start[NT + 1];  // exclusive prefix sum of bbox pixel counts
   __shared__ int s_wtot[NT / 32];
+#ifndef TRB_K1_NESTED_ITEMS
+  __shared__ unsigned char s_item_face[kK1ItemTable];  // staged face of every (face, pixel) item of the chunk
+#endif
 
   const trb_view vd = a.views[n];
   const bool persp = a.flags & TRB_PERSPECTIVE_CORRECT, clip = a.flags & TRB_CLIP_BARYCENTRIC;
@@ -304,6 +308,81 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     if (tid == 0) { atomicAdd(&g_k1_phase[6], (unsigned long long)total); atomicAdd(&g_k1_phase[7], (unsigned long long)min(NT, nlist - base)); }
 #endif
 
+#ifdef TRB_KN_STATS
+    __shared__ unsigned long long s_itm_max, s_itm_sum;
+    if (tid == 0) { s_itm_max = 0; s_itm_sum = 0; }
+    __syncthreads();
+    const long long itm_t0 = clock64();
+#endif
+#ifndef TRB_K1_NESTED_ITEMS
+    // ---- (face, pixel) items, FLAT: item j of the chunk goes to thread j % 256 in round j / 256, so the lanes of a
+    // warp hold consecutive items -- mostly of the same face (its staged record is a shared-memory broadcast) -- and
+    // all run the same straight-line code: the face of an item comes from a lookup table the staging threads fill
+    // (one entry per item), not from per-thread nested face / pixel loops whose trip counts differ lane by lane
+    // (the nested version issued ~1,700 warp instructions per tile for ~4 items per thread).
+    const int m = min(NT, nlist - base);  // staged faces
+    const bool use_table = total <= kK1ItemTable;
+    if (use_table) {
+      const int my0 = s_start[tid], my1 = s_start[tid + 1];   // empty for tid >= m (npx == 0)
+      for (int j = my0; j < my1; ++j) s_item_face[j] = (unsigned char)tid;
+    }
+    __syncthreads();
+    for (int item = tid; item < total; item += NT) {
+      int fj;
+      if (use_table) {
+        fj = s_item_face[item];
+      } else {
+        int lo = 0, hi = m - 1;  // last staged face whose run starts at or before `item`
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_start[mid] <= item) lo = mid; else hi = mid - 1;
+        }
+        fj = lo;
+      }
+      const int k = item - s_start[fj];
+      const float4 bb = s_bb[fj], va = s_va[fj], vb = s_vb[fj];
+      const float2 vc = s_vc[fj];
+      const int rng = s_rng[fj], lf = s_id[fj];
+      FaceXYZ v;
+      v.x0 = va.x; v.y0 = va.y; v.z0 = va.z; v.x1 = va.w;
+      v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
+      const float area = vc.y;
+      const int c0 = rng & 15, r0 = (rng >> 4) & 15, bw = ((rng >> 8) & 15) + 1;
+      const int dr = (k * kInvWidth[bw]) >> 16;
+      const int lr = r0 + dr, lc = c0 + (k - dr * bw);
+      const float qx = s_px[lc], qy = s_py[lr];
+      if ((qx > bb.y) || (qx < bb.x) || (qy > bb.w) || (qy < bb.z)) continue;
+      // Early depth reject (blur 0 only, where every candidate is strictly inside its face): the interpolated depth
+      // is then a convex combination of the vertex depths up to a few ulp -- times area_raw / (area_raw + kEps)
+      // without perspective correction or clipping, where the weights are not renormalised -- so a pixel whose
+      // current front-most candidate is nearer than that bound cannot be won by this face.  zlo = 0 disables it.
+      float zlo = 0.0f;
+      if (hard_edges) {
+        const float zmin = min3f(v.z0, v.z1, v.z2);
+        if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
+        else if (clip) zlo = zmin * 0.99999f;
+        else zlo = zmin * 0.99999f * (area > 0.0f ? fmaxf(0.0f, (area - 2e-8f) / area) : 1.0f);
+      }
+      if (reinterpret_cast<const unsigned*>(s_key)[2 * (lr * TX + lc) + 1] < __float_as_uint(zlo)) continue;
+      const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
+      const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
+      const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);
+      if (hard_edges) {
+        // blur 0: w_i = e_i / area keeps the sign of e_i * area exactly => exact reject
+        if (area > 0.0f ? (e0 <= 0.0f || e1 <= 0.0f || e2 <= 0.0f)
+                        : (area < 0.0f && (e0 >= 0.0f || e1 >= 0.0f || e2 >= 0.0f)))
+          continue;
+      }
+      float pz, b0, b1, b2;
+      bool inside;
+      if (!eval_from_edges(v, area, e0, e1, e2, persp, clip, pz, b0, b1, b2, inside)) continue;
+      if (!inside) {
+        if (hard_edges) continue;
+        if (triangle_d2(v, qx, qy) >= blur) continue;
+      }
+      atomicMin(&s_key[lr * TX + lc], pack_key(pz, lf));
+    }
+#else
     // ---- deal the (face, pixel) pairs out in equal contiguous runs
     const int m = min(NT, nlist - base);  // staged faces
     const int ipt = (total + NT - 1) / NT;
@@ -373,7 +452,17 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
         k = 0;
       }
     }
+#endif
+#ifdef TRB_KN_STATS
+    {
+      const unsigned long long dt = (unsigned long long)(clock64() - itm_t0);
+      atomicMax(&s_itm_max, dt); atomicAdd(&s_itm_sum, dt);
+    }
+#endif
     __syncthreads();  // staging arrays are rewritten by the next chunk
+#ifdef TRB_KN_STATS
+    if (tid == 0) { atomicAdd(&g_k1_phase[8], s_itm_max); atomicAdd(&g_k1_phase[9], s_itm_sum / NT); }
+#endif
     K1_T(3);
   }
   // ---- epilogue.  Only the covered pixels (a third of a busy tile of the cow batch) need the division-heavy
@@ -1280,7 +1369,7 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
 
 #ifdef TRB_KN_STATS
 extern "C" int trb_debug_k1_phases(unsigned long long* host_out) {
-  unsigned long long zero[8] = {0};
+  unsigned long long zero[16] = {0};
   if (cudaMemcpyFromSymbol(host_out, trb::g_k1_phase, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
   if (cudaMemcpyToSymbol(trb::g_k1_phase, zero, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
   return TRB_OK;

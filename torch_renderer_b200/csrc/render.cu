@@ -232,6 +232,7 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
   __shared__ int s_wtot[NT / 32];
 #ifndef TRB_K1_NESTED_ITEMS
   __shared__ unsigned char s_item_face[kK1ItemTable];  // staged face of every (face, pixel) item of the chunk
+  __shared__ unsigned s_zlo_bits[NT];                  // bits of every staged face's depth lower bound
 #endif
 
   const trb_view vd = a.views[n];
@@ -279,7 +280,22 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
           s_vb[tid] = make_float4(v.y1, v.z1, v.x2, v.y2);
           s_vc[tid] = make_float2(v.z2, fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps));
           s_id[tid] = lf;
-          s_rng[tid] = (c0 - tile_x0) | ((r0 - tile_y0) << 4) | ((c1 - c0) << 8);
+          // box origin, width - 1 and the reciprocal-multiply constant of the width (k / w for k < 256)
+          s_rng[tid] = (c0 - tile_x0) | ((r0 - tile_y0) << 4) | ((c1 - c0) << 8) | (kInvWidth[c1 - c0 + 1] << 12);
+#ifndef TRB_K1_NESTED_ITEMS
+          {
+            // early depth reject bound of this face (see the item loop), computed once per face
+            const float area_s = fadd(edge_fn(v.x2, v.y2, v.x0, v.y0, v.x1, v.y1), kEps);
+            float zlo = 0.0f;
+            if (hard_edges) {
+              const float zmin = min3f(v.z0, v.z1, v.z2);
+              if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
+              else if (clip) zlo = zmin * 0.99999f;
+              else zlo = zmin * 0.99999f * (area_s > 0.0f ? fmaxf(0.0f, (area_s - 2e-8f) / area_s) : 1.0f);
+            }
+            s_zlo_bits[tid] = __float_as_uint(zlo);
+          }
+#endif
         }
       }
     }
@@ -348,22 +364,15 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
       v.y1 = vb.x; v.z1 = vb.y; v.x2 = vb.z; v.y2 = vb.w; v.z2 = vc.x;
       const float area = vc.y;
       const int c0 = rng & 15, r0 = (rng >> 4) & 15, bw = ((rng >> 8) & 15) + 1;
-      const int dr = (k * kInvWidth[bw]) >> 16;
+      const int dr = (k * (rng >> 12)) >> 16;
       const int lr = r0 + dr, lc = c0 + (k - dr * bw);
       const float qx = s_px[lc], qy = s_py[lr];
       if ((qx > bb.y) || (qx < bb.x) || (qy > bb.w) || (qy < bb.z)) continue;
       // Early depth reject (blur 0 only, where every candidate is strictly inside its face): the interpolated depth
       // is then a convex combination of the vertex depths up to a few ulp -- times area_raw / (area_raw + kEps)
       // without perspective correction or clipping, where the weights are not renormalised -- so a pixel whose
-      // current front-most candidate is nearer than that bound cannot be won by this face.  zlo = 0 disables it.
-      float zlo = 0.0f;
-      if (hard_edges) {
-        const float zmin = min3f(v.z0, v.z1, v.z2);
-        if (persp) zlo = zmin >= 1e-3f ? zmin * 0.99999f : 0.0f;
-        else if (clip) zlo = zmin * 0.99999f;
-        else zlo = zmin * 0.99999f * (area > 0.0f ? fmaxf(0.0f, (area - 2e-8f) / area) : 1.0f);
-      }
-      if (reinterpret_cast<const unsigned*>(s_key)[2 * (lr * TX + lc) + 1] < __float_as_uint(zlo)) continue;
+      // current front-most candidate is nearer than that bound cannot be won by this face.  Bound 0 disables it.
+      if (reinterpret_cast<const unsigned*>(s_key)[2 * (lr * TX + lc) + 1] < s_zlo_bits[fj]) continue;
       const float e0 = edge_fn(qx, qy, v.x1, v.y1, v.x2, v.y2);
       const float e1 = edge_fn(qx, qy, v.x2, v.y2, v.x0, v.y0);
       const float e2 = edge_fn(qx, qy, v.x0, v.y0, v.x1, v.y1);

@@ -850,3 +850,21 @@ def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, 
         assert (out[True][0] - out[False][0]).abs().max() < 1e-5
     for a, b in zip(out[True][1:], out[False][1:]):
         assert rel_l2(a, b) < 1e-4      # two runs of the same kernels: atomics order + the normals' ulps through the blend
+
+
+def test_k1_many_screen_sized_faces_item_table_overflow():
+    """K=1 tile raster with more (face, pixel) work items per staging chunk than its per-item face table holds
+    (40 screen-sized faces over every 16x16 tile = 10,240 items > 4,096): the binary-search path, against the oracle;
+    and with a few hundred small faces mixed in (both paths in one image)."""
+    g = torch.Generator().manual_seed(21)
+    big = torch.cat([torch.rand(40, 3, 2, generator=g) * 3.0 - 1.5, 1.0 + torch.rand(40, 3, 1, generator=g) * 2], -1)
+    c = torch.rand(400, 1, 2, generator=g) * 2.0 - 1.0
+    small = torch.cat([c + 0.05 * torch.randn(400, 3, 2, generator=g), 0.8 + torch.rand(400, 3, 1, generator=g)], -1)
+    for tris in (big, torch.cat([big[:25], small])):
+        verts = tris.reshape(-1, 3).float()
+        faces = torch.arange(verts.shape[0]).reshape(-1, 3)
+        for persp in (False, True):
+            want = oracle_rasterize(verts[None], faces, (64, 80), 0.0, 1, persp, False)
+            got = _cuda_raster_from_ndc(verts[None], faces, (64, 80), 0.0, 1, persp, False)
+            _assert_fragments_equal(got, want)
+            assert (want[0] >= 0).mean() > 0.5

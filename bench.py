@@ -493,6 +493,14 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# Warp instructions per launch of the K>1 fine kernel on the C5 chunk / C3, from the committed ncu captures
+# (profiles/r02_ncu_kn_C5_after.txt, r02_ncu_kn_C3_after.txt: smsp__inst_executed.sum; the fine kernels' instruction
+# streams did not change afterwards).  C5 is bound by instruction issue, not by HBM, so its fine kernel is also
+# reported against the issue-slot roofline: warp instructions / (148 SMs x 4 schedulers x SM clock x kernel time).
+KN_FINE_WARP_INSTRUCTIONS = {"C5": 3_241_201_101, "C3": 55_032_257}
+KN_FINE_LANES_PER_INSTRUCTION = {"C5": 19.44, "C3": 23.20}
+
+
 def measure_other_configs(dev, args, peak):
     """C1, C3 (teapot, cow), C4, the reference's camera_pose_optimizer step and one 4-view chunk of C5 through the
     public API, eager: ms/step = median of `repeats` repeats of `steps` steps (CUDA events), the two fused kernels'
@@ -566,7 +574,18 @@ def measure_other_configs(dev, args, peak):
                     del cap
                 except Exception as e:  # noqa: BLE001
                     graph = {"error": f"{type(e).__name__}: {e}"[:300]}
+            issue = None
+            if name in KN_FINE_WARP_INSTRUCTIONS and fine:
+                slots = 148 * 4 * 1.965e9 * statistics.median(fine) * 1e-3     # issue slots at the max SM clock
+                issue = {"kernel": "render_fine_kn_kernel", "warp_instructions_per_launch": KN_FINE_WARP_INSTRUCTIONS[name],
+                         "issue_slot_frac": round(KN_FINE_WARP_INSTRUCTIONS[name] / slots, 4),
+                         "lanes_per_instruction": KN_FINE_LANES_PER_INSTRUCTION[name],
+                         "thread_slot_frac": round(KN_FINE_WARP_INSTRUCTIONS[name] * KN_FINE_LANES_PER_INSTRUCTION[name]
+                                                   / 32 / slots, 4),
+                         "source": "ncu smsp__inst_executed.sum (profiles/r02_ncu_kn_*_after.txt) / (148 SMs x 4 "
+                                   "schedulers x 1965 MHz x this run's kernel time)"}
             out[name] = {"what": info["what"], "views_per_s": round(info["views"] / ms * 1e3, 2), "captured": graph,
+                         "issue_roofline": issue,
                          "ms_per_step": round(ms, 4), "ms_per_step_repeats": [round(r, 4) for r in reps],
                          "host_issue_ms_per_step": round(statistics.median(host), 4), "steps": steps,
                          "fine_kernel_ms": round(statistics.median(fine), 4) if fine else None,

@@ -20,6 +20,12 @@ names = ["busy_tiles", "list_entries", "faces_staged", "walk_iters", "pass_zlo",
 out = {n: int(buf[i]) for i, n in enumerate(names)}
 out["max_list_entries"] = int(buf[14]); out["max_walk_cycles"] = int(buf[15])
 out["views"] = info["views"]
+if hasattr(L, "trb_debug_kn_phases"):
+    ph = (ctypes.c_ulonglong * 8)()
+    L.trb_debug_kn_phases(ph)
+    t = max(int(ph[0]), 1)
+    out["phase_cycles_per_busy_tile_thread0"] = {"tiles": t, "list ordering": round(int(ph[1]) / t), "staging": round(int(ph[2]) / t),
+                                                 "walk": round(int(ph[3]) / t), "epilogue": round(int(ph[4]) / t)}
 if hasattr(L, "trb_debug_bw_stats"):
     bw = (ctypes.c_ulonglong * 8)()
     L.trb_debug_bw_stats(bw)

@@ -35,9 +35,12 @@ constexpr int kInsideBit = (int)0x80000000u;
 // trb_debug_kn_stats).  Not compiled into the product library.
 #ifdef TRB_KN_STATS
 __device__ unsigned long long g_kn_stats[16];
+__device__ unsigned long long g_kn_phase[8];   // thread 0: [0] busy tiles, cycles in [1] list ordering, [2] staging, [3] walk, [4] epilogue
+#define KN_PH(i) do { if (tid == 0) { const long long n_ = clock64(); atomicAdd(&g_kn_phase[i], (unsigned long long)(n_ - kn_pt)); kn_pt = n_; } } while (0)
 #define KN_STAT(i, v) (kn_st[i] += (v))
 #else
 #define KN_STAT(i, v) ((void)0)
+#define KN_PH(i) ((void)0)
 #endif
 
 // Block-wide maximum of a small non-negative int; contains __syncthreads (every thread must call it).
@@ -210,7 +213,8 @@ render_fine_kn_kernel(const FineArgs a) {
   unsigned kn_st[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (tid == 0) { KN_STAT(0, 1); KN_STAT(1, nlist); }
   const long long kn_t0 = clock64();
-  if (tid == 0) atomicMax(&g_kn_stats[14], (unsigned long long)nlist);
+  long long kn_pt = kn_t0;
+  if (tid == 0) { atomicMax(&g_kn_stats[14], (unsigned long long)nlist); atomicAdd(&g_kn_phase[0], 1ull); }
 #endif
   int cnt = 0;
   float kth = 3.0e38f;  // depth of the pixel's K-th layer once the list is full (register copy of kz[K-1])
@@ -286,6 +290,7 @@ render_fine_kn_kernel(const FineArgs a) {
       __syncthreads();
     }
 
+    KN_PH(1);
     bool stop = false;
     for (int base = 0; base < m; base += NT) {
       // ---- stage up to NT faces of the list
@@ -322,6 +327,7 @@ render_fine_kn_kernel(const FineArgs a) {
       __syncthreads();
       const int mm = min(NT, m - base);
       if (tid == 0) KN_STAT(2, mm);
+      KN_PH(2);
       if (live) {
         for (int q = slice; q < mm; q += SPLIT) {
           KN_STAT(3, 1);
@@ -428,10 +434,11 @@ render_fine_kn_kernel(const FineArgs a) {
         const float bound = s_bound[s_chunk_bucket[base / NT + 1]];
         const float zl = (persp && bound < 1e-3f) ? 0.0f : bound * 0.99999f;
         const bool done = !live || zl > kth;
-        if (__syncthreads_and(done)) { stop = true; if (tid == 0) KN_STAT(12, 1); break; }
+        if (__syncthreads_and(done)) { stop = true; if (tid == 0) KN_STAT(12, 1); KN_PH(3); break; }
       } else {
         __syncthreads();
       }
+      KN_PH(3);
     }
     (void)stop;
   }
@@ -467,7 +474,8 @@ render_fine_kn_kernel(const FineArgs a) {
   const bool sparse = a.sparse != 0;
   const int n_write = (!live || slice != 0) ? 0 : (sparse ? (total > 0 ? min(total + 1, K) : 0) : K);
   if (slice == 0) s_wr[p] = n_write;
-  const int k_end = sparse ? block_max_sync<NT>(n_write) : K;   // s_wr is published by the barrier after parking
+  const bool dist_only_pre = sparse && SHADER == TRB_SHADER_SOFT_SILHOUETTE;   // see dist_only below
+  const int k_end = dist_only_pre ? 0 : (sparse ? block_max_sync<NT>(n_write) : K);   // s_wr: published by the barrier after parking
 
   ViewParams vp;
   const ShadeIn sin = {a.verts_world, a.normals, a.colors, a.faces, a.uv};
@@ -491,6 +499,31 @@ render_fine_kn_kernel(const FineArgs a) {
   // its backward use the distances only), so the epilogue skips the nine IEEE divisions per layer that produce them
   const bool dist_only = sparse && SHADER == TRB_SHADER_SOFT_SILHOUETTE;
   int ia = 0, ib = 0;   // merge cursors
+  if (dist_only) {
+    // No parking, no barriers: the only things written are 12 bytes per sample (face + signed distance) of COVERED
+    // pixels -- a few MB -- so every thread stores its own layers straight to global memory.  (The coalesced,
+    // parked write-out below exists for the dense layout's 28*K bytes per pixel.)  The backward takes the number of
+    // layers from the covered-pixel list, so no terminator layer is written either.
+    if (live) {
+      const size_t g0 = (((size_t)n * H + yi) * W + xi) * K;
+      for (int k = 0; k < total; ++k) {
+        bool take_a = true;
+        if (SPLIT == 2)
+          take_a = ib >= cntB || (ia < cntA && cand_less(kz[ia * NT + colA], kf[ia * NT + colA] & kFaceMask,
+                                                         kz[ib * NT + colB], kf[ib * NT + colB] & kFaceMask));
+        const int f_raw = take_a ? kf[ia * NT + colA] : kf[ib * NT + colB];
+        if (take_a) ++ia; else ++ib;
+        if (SPLIT == 2 && (k & 1) != slice) continue;
+        const int f = f_raw & kFaceMask;
+        const FaceXYZ v = load_face(a.verts_ndc, a.faces, vd, f);
+        const float d2 = triangle_d2(v, px, py);
+        const float d = (f_raw & kInsideBit) ? -d2 : d2;
+        alpha *= 1.0f - sigmoidf(-d / a.sigma);
+        st_cs(a.p2f + g0 + k, (long long)vd.p2f_base + f);
+        st_cs(a.dists + g0 + k, d);
+      }
+    }
+  } else
   for (int k0 = 0; k0 < k_end; k0 += KG) {
     const int kg = min(KG, k_end - k0);
     for (int kk = 0; kk < kg; ++kk) {
@@ -563,6 +596,7 @@ render_fine_kn_kernel(const FineArgs a) {
     }
     __syncthreads();
   }
+  KN_PH(4);
   if (SHADER == TRB_SHADER_NONE) return;
   if (SPLIT == 2 && SHADER != TRB_SHADER_HARD_PHONG) {
     // slice 1 hands its share of the blend sums to slice 0 (the parking area is free again)
@@ -627,6 +661,12 @@ int launch_render_fine_kn(int shader, int light, int N, cudaStream_t st, const F
 
 #ifdef TRB_KN_STATS
 // Copies the 16 walk counters to `host_out` and clears them (diagnostic builds only; synchronises).
+extern "C" int trb_debug_kn_phases(unsigned long long* host_out) {
+  unsigned long long zero[8] = {0};
+  if (cudaMemcpyFromSymbol(host_out, trb::g_kn_phase, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  if (cudaMemcpyToSymbol(trb::g_kn_phase, zero, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;
+  return TRB_OK;
+}
 extern "C" int trb_debug_kn_stats(unsigned long long* host_out) {
   unsigned long long zero[16] = {0};
   if (cudaMemcpyFromSymbol(host_out, trb::g_kn_stats, sizeof(zero)) != cudaSuccess) return TRB_ERR_CUDA;

@@ -41,7 +41,10 @@
 extern "C" {
 #endif
 
-#define TRB_ABI_VERSION 3
+/* 4 (round 2): trb_render_config.sparse_fragments (was `reserved`), layer counts appended to the covered-pixel list
+ * (trb_render_sizes reports the new length), trb_points_raster_forward_binned / _workspace_bytes,
+ * trb_allreduce_set_timing. */
+#define TRB_ABI_VERSION 4
 #define TRB_MAX_FACES_PER_PIXEL 150
 
 typedef void* trb_stream_t; /* cudaStream_t */

@@ -14,6 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # TRB_LIB_PATH selects another build of the same ABI (same-box A/B of kernel variants: profiles/ab_run.sh)
 LIB_PATH = os.environ.get("TRB_LIB_PATH") or os.path.join(_PKG, "libtrb.so")
 
+ABI_VERSION = 4   # include/trb.h TRB_ABI_VERSION
 TRB_OK, TRB_ERR_BAD_ARG, TRB_ERR_K_TOO_LARGE, TRB_ERR_WORKSPACE, TRB_ERR_CUDA = range(5)
 
 PERSPECTIVE_CORRECT, CLIP_BARYCENTRIC, CULL_BACKFACES = 1, 2, 4
@@ -113,7 +114,7 @@ def lib() -> ctypes.CDLL:
             fn.restype = _c.c_int
         handle.trb_status_string.argtypes = [_i]
         handle.trb_status_string.restype = _c.c_char_p
-        if handle.trb_abi_version() != 3:
+        if handle.trb_abi_version() != ABI_VERSION:
             raise TrbLibraryError("libtrb.so ABI version mismatch; rebuild it")
         for which, (name, size) in enumerate((("trb_view", 32), ("trb_shade_config", _c.sizeof(ShadeConfig)),
                                               ("trb_render_config", _c.sizeof(RenderConfig)),

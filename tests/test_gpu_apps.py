@@ -296,3 +296,62 @@ def _capture_step_body(trb, dev, load_mesh, normalize_mesh):
         cap.check()
     with pytest.raises(trb.NearPlaneCrossed):
         cap()
+
+
+def test_captured_pose_optimisation_with_adam_converges():
+    """The whole optimisation step of the reference's camera_pose_optimizer loop (:299-329) -- zero_grad, silhouette
+    + Phong renders of the pose, loss.backward(), Adam.step() -- captured ONCE with trb.capture_step and replayed:
+    the pose converges like the eager loop, and the near-plane flag stays down."""
+    trb = _trb()
+    with torch.cuda.stream(torch.cuda.Stream(device=DEV)):
+        torch.manual_seed(0)
+        v, f = load_mesh("teapot")
+        v = normalize_mesh(v)
+        mesh = trb.Meshes([v.to(DEV)], [f.to(DEV)],
+                          textures=trb.TexturesVertex(torch.rand(1, v.shape[0], 3, device=DEV)))
+        cams = trb.FoVPerspectiveCameras(device=DEV)
+        blend = trb.BlendParams(SIGMA, 1e-4, (0.0, 0.0, 0.0))
+        sil = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=96, blur_radius=BLUR,
+                                                                                  faces_per_pixel=20)),
+                               trb.SoftSilhouetteShader(blend))
+        phong = trb.MeshRenderer(trb.MeshRasterizer(cams, trb.RasterizationSettings(image_size=96)),
+                                 trb.SoftPhongShader(device=DEV, cameras=cams, blend_params=blend,
+                                                     lights=trb.PointLights(device=DEV, location=[[0.0, 0.0, -3.0]])))
+        R_ref, T_ref = trb.look_at_view_transform(2.7, 30.0, 60.0)
+        q_ref = torch.cat([T_ref, trb.transforms.matrix_to_quaternion(R_ref)], -1).to(DEV)
+
+        def render(pose):
+            R = trb.transforms.quaternion_to_matrix(pose[:, 3:]); T = pose[:, :3]
+            return sil(mesh, R=R, T=T)[..., 3], phong(mesh, R=R, T=T)[..., :3]
+
+        with torch.no_grad():
+            a_ref, c_ref = render(q_ref)
+        R0, T0 = trb.look_at_view_transform(2.9, 22.0, 48.0)
+        pose = torch.cat([T0, trb.transforms.matrix_to_quaternion(R0)], -1).to(DEV).requires_grad_(True)
+        opt = torch.optim.Adam([pose], lr=0.01, capturable=True)
+        loss_out = torch.zeros((), device=DEV)
+
+        def step():
+            opt.zero_grad(set_to_none=False) if pose.grad is not None else None
+            alpha, rgb = render(pose)
+            loss = (alpha - a_ref).abs().mean() + 0.1 * ((rgb - c_ref) ** 2).mean()
+            loss.backward()
+            opt.step()
+            loss_out.copy_(loss.detach())
+            return loss_out
+
+        def pose_error():
+            q = pose.detach()
+            qn = q[:, 3:] / q[:, 3:].norm()
+            qr = q_ref[:, 3:] / q_ref[:, 3:].norm()
+            return float((q[:, :3] - q_ref[:, :3]).norm() + torch.minimum((qn - qr).norm(), (qn + qr).norm()))
+
+        e0 = pose_error()
+        cap = trb.capture_step(step, warmup=3)        # 3 warm-up steps + the captured one already move the pose
+        l0 = float(cap())
+        for _ in range(150):
+            cap()
+        cap.check()
+        l1, e1 = float(loss_out), pose_error()
+        assert l1 < 0.3 * l0, (l0, l1)
+        assert e1 < 0.5 * e0, (e0, e1)

@@ -82,6 +82,8 @@ class TexturesVertex:
 
     def verts_features_packed(self) -> torch.Tensor:
         self._materialize()
+        if len(self._feats) == 1:
+            return self._feats[0]          # one mesh: the packed tensor IS its feature tensor (no copy kernel)
         return torch.cat(self._feats, dim=0)
 
     def verts_features_padded(self) -> torch.Tensor:

@@ -133,7 +133,7 @@ def run_ours(args):
     import torch.distributed as dist
     import torch_renderer_b200 as trb
     from torch_renderer_b200 import ops
-    from torch_renderer_b200.parallel import allreduce_shared_grads
+    from torch_renderer_b200.parallel import allreduce_shared_grads, fused_backward_allreduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,21 +198,42 @@ def run_ours(args):
         images.backward(grad_img)
         return images
 
-    def step_device():
+    def step_separate():        # the all-reduce as its own kernel after the backward (round-2 baseline, kept for the A/B)
         core_device()
         allreduce_shared_grads([verts.grad, cols.grad])
+
+    def step_fused():           # the all-reduce's push half inside the backward's tail kernel + a receive kernel
+        for p in params:
+            p.grad = None
+        images = renderer(meshes, R=Rd, T=Td)
+        with fused_backward_allreduce(dev) as fused:
+            images.backward(grad_img)
+        if not fused:           # no peer memory: NCCL after the backward
+            allreduce_shared_grads([verts.grad, cols.grad])
+        return images
+
+    step_device = step_fused if (world > 1 and args.collective == "fused") else step_separate
+    e2e_fused = world > 1 and args.collective == "fused"
+
+    def _fused_available():     # a live PeerAllReduce exists once the first multi-GPU step has run
+        from torch_renderer_b200 import parallel as _p
+        return any(v not in (None, False) for v in _p._peer_allreduce.values())
 
     # pinned host buffers for the end-to-end leg: ONE packed buffer each way (inputs in; gradients + metric out)
     host_in = torch.cat([t.reshape(-1) for t in host_params]).pin_memory()
     host_out = torch.empty(sum(sizes) + 1, dtype=torch.float32).pin_memory()
     dev_out = torch.empty(sum(sizes) + 1, dtype=torch.float32, device=dev)
 
-    def core_e2e():             # H2D of this step's inputs + forward + backward + metric
+    def core_e2e():             # H2D of this step's inputs + forward + backward (+ fused all-reduce) + metric
         for p in params:
             p.grad = None
         dev_in.copy_(host_in, non_blocking=True)   # lands in verts / cols / Rd / Td (views of dev_in)
         images = renderer(meshes, R=Rd, T=Td)
-        images.backward(grad_img)
+        if e2e_fused:
+            with fused_backward_allreduce(dev):
+                images.backward(grad_img)
+        else:
+            images.backward(grad_img)
         # the step's result read back by the host: mean alpha (silhouette coverage) ...
         dev_out[-1:].copy_(images.detach()[..., 3].mean().reshape(1))
 
@@ -274,6 +295,8 @@ def run_ours(args):
     # world > 1: the all-reduce of the shared gradients is part of the captured step (the peer-memory kernel keeps
     # its epochs in device memory, so it replays); its block 0 accumulates push / wait nanoseconds (diagnostics)
     ar_timing = None
+    fused_in_use = False
+    e2e_fused = e2e_fused and _fused_available()
     if world > 1:
         ar_timing = torch.zeros(3, dtype=torch.int64, device=dev)
         from torch_renderer_b200 import _lib as _l
@@ -286,8 +309,10 @@ def run_ours(args):
                 core_run()
                 allreduce_shared_grads([verts.grad, cols.grad])
             mode_device += " + eager all-reduce"
+            fused_in_use = False
         else:
-            mode_device = "cuda-graph (all-reduce captured)"
+            fused_in_use = step_device is step_fused and _fused_available()
+            mode_device = "cuda-graph (all-reduce captured" + (", push fused into the backward tail)" if fused_in_use else ")")
         run_device = step_run
     else:
         run_device, mode_device = graphed(core_device)
@@ -311,7 +336,9 @@ def run_ours(args):
         per_rank = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(per_rank, t)
         calls = max(int(t[2].item()), 1)
-        ar_report = {"what": "block 0 of the peer all-reduce kernel, %globaltimer ns averaged over the timed steps, per rank",
+        ar_report = {"what": ("block 0 of the receive kernel (the push runs inside post_backward_kernel's last blocks: push_us is 0 here)"
+                              if fused_in_use else "block 0 of the peer all-reduce kernel") +
+                             ", %globaltimer ns averaged over the timed steps, per rank",
                      "push_us": [round(float(r[0]) / max(int(r[2]), 1) / 1e3, 2) for r in per_rank],
                      "wait_and_sum_us": [round(float(r[1]) / max(int(r[2]), 1) / 1e3, 2) for r in per_rank],
                      "calls": calls,
@@ -321,6 +348,20 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * N / (ms_step / 1e3)
+    # same box, same process: the step with the all-reduce as its own kernel after the backward (the other variant)
+    collective_ab = None
+    if world > 1 and fused_in_use:
+        sep_run, sep_mode = graphed(step_separate)
+        if sep_mode == "cuda-graph":
+            for _ in range(200):
+                sep_run()
+            ms_sep = timed(sep_run, args.steps)[0] / args.steps
+            for _ in range(200):
+                run_device()
+            ms_fused_again = timed(run_device, args.steps)[0] / args.steps
+            collective_ab = {"fused_into_backward_tail_ms_per_step": round(ms_fused_again, 4),
+                             "separate_kernel_ms_per_step": round(ms_sep, 4),
+                             "what": "same process, both captured in the step graph, timed back to back after the headline"}
 
     # per-kernel durations: the same steps again, with CUDA events recorded by libtrb on the launching
     # stream right around its two dominant kernels (the fused fine pass and the fused backward), and
@@ -381,7 +422,8 @@ def run_ours(args):
 
         def run_e2e():
             core_e2e_run()
-            allreduce_shared_grads([verts.grad, cols.grad])
+            if not e2e_fused:
+                allreduce_shared_grads([verts.grad, cols.grad])
             readback_run()
 
     for _ in range(max(3, args.warmup)):
@@ -402,6 +444,27 @@ def run_ours(args):
     # the peer kernel sums in rank order -- and (b) NCCL's own all-reduce of the copies (its order is its own:
     # tolerance).  Every rank checks its own result; the verdicts are AND-ed.
     collective_check = None
+    fused_check = None
+    if world > 1 and fused_in_use:
+        # the fused form sums in place inside the backward, so its inputs are not observable: the result must be
+        # bit-identical on every rank (same values, same rank order) and agree with NCCL's all-reduce of the local
+        # gradients of a separate, un-reduced backward (whose atomics settle in another order: tolerance)
+        step_fused()
+        got = [verts.grad.detach().clone(), cols.grad.detach().clone()]
+        core_device()
+        same = close = True
+        for g, loc in zip(got, (verts.grad, cols.grad)):
+            every = [torch.empty_like(g) for _ in range(world)]
+            dist.all_gather(every, g)
+            same = same and all(bool(torch.equal(every[0], e)) for e in every[1:])
+            nccl = loc.detach().clone()
+            dist.all_reduce(nccl)
+            close = close and bool(torch.allclose(g, nccl, rtol=1e-4, atol=1e-5 * float(nccl.abs().max())))
+        flags = torch.tensor([int(same), int(close)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        same, close = bool(flags[0].item()), bool(flags[1].item())
+        fused_check = ("ok" if (same and close) else "MISMATCH") + \
+            f" (bit-identical on all {world} ranks: {same}; vs NCCL all-reduce of a separate backward within 1e-4: {close})"
     if world > 1:
         core_device()
         local = [verts.grad.detach().clone(), cols.grad.detach().clone()]
@@ -482,6 +545,10 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if collective_check is not None:
             line["collective_check"] = collective_check
+        if fused_check is not None:
+            line["collective_check_fused"] = fused_check
+        if collective_ab is not None:
+            line["collective_ab"] = collective_ab
         if ar_report is not None:
             line["collective_timing"] = ar_report
         if other is not None:
@@ -773,6 +840,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--repeats", type=int, default=5, help="timed repeats of --steps steps; the median is reported")
     ap.add_argument("--no-configs", action="store_true", help="skip the other_configs block (C1, C3, C4, pose step, C5 chunk)")
+    ap.add_argument("--collective", choices=("fused", "separate"), default="separate",
+                    help="N > 1: the all-reduce as its own kernel behind the backward (default: it measured 1.5-4.5 us "
+                         "per step faster, profiles/r02_collective_ab.md) or pushed from the backward's tail kernel "
+                         "(parallel.fused_backward_allreduce; adds a same-process A/B of both to the line)")
     ap.add_argument("--no-c5", action="store_true", help="skip BASELINE configs[4] at spec (1M faces x 1024 views)")
     ap.add_argument("--c5-views", type=int, default=1024)
     ap.add_argument("--c5-chunk", type=int, default=32, help="views per chunk of a rank's C5 slice (bounds Fragments memory)")

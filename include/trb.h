@@ -41,10 +41,11 @@
 extern "C" {
 #endif
 
-/* 4 (round 2): trb_render_config.sparse_fragments (was `reserved`), layer counts appended to the covered-pixel list
+/* 5 (round 2): trb_render_backward_allreduce + trb_peer_sum (the all-reduce's push half inside the backward tail).
+ * 4 (round 2): trb_render_config.sparse_fragments (was `reserved`), layer counts appended to the covered-pixel list
  * (trb_render_sizes reports the new length), trb_points_raster_forward_binned / _workspace_bytes,
  * trb_allreduce_set_timing. */
-#define TRB_ABI_VERSION 4
+#define TRB_ABI_VERSION 5
 #define TRB_MAX_FACES_PER_PIXEL 150
 
 typedef void* trb_stream_t; /* cudaStream_t */
@@ -305,6 +306,40 @@ int trb_render_backward(const trb_render_config* host_cfg, const trb_view* views
                         float* grad_verts_world, float* grad_vert_colors, float* grad_R, float* grad_T,
                         float* grad_proj, float* grad_view_params, float* scratch,
                         const trb_uv_texture* host_uv, int device, trb_stream_t stream);
+
+/* The same backward with the multi-GPU sum of the view-shared gradients fused into its tail (the
+ * exchange step of the path): the last blocks of the kernel that finalises grad_verts_world / grad_vert_colors push
+ * the finished values, tagged with the call's epoch, straight into every peer's inbox (trb_allreduce_sum_f32's
+ * protocol, inbox and epoch counters -- fused and stand-alone calls may alternate), and a short receive kernel sums
+ * what arrives, in rank order, back into grad_verts_world / grad_vert_colors: on return (in stream order) they hold
+ * the sums over all ranks, bit-identical on every rank.  grad_R / grad_T / grad_proj / grad_view_params / the UV
+ * map's gradient stay local.  Segments: grad_verts_world (3 * num_world_verts floats) when non-NULL, then
+ * grad_vert_colors (Phong shaders with vertex colours) when non-NULL; together they must fit capacity_floats and
+ * every rank must make the same sequence of calls with the same layout.  A rank with an empty batch cannot take
+ * part (TRB_ERR_BAD_ARG).  A peer that does not arrive within the spin limit raises *error_flag (device int) and
+ * leaves the affected values un-reduced.
+ * Host struct; every pointer inside is a DEVICE pointer except host_peer_inbox (host array of `world` device
+ * pointers: rank r's inbox as mapped into this process, as for trb_allreduce_sum_f32). */
+typedef struct trb_peer_sum {
+  void* const* host_peer_inbox;
+  int64_t capacity_floats;
+  int32_t rank, world;
+  uint32_t* epochs;        /* trb_allreduce_grid(capacity_floats) counters, shared with trb_allreduce_sum_f32 */
+  int32_t* error_flag;
+  uint32_t* done_counter;  /* one zero-initialised word; the receive kernel leaves it zero again */
+} trb_peer_sum;
+
+int trb_render_backward_allreduce(const trb_render_config* host_cfg, const trb_view* views,
+                                  const float* verts_world, const int32_t* faces, const float* vert_colors,
+                                  const float* R, const float* T, const float* proj, const float* view_params,
+                                  const float* verts_ndc, const float* normals_raw, const float* normals,
+                                  const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                                  const float* dists, const int32_t* hit_pixels, const float* grad_images,
+                                  const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                  float* grad_verts_world, float* grad_vert_colors, float* grad_R, float* grad_T,
+                                  float* grad_proj, float* grad_view_params, float* scratch,
+                                  const trb_uv_texture* host_uv, const trb_peer_sum* host_peer, int device,
+                                  trb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Point-cloud rendering (replaces _C.rasterize_points / _C.rasterize_points_backward and the compositors

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     # the Python binding covers the same set
     assert set(syms) == set(_lib.declared_symbols())
     L = _lib.lib()
-    assert L.trb_abi_version() == 4
+    assert L.trb_abi_version() == 5
     assert L.trb_status_string(2).decode().startswith("faces_per_pixel")
 
 

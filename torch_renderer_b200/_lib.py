@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # TRB_LIB_PATH selects another build of the same ABI (same-box A/B of kernel variants: profiles/ab_run.sh)
 LIB_PATH = os.environ.get("TRB_LIB_PATH") or os.path.join(_PKG, "libtrb.so")
 
-ABI_VERSION = 4   # include/trb.h TRB_ABI_VERSION
+ABI_VERSION = 5   # include/trb.h TRB_ABI_VERSION
 TRB_OK, TRB_ERR_BAD_ARG, TRB_ERR_K_TOO_LARGE, TRB_ERR_WORKSPACE, TRB_ERR_CUDA = range(5)
 
 PERSPECTIVE_CORRECT, CLIP_BARYCENTRIC, CULL_BACKFACES = 1, 2, 4
@@ -49,6 +49,12 @@ class UvTexture(ctypes.Structure):
                 ("map_h", _c.c_int32), ("map_w", _c.c_int32)]
 
 
+class PeerSum(ctypes.Structure):
+    """trb_peer_sum: what trb_render_backward_allreduce needs to push the shared gradients to the peers."""
+    _fields_ = [("host_peer_inbox", _vp), ("capacity_floats", _i64), ("rank", _c.c_int32), ("world", _c.c_int32),
+                ("epochs", _vp), ("error_flag", _vp), ("done_counter", _vp)]
+
+
 # name -> argtypes; every function returns int (trb_status) unless noted
 _SIGNATURES = {
     "trb_abi_version": [],
@@ -71,6 +77,8 @@ _SIGNATURES = {
     "trb_render_sizes": [_c.POINTER(RenderConfig), _c.POINTER(_sz), _c.POINTER(_i64), _c.POINTER(_i64)],
     "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _c.POINTER(UvTexture), _i, _vp],
     "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture), _i, _vp],
+    "trb_render_backward_allreduce": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture),
+                                                                                _c.POINTER(PeerSum), _i, _vp],
     "trb_debug_set_events": [_vp, _vp, _vp, _vp],
     "trb_points_raster_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "trb_points_raster_workspace_bytes": [_i, _i, _i, _i64, _c.POINTER(_sz)],

@@ -16,6 +16,7 @@
 // memory, so the kernel can be replayed from a CUDA graph and the segment layout may change between calls.
 #include "trb_internal.cuh"
 #include "stages.cuh"   // pdl_wait
+#include "allreduce.cuh"
 
 namespace trb {
 
@@ -27,30 +28,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
-}
-
-constexpr int kMaxSegments = 4;
-constexpr int kMaxPeers = 16;
-constexpr int kArChunk = 1024;  // elements per block
-
-struct ArSegments {
-  float* ptr[kMaxSegments];
-  long long start[kMaxSegments + 1];  // prefix offsets; start[count] = total
-  int count;
-};
-
-struct ArPeers {
-  // rank r's inbox as mapped here: [2 parities][world senders][capacity] words of (epoch << 32 | value bits)
-  unsigned long long* inbox[kMaxPeers];
-};
-
-__device__ __forceinline__ void st_relaxed_sys_b64(unsigned long long* addr, unsigned long long w) {
-  asm volatile("st.global.relaxed.sys.b64 [%0], %1;" ::"l"(addr), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_b64(const unsigned long long* addr) {
-  unsigned long long w;
-  asm volatile("ld.global.relaxed.sys.b64 %0, [%1];" : "=l"(w) : "l"(addr) : "memory");
-  return w;
 }
 
 __global__ void __launch_bounds__(256)
@@ -72,10 +49,7 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
     const long long i = (long long)blockIdx.x * kArChunk + u * 256 + threadIdx.x;
     dst[u] = nullptr; v[u] = 0.0f;
     if (i < total) {
-      int s = 0;
-#pragma unroll
-      for (int k = 1; k < kMaxSegments; ++k) s += (k < seg.count && i >= seg.start[k]) ? 1 : 0;
-      dst[u] = seg.ptr[s] + (i - seg.start[s]);
+      dst[u] = ar_element(seg, i);
       v[u] = *dst[u];
       for (int r = 0; r < world; ++r)
         if (r != rank)
@@ -127,6 +101,72 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
   }
 }
 
+// The receive-and-sum half on its own: the push half ran inside post_backward_kernel (render_stages.cu), whose last
+// blocks wrote this rank's finished gradients into the peers' inboxes while the rest of that kernel drained.  Same
+// inbox, epochs and rank-ordered sum as allreduce_push_kernel, so fused and stand-alone calls can alternate.
+__global__ void __launch_bounds__(256)
+allreduce_receive_kernel(const ArSegments seg, const ArPeers p, int rank, int world, long long capacity,
+                         unsigned* epochs, int* error, unsigned* done, unsigned long long* timing) {
+  constexpr int PER = kArChunk / 256;
+  pdl_wait();
+  const bool timed = timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t1 = timed ? global_ns() : 0ull;
+  const unsigned epoch = epochs[blockIdx.x] + 1u;
+  const long long total = seg.start[seg.count];
+  const size_t parity_off = (size_t)(epoch & 1u) * world * capacity;
+  const unsigned long long* mine = p.inbox[rank] + parity_off;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const long long i = (long long)blockIdx.x * kArChunk + u * 256 + threadIdx.x;
+    if (i >= total) continue;
+    float* dst = ar_element(seg, i);
+    const float own = *dst;
+    float acc = 0.0f;
+    bool ok = true;
+    for (int r0 = 0; r0 < world && ok; r0 += 8) {
+      unsigned long long w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + j;
+        if (r < world && r != rank) w[j] = ld_relaxed_sys_b64(mine + (size_t)r * capacity + i);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + j;
+        if (r >= world || !ok) continue;
+        if (r == rank) { acc += own; continue; }
+        const unsigned long long* src = mine + (size_t)r * capacity + i;
+        unsigned spins = 0;
+        while ((unsigned)(w[j] >> 32) != epoch) {
+          if (++spins > (1u << 26)) { atomicExch(error, 1); ok = false; break; }
+          w[j] = ld_relaxed_sys_b64(src);
+        }
+        acc += __uint_as_float((unsigned)w[j]);
+      }
+    }
+    if (ok) *dst = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epochs[blockIdx.x] = epoch;
+    if (blockIdx.x == 0) *done = 0u;   // the next post_backward_kernel counts its blocks from zero again
+  }
+  if (timed) {
+    const unsigned long long t2 = global_ns();
+    timing[1] += t2 - t1; timing[2] += 1ull;
+  }
+}
+
+int launch_allreduce_receive(const ArPush& a, cudaStream_t st) {
+  const long long total = a.seg.start[a.seg.count];
+  if (total == 0) return TRB_OK;
+  const int grid = (int)((total + kArChunk - 1) / kArChunk);
+  TRB_CUDA_TRY(launch_pdl(allreduce_receive_kernel, dim3(grid), dim3(256), 0, st, a.seg, a.peers, a.rank, a.world,
+                          a.capacity, a.epochs, a.error, a.done, g_ar_timing));
+  TRB_LAUNCH_CHECK();
+  return TRB_OK;
+}
+
 }  // namespace trb
 
 using namespace trb;
@@ -139,30 +179,14 @@ extern "C" int trb_allreduce_grid(int64_t capacity_floats) {
 extern "C" int trb_allreduce_sum_f32(float* const* host_segments, const int64_t* host_counts, int num_segments,
                                      void* const* host_peer_inbox, int64_t capacity_floats, int rank, int world,
                                      uint32_t* epochs, int32_t* error_flag, int device, trb_stream_t stream) {
-  if (num_segments < 1 || num_segments > kMaxSegments || world < 1 || world > kMaxPeers || rank < 0 ||
-      rank >= world || !host_segments || !host_counts || !host_peer_inbox || !error_flag || !epochs ||
-      capacity_floats < 1)
-    return TRB_ERR_BAD_ARG;
+  if (!error_flag || !epochs) return TRB_ERR_BAD_ARG;
   ArSegments seg;
-  seg.count = num_segments;
-  long long total = 0;
-  for (int i = 0; i < kMaxSegments; ++i) {
-    seg.ptr[i] = i < num_segments ? host_segments[i] : nullptr;
-    seg.start[i] = total;
-    if (i < num_segments) {
-      if (host_counts[i] < 0 || !host_segments[i]) return TRB_ERR_BAD_ARG;
-      total += host_counts[i];
-    }
-  }
-  seg.start[kMaxSegments] = total;
-  for (int i = num_segments; i <= kMaxSegments; ++i) seg.start[i] = total;
-  if (total == 0) return TRB_OK;
-  if (total > capacity_floats) return TRB_ERR_BAD_ARG;
   ArPeers p;
-  for (int r = 0; r < kMaxPeers; ++r) {
-    p.inbox[r] = r < world ? (unsigned long long*)host_peer_inbox[r] : nullptr;
-    if (r < world && !p.inbox[r]) return TRB_ERR_BAD_ARG;
-  }
+  long long total = 0;
+  const int rc = ar_fill_tables(host_segments, host_counts, num_segments, host_peer_inbox, capacity_floats, rank, world,
+                                seg, p, total);
+  if (rc != TRB_OK) return rc;
+  if (total == 0) return TRB_OK;
   TRB_ENTER(device);
   const int grid = (int)((total + kArChunk - 1) / kArChunk);
   TRB_CUDA_TRY(launch_pdl(allreduce_push_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, seg, p, rank, world,

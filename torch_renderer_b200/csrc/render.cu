@@ -1294,21 +1294,23 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   return TRB_OK;
 }
 
-extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view* views,
-                                   const float* verts_world, const int32_t* faces, const float* vert_colors,
-                                   const float* R, const float* T, const float* proj, const float* view_params,
-                                   const float* verts_ndc, const float* normals_raw, const float* normals,
-                                   const int64_t* pix_to_face, const float* zbuf, const float* bary,
-                                   const float* dists, const int32_t* tile_hit, const float* grad_images,
-                                   const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
-                                   float* grad_verts_world, float* grad_vert_colors, float* grad_R,
-                                   float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
-                                   const trb_uv_texture* uv, int device, trb_stream_t stream) {
+static int render_backward_impl(const trb_render_config* cfg, const trb_view* views,
+                                const float* verts_world, const int32_t* faces, const float* vert_colors,
+                                const float* R, const float* T, const float* proj, const float* view_params,
+                                const float* verts_ndc, const float* normals_raw, const float* normals,
+                                const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                                const float* dists, const int32_t* tile_hit, const float* grad_images,
+                                const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                float* grad_verts_world, float* grad_vert_colors, float* grad_R,
+                                float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
+                                const trb_uv_texture* uv, int device, trb_stream_t stream,
+                                const trb_peer_sum* peer) {
   int rc = check_render_cfg(cfg);
   if (rc != TRB_OK) return rc;
   const trb_shade_config& sc = cfg->shade;
   const int N = sc.N, H = sc.H, W = sc.W, K = sc.K;
-  if (N == 0 || cfg->max_face_count == 0) return TRB_OK;
+  // (the fused all-reduce is a collective: a rank with nothing to render cannot skip it)
+  if (N == 0 || cfg->max_face_count == 0) return peer ? TRB_ERR_BAD_ARG : TRB_OK;
   if (!views || !verts_world || !faces || !R || !T || !proj || !verts_ndc || !pix_to_face || !zbuf || !bary ||
       !dists || !tile_hit || !scratch)
     return TRB_ERR_BAD_ARG;
@@ -1320,6 +1322,20 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
     return TRB_ERR_BAD_ARG;
   if (phong && (!view_params || (!vert_colors && !use_uv))) return TRB_ERR_BAD_ARG;
   if (lit && (!normals_raw || !normals)) return TRB_ERR_BAD_ARG;
+  // multi-GPU: the shared gradients (vertices, then vertex colours) leave for the peers from inside the tail kernel
+  ArPush push;
+  if (peer) {
+    float* segs[2]; int64_t cnts[2]; int ns = 0;
+    if (grad_verts_world) { segs[ns] = grad_verts_world; cnts[ns++] = 3 * cfg->num_world_verts; }
+    if (grad_vert_colors && phong && !use_uv) { segs[ns] = grad_vert_colors; cnts[ns++] = 3 * cfg->num_world_verts; }
+    if (ns == 0 || !peer->epochs || !peer->error_flag || !peer->done_counter) return TRB_ERR_BAD_ARG;
+    long long total = 0;
+    rc = ar_fill_tables(segs, cnts, ns, peer->host_peer_inbox, peer->capacity_floats, peer->rank, peer->world,
+                        push.seg, push.peers, total);
+    if (rc != TRB_OK) return rc;
+    push.capacity = peer->capacity_floats; push.rank = peer->rank; push.world = peer->world;
+    push.epochs = peer->epochs; push.error = peer->error_flag; push.done = peer->done_counter;
+  }
   TRB_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_ndc = (size_t)cfg->num_ndc_verts, V = (size_t)cfg->num_world_verts;
@@ -1371,9 +1387,44 @@ extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view*
   rc = run_backward_post(cfg, views, verts_world, faces, R, T, proj, view_params, g_vp, normals_raw, g_ndc4,
                          a.g_verts_world ? g_world4 : nullptr, a.g_colors ? g_col4 : nullptr,
                          normals_chain ? g_norm4 : nullptr, grad_verts_world, grad_vert_colors, grad_R, grad_T,
-                         grad_proj, geom, cam_chain, normals_chain, st);
+                         grad_proj, geom, cam_chain, normals_chain, st, peer ? &push : nullptr);
   if (rc != TRB_OK) return rc;
   return TRB_OK;
+}
+
+extern "C" int trb_render_backward(const trb_render_config* cfg, const trb_view* views,
+                                   const float* verts_world, const int32_t* faces, const float* vert_colors,
+                                   const float* R, const float* T, const float* proj, const float* view_params,
+                                   const float* verts_ndc, const float* normals_raw, const float* normals,
+                                   const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                                   const float* dists, const int32_t* tile_hit, const float* grad_images,
+                                   const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                   float* grad_verts_world, float* grad_vert_colors, float* grad_R,
+                                   float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
+                                   const trb_uv_texture* uv, int device, trb_stream_t stream) {
+  return render_backward_impl(cfg, views, verts_world, faces, vert_colors, R, T, proj, view_params, verts_ndc,
+                              normals_raw, normals, pix_to_face, zbuf, bary, dists, tile_hit, grad_images, grad_zbuf,
+                              grad_bary, grad_dists, grad_verts_world, grad_vert_colors, grad_R, grad_T, grad_proj,
+                              grad_view_params, scratch, uv, device, stream, nullptr);
+}
+
+extern "C" int trb_render_backward_allreduce(const trb_render_config* cfg, const trb_view* views,
+                                             const float* verts_world, const int32_t* faces,
+                                             const float* vert_colors, const float* R, const float* T,
+                                             const float* proj, const float* view_params, const float* verts_ndc,
+                                             const float* normals_raw, const float* normals,
+                                             const int64_t* pix_to_face, const float* zbuf, const float* bary,
+                                             const float* dists, const int32_t* tile_hit, const float* grad_images,
+                                             const float* grad_zbuf, const float* grad_bary, const float* grad_dists,
+                                             float* grad_verts_world, float* grad_vert_colors, float* grad_R,
+                                             float* grad_T, float* grad_proj, float* grad_view_params, float* scratch,
+                                             const trb_uv_texture* uv, const trb_peer_sum* host_peer, int device,
+                                             trb_stream_t stream) {
+  if (!host_peer) return TRB_ERR_BAD_ARG;
+  return render_backward_impl(cfg, views, verts_world, faces, vert_colors, R, T, proj, view_params, verts_ndc,
+                              normals_raw, normals, pix_to_face, zbuf, bary, dists, tile_hit, grad_images, grad_zbuf,
+                              grad_bary, grad_dists, grad_verts_world, grad_vert_colors, grad_R, grad_T, grad_proj,
+                              grad_view_params, scratch, uv, device, stream, host_peer);
 }
 
 #ifdef TRB_KN_STATS

@@ -4,6 +4,7 @@
 #include "raster_internal.cuh"
 #include "shade_math.cuh"
 #include "trb_internal.cuh"
+#include "allreduce.cuh"
 
 namespace trb {
 
@@ -84,7 +85,7 @@ int run_backward_post(const trb_render_config* cfg, const trb_view* views, const
                       const float* view_params, const float* g_view_params, const float* normals_raw,
                       const float4* g_ndc4, const float4* g_world4, const float4* g_col4, const float4* g_norm4,
                       float* grad_verts, float* grad_colors, float* grad_R, float* grad_T, float* grad_proj,
-                      bool geom, bool cam_chain, bool normals_chain, cudaStream_t st);
+                      bool geom, bool cam_chain, bool normals_chain, cudaStream_t st, const ArPush* push = nullptr);
 
 // Fine pass of one batch: the K == 1 strip kernel (render.cu) or the K > 1 kernel (render_kn.cu).
 int launch_render_fine(int shader, int light, int N, cudaStream_t st, const FineArgs& a);

@@ -142,6 +142,9 @@ struct PostArgs {
   float* grad_verts; float* grad_colors; float* grad_R; float* grad_T; float* grad_proj;
   int N, perspective, bpv; long long V, F;
   int b_transform, b_cam, b_final;  // cumulative block boundaries of the roles
+  int b_push;                       // first block of the push role (= number of blocks of roles 0-3); grid size when off
+  int has_push;
+  ArPush push;
 };
 
 // Everything after the fused backward kernel, in one launch (all accumulation is atomic):
@@ -149,10 +152,27 @@ struct PostArgs {
 //  role 1  camera centre -> R, T;
 //  role 2  per vertex: unpack the float4 accumulators of the world-position path and of the colours;
 //  role 3  per face: gradient of the unit vertex normals through the normalisation (recomputed per corner
-//          instead of a separate per-vertex pass) and through the area-weighted face normal.
+//          instead of a separate per-vertex pass) and through the area-weighted face normal;
+//  role 4  (multi-GPU, opt-in: trb_render_backward_allreduce) the LAST blocks of the grid push this rank's finished
+//          grad_verts / grad_colors into the peers' inboxes (allreduce.cuh) as soon as every block of roles 0-3 has
+//          signed off on a device counter: the gradients leave for the peers from inside the kernel that finishes
+//          them, and the NVLink flight overlaps this kernel's drain and the launch of the receive kernel.
+//          Blocks are dispatched in index order, so every block the push role waits for is resident or finished
+//          when it starts; the wait is bounded all the same (error flag instead of a hang).
 __global__ void __launch_bounds__(256) post_backward_kernel(const PostArgs p) {
   pdl_wait();
   const int b = blockIdx.x;
+  if (p.has_push && b >= p.b_push) {
+    const unsigned epoch = p.push.epochs[b - p.b_push] + 1u;   // fetched while the counter is still moving
+    if (threadIdx.x == 0) {
+      unsigned spins = 0;
+      while (ld_acquire_gpu_u32(p.push.done) < (unsigned)p.b_push)
+        if (++spins > (1u << 24)) { atomicExch(p.push.error, 1); break; }
+    }
+    __syncthreads();
+    ar_push_block(p.push.seg, p.push.peers, p.push.rank, p.push.world, p.push.capacity, epoch, b - p.b_push);
+    return;
+  }
   if (b < p.b_transform) {
     const int n = b / p.bpv, bx = b - n * p.bpv;
     const trb_view vd = p.views[n];
@@ -165,30 +185,38 @@ __global__ void __launch_bounds__(256) post_backward_kernel(const PostArgs p) {
     if (n < p.N) camera_center_backward_one(p.R, p.view_params, p.g_view_params, p.grad_R, p.grad_T, n);
   } else if (b < p.b_final) {
     const long long v = (long long)(b - p.b_cam) * 256 + threadIdx.x;
-    if (v >= p.V) return;
-    if (p.g_world4 && p.grad_verts) {
-      const float4 g = p.g_world4[v];
-      atomicAdd(p.grad_verts + 3 * v, g.x); atomicAdd(p.grad_verts + 3 * v + 1, g.y);
-      atomicAdd(p.grad_verts + 3 * v + 2, g.z);
-    }
-    if (p.g_col4 && p.grad_colors) {
-      const float4 g = p.g_col4[v];
-      p.grad_colors[3 * v] += g.x; p.grad_colors[3 * v + 1] += g.y; p.grad_colors[3 * v + 2] += g.z;
+    if (v < p.V) {
+      if (p.g_world4 && p.grad_verts) {
+        const float4 g = p.g_world4[v];
+        atomicAdd(p.grad_verts + 3 * v, g.x); atomicAdd(p.grad_verts + 3 * v + 1, g.y);
+        atomicAdd(p.grad_verts + 3 * v + 2, g.z);
+      }
+      if (p.g_col4 && p.grad_colors) {
+        const float4 g = p.g_col4[v];
+        p.grad_colors[3 * v] += g.x; p.grad_colors[3 * v + 1] += g.y; p.grad_colors[3 * v + 2] += g.z;
+      }
     }
   } else {
     const long long f = (long long)(b - p.b_final) * 256 + threadIdx.x;
-    if (f >= p.F) return;
-    const int ids[3] = {__ldg(p.faces + 3 * f), __ldg(p.faces + 3 * f + 1), __ldg(p.faces + 3 * f + 2)};
-    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    if (f < p.F) {
+      const int ids[3] = {__ldg(p.faces + 3 * f), __ldg(p.faces + 3 * f + 1), __ldg(p.faces + 3 * f + 2)};
+      float gx = 0.0f, gy = 0.0f, gz = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float4 g = p.g_norm4[ids[k]];
-      const float* r = p.normals_raw + 3 * (size_t)ids[k];
-      float ox, oy, oz;
-      normalize_row_backward(r[0], r[1], r[2], g.x, g.y, g.z, ox, oy, oz);
-      gx += ox; gy += oy; gz += oz;
+      for (int k = 0; k < 3; ++k) {
+        const float4 g = p.g_norm4[ids[k]];
+        const float* r = p.normals_raw + 3 * (size_t)ids[k];
+        float ox, oy, oz;
+        normalize_row_backward(r[0], r[1], r[2], g.x, g.y, g.z, ox, oy, oz);
+        gx += ox; gy += oy; gz += oz;
+      }
+      face_normal_backward_apply(p.verts, ids[0], ids[1], ids[2], gx, gy, gz, p.grad_verts);
     }
-    face_normal_backward_apply(p.verts, ids[0], ids[1], ids[2], gx, gy, gz, p.grad_verts);
+  }
+  if (p.has_push) {
+    // this block's share of the gradients is in L2 before the counter moves (fence, then barrier, then one atomic)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.push.done, 1u);
   }
 }
 
@@ -197,8 +225,8 @@ int run_backward_post(const trb_render_config* cfg, const trb_view* views, const
                       const float* view_params, const float* g_view_params, const float* normals_raw,
                       const float4* g_ndc4, const float4* g_world4, const float4* g_col4, const float4* g_norm4,
                       float* grad_verts, float* grad_colors, float* grad_R, float* grad_T, float* grad_proj,
-                      bool geom, bool cam_chain, bool normals_chain, cudaStream_t st) {
-  PostArgs p;
+                      bool geom, bool cam_chain, bool normals_chain, cudaStream_t st, const ArPush* push) {
+  PostArgs p = PostArgs();
   p.verts = verts_world; p.faces = faces; p.R = R; p.T = T; p.proj = proj; p.views = views;
   p.view_params = view_params; p.g_view_params = g_view_params; p.normals_raw = normals_raw;
   p.g_ndc4 = g_ndc4; p.g_world4 = g_world4; p.g_col4 = g_col4; p.g_norm4 = g_norm4;
@@ -210,9 +238,17 @@ int run_backward_post(const trb_render_config* cfg, const trb_view* views, const
   p.b_transform = geom ? p.N * p.bpv : 0;
   p.b_cam = p.b_transform + (cam_chain ? ceil_div(p.N, 256) : 0);
   p.b_final = p.b_cam + (finalize ? (int)ceil_div64(p.V, 256) : 0);
-  const int total = p.b_final + (normals_chain ? (int)ceil_div64(p.F, 256) : 0);
+  int total = p.b_final + (normals_chain ? (int)ceil_div64(p.F, 256) : 0);
+  p.b_push = total;
+  p.has_push = 0;
+  if (push) {
+    p.has_push = 1;
+    p.push = *push;
+    total += (int)ceil_div64(push->seg.start[push->seg.count], kArChunk);
+  }
   if (total == 0) return TRB_OK;
   TRB_CUDA_TRY(launch_pdl(post_backward_kernel, dim3(total), dim3(256), 0, st, p));
+  if (push) return launch_allreduce_receive(*push, st);
   return TRB_OK;
 }
 

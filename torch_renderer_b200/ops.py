@@ -725,23 +725,44 @@ class _RenderFn(torch.autograd.Function):
                                 g_tex.data_ptr() if n_tex else 0, tex_map.shape[0], tex_map.shape[1])
         f32 = lambda t: None if t is None else _f32c(t)
         want_vp = vp is not None
-        with _timed("render_backward", dev):
-            check(_lib.lib().trb_render_backward(
-                ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
+        want_cols = need[1] and colors is not None
+        args = (ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
                 _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, p_p2f, p_zbuf,
                 p_bary, p_dists, p_hit, _ptr(f32(g_images) if shader != _lib.SHADER_NONE else None),
                 _ptr(f32(g_zbuf)), _ptr(f32(g_bary)), _ptr(f32(g_dists)),
-                _ptr(g_verts if need[0] else None), _ptr(g_cols if (need[1] and colors is not None) else None),
+                _ptr(g_verts if need[0] else None), _ptr(g_cols if want_cols else None),
                 _ptr(g_R if need[2] else None), _ptr(g_T if need[3] else None), _ptr(g_proj if need[4] else None),
-                _ptr(g_vp if want_vp else None), _ptr(scratch), None if uv is None else ctypes.byref(uv),
-                dev.index, _stream(dev)), "render backward")
-        _bump(2)  # fused backward, post
+                _ptr(g_vp if want_vp else None), _ptr(scratch), None if uv is None else ctypes.byref(uv))
+        # multi-GPU (parallel.fused_backward_allreduce): the sum of the view-shared gradients over the ranks is part
+        # of this backward -- pushed to the peers by the tail kernel, summed by a short receive kernel
+        peer = _backward_peer_sum
+        fused = peer is not None and (need[0] or want_cols)
+        with _timed("render_backward", dev):
+            if fused:
+                n_shared = V * 3 * (int(bool(need[0])) + int(bool(want_cols) and shader in (
+                    _lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG) and tex_map is None))
+                check(_lib.lib().trb_render_backward_allreduce(*args, ctypes.byref(peer.peer_sum(n_shared, dev)),
+                                                               dev.index, _stream(dev)), "render backward")
+                peer.count_call()
+            else:
+                check(_lib.lib().trb_render_backward(*args, dev.index, _stream(dev)), "render backward")
+        _bump(3 if fused else 2)  # fused backward, post (+ receive)
         return (g_verts.view(V, 3) if need[0] else None,
                 g_cols.view(V, 3) if (need[1] and colors is not None) else None,
                 g_tex.view(tex_map.shape) if n_tex else None,
                 g_R.view(N, 3, 3) if need[2] else None, g_T.view(N, 3) if need[3] else None,
                 g_proj.view(N, 4) if need[4] else None,
                 g_vp.view(N, _lib.VIEW_PARAM_STRIDE) if (need[5] and want_vp) else None, None, None, None)
+
+
+# The PeerAllReduce (parallel.py) the next fused backwards push their shared gradients through; None = off.  A plain
+# module global: autograd runs backward on its own thread.
+_backward_peer_sum = None
+
+
+def set_backward_peer_sum(peer) -> None:
+    global _backward_peer_sum
+    _backward_peer_sum = peer
 
 
 def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec: dict, tex_map=None):

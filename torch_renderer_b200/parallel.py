@@ -15,6 +15,7 @@ B200-native addition BASELINE.json's north_star asks for.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -73,6 +74,9 @@ class PeerAllReduce:
         self.peer_inbox = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         self.epochs = torch.zeros(_lib.lib().trb_allreduce_grid(self.capacity), dtype=torch.int32, device=device)
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)   # block counter of the fused backward tail
+        self._peer_sum = _lib.PeerSum(ctypes.cast(self.peer_inbox, ctypes.c_void_p), self.capacity, self.rank,
+                                      self.world, self.epochs.data_ptr(), self.error.data_ptr(), self.done.data_ptr())
         self.calls = 0     # allreduce_shared_grads reads the error flag every _CHECK_EVERY calls
 
     def __call__(self, grads: Sequence[torch.Tensor]) -> None:
@@ -88,6 +92,20 @@ class PeerAllReduce:
             seg, cnt, n, self.peer_inbox, self.capacity, self.rank, self.world, self.epochs.data_ptr(),
             self.error.data_ptr(), self.device.index, torch._C._cuda_getCurrentRawStream(self.device.index)),
             "peer all-reduce")
+
+    def peer_sum(self, n_floats: int, device: torch.device):
+        """The ``trb_peer_sum`` record for ``trb_render_backward_allreduce`` (ops._RenderFn.backward)."""
+        if n_floats > self.capacity:
+            raise ValueError(f"fused_backward_allreduce: {n_floats} shared gradient values do not fit the "
+                             f"{self.capacity}-value inbox; use allreduce_shared_grads after the backward instead")
+        if device != self.device:
+            raise ValueError("fused_backward_allreduce: the render runs on another device than the inbox")
+        return self._peer_sum
+
+    def count_call(self) -> None:
+        self.calls += 1
+        if self.calls % _CHECK_EVERY == 0 and not torch.cuda.is_current_stream_capturing():
+            self.check()
 
     def check(self) -> None:
         """Raises if a peer's data did not arrive (synchronises; call outside timed regions)."""
@@ -129,6 +147,43 @@ def check_peer_allreduce() -> None:
     for v in _peer_allreduce.values():
         if v not in (None, False):
             v.check()
+
+
+@contextlib.contextmanager
+def fused_backward_allreduce(device=None, group=None):
+    """Inside this context the backward of every fused render (``MeshRenderer`` / ``MeshRendererWithFragments`` /
+    ``MeshRasterizer`` on the fused path) returns the gradients of the mesh's vertices and vertex colours already
+    SUMMED over the ranks: the kernel that finalises them pushes them into the peers' memory from its last blocks
+    and a short receive kernel adds what arrives (``trb_render_backward_allreduce``, include/trb.h) -- the step's one
+    exchange rides on the tail of the backward instead of following it.  Per-view gradients (R, T, camera and
+    light parameters) and UV-map gradients stay local.
+
+        with fused_backward_allreduce() as fused:
+            loss.backward()
+        if not fused:                                   # no peer memory on this box / group: NCCL afterwards
+            allreduce_shared_grads([verts.grad, colors.grad])
+
+    Yields False (and changes nothing) when torch.distributed is not initialised, the world size is 1, the backend
+    is not NCCL or peer memory cannot be set up (agreed on collectively).  Every rank must run the same renders in
+    the same order; the mesh must be replicated (same vertex count on every rank, 6 V values <= 65,536) and every
+    rank's batch non-empty.  Gradients that reach the shared parameters by other routes (regularisers computed
+    identically on every rank) are not touched -- each rank ends with sum-over-ranks(render) + its own regulariser,
+    the same tensor everywhere."""
+    from . import ops
+    peer = None
+    if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+            and dist.get_backend(group) == "nccl" and torch.cuda.is_available()
+            and not os.environ.get("TRB_NCCL_ALLREDUCE")):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        peer = _get_peer_allreduce(1, dev, group)
+    if peer is None:
+        yield False
+        return
+    ops.set_backward_peer_sum(peer)
+    try:
+        yield True
+    finally:
+        ops.set_backward_peer_sum(None)
 
 
 def allreduce_shared_grads(tensors: Sequence[Optional[torch.Tensor]], group=None, async_op: bool = False):

@@ -234,8 +234,10 @@ def run_ours(args):
                 images.backward(grad_img)
         else:
             images.backward(grad_img)
-        # the step's result read back by the host: mean alpha (silhouette coverage) ...
-        dev_out[-1:].copy_(images.detach()[..., 3].mean().reshape(1))
+        # the step's result read back by the host: mean alpha (silhouette coverage), from the per-view sums the fine
+        # kernel accumulates while it writes the pixels (images.alpha_sum; a second pass over the 268 MB image batch
+        # -- images[..., 3].mean() -- costs 63 us on its own, profiles/r02_mean_alpha_cost.json) ...
+        dev_out[-1:].copy_((images.alpha_sum.sum() / float(N * H * W)).reshape(1))
 
     def readback_e2e():         # ... and every gradient (after the all-reduce of the shared ones)
         torch.cat([p.grad.reshape(-1) for p in params], out=dev_out[:-1])
@@ -430,6 +432,13 @@ def run_ours(args):
         run_e2e()
     ms_e2e = timed(run_e2e, args.steps)[0] / args.steps
     e2e_value = world * N / (ms_e2e / 1e3)
+    # the metric the host read back (fused per-view alpha sums) against a second pass over the image batch
+    torch.cuda.synchronize()
+    e2e_metric = float(host_out[-1].item())
+    with torch.no_grad():
+        metric_ref = float(renderer(meshes, R=Rd, T=Td)[..., 3].double().mean().item())
+    if not abs(e2e_metric - metric_ref) <= 1e-4 * abs(metric_ref) + 1e-7:
+        raise SystemExit(f"bench: the fused mean-alpha metric {e2e_metric} disagrees with images[..., 3].mean() = {metric_ref}")
     h2d = host_in.numel() * 4
     d2h = host_out.numel() * 4
 
@@ -521,7 +530,11 @@ def run_ours(args):
                        "near_plane": "z_clip 0.5 checked once before the timed region (no vertex behind it); not re-asked per step",
                        "launch_mode": mode_device, "e2e_launch_mode": mode_e2e},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e, 4)},
+                    "ms_per_step": round(ms_e2e, 4),
+                    "result_read_back": {"what": "every gradient + mean alpha of the image batch; the mean comes from the "
+                                                 "per-view alpha sums the fine kernel accumulates (images.alpha_sum), "
+                                                 "checked here against a second pass over the images",
+                                         "mean_alpha": e2e_metric, "images_mean_alpha": metric_ref}},
             "gpu_launches": launches,
             "timing": {"protocol": f"median of {args.repeats} repeats of {args.steps} steps, CUDA events on the launching "
                                    "stream, barrier + synchronize around every repeat, max over ranks",

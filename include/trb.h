@@ -41,7 +41,8 @@
 extern "C" {
 #endif
 
-/* 5 (round 2): trb_render_backward_allreduce + trb_peer_sum (the all-reduce's push half inside the backward tail).
+/* 5 (round 2): trb_render_backward_allreduce + trb_peer_sum (the all-reduce's push half inside the backward tail);
+ * per-view alpha sums at the end of hit_pixels (trb_render_sizes reports the new length).
  * 4 (round 2): trb_render_config.sparse_fragments (was `reserved`), layer counts appended to the covered-pixel list
  * (trb_render_sizes reports the new length), trb_points_raster_forward_binned / _workspace_bytes,
  * trb_allreduce_set_timing. */
@@ -284,7 +285,10 @@ int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes,
  * Outputs: verts_ndc f32[num_ndc_verts,3]; normals_raw, normals f32[num_world_verts,3] (Phong only);
  * Fragments; images f32[N,H,W,4] (NULL when shader is NONE); hit_pixels i32[hit_pixels_len]: [0] = number of
  * covered pixels C, [1 .. 1+C) their linear pixel ids (tile by tile), and for faces_per_pixel > 1
- * [1+N*H*W .. 1+N*H*W+C) the number of layers each of them got -- the list the fused backward walks. */
+ * [1+N*H*W .. 1+N*H*W+C) the number of layers each of them got -- the list the fused backward walks.  The LAST N
+ * words are f32: the sum of the alpha channel images[n,:,:,3] of every view, accumulated by the fine kernel as it
+ * writes the pixels (a coverage metric / silhouette-area term that costs no second pass over the image; float atomics:
+ * the last bits depend on the order of arrival).  Untouched when shader is NONE. */
 int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        const float* verts_world, const int32_t* faces, const float* vert_colors,
                        const float* R, const float* T, const float* proj, float* view_params,

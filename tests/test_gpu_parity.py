@@ -837,6 +837,10 @@ def test_image_only_renderer_sparse_fragments_equal_dense(shader_kind, K, blur, 
             junk = torch.full((N * size[0] * size[1] * K * 8,), float("nan"), device=DEV)
             del junk
             img = trb.MeshRenderer(rast, shader)(mesh, R=R, T=T)
+        # the fine kernel's own per-view sums of the alpha channel (ops.render: images.alpha_sum), both layouts
+        want_alpha = img.detach()[..., 3].double().sum((1, 2))
+        assert img.alpha_sum.shape == (N,) and not img.alpha_sum.requires_grad
+        assert ((img.alpha_sum.double() - want_alpha).abs() <= 1e-5 * want_alpha.abs() + 1e-4).all()
         torch.manual_seed(2)
         w = torch.rand(img.shape, device=DEV)
         (img * w).sum().backward()

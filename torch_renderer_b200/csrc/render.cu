@@ -556,6 +556,19 @@ __device__ __forceinline__ void raster_tile_k1(const FineArgs& a, int t) {
     }
   }
   st_cs(reinterpret_cast<float4*>(a.images) + hpix, out);
+  if (a.alpha_sum != nullptr) {
+    // per-view sum of the alpha channel (a coverage metric / silhouette-area loss without re-reading the image):
+    // lanes [0, wcnt) of this warp got here
+    const int wcnt = min(32, s_nhit - warp * 32);
+    const unsigned m = wcnt >= 32 ? 0xffffffffu : ((1u << wcnt) - 1u);
+    float asum = out.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_down_sync(m, asum, o);
+      if (lane + o < wcnt) asum += t;
+    }
+    if (lane == 0) atomicAdd(a.alpha_sum + n, asum);
+  }
   K1_T(5);
 }
 
@@ -1223,7 +1236,8 @@ extern "C" int trb_render_sizes(const trb_render_config* cfg, size_t* workspace_
   const TileGrid tg = make_tile_grid(s.H, s.W, s.K);
   if (workspace_bytes) *workspace_bytes = make_ws_layout(s.N, tg, cfg->pair_capacity).total;
   // hit_pixels = [count, pixel ids ... (N*H*W slots), layer counts ... (N*H*W slots, faces_per_pixel > 1 only)]
-  if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W * (s.K > 1 ? 2 : 1) + 1;
+  // count, pixel ids, (K > 1) layer counts, and N floats: the per-view sums of the alpha channel
+  if (num_tiles) *num_tiles = (int64_t)s.N * s.H * s.W * (s.K > 1 ? 2 : 1) + 1 + s.N;
   // backward scratch: float4 accumulators for grad NDC verts [num_ndc_verts], world verts, colours and
   // normals [V each], then grad of the raw normals [V,3]
   if (backward_scratch_floats) *backward_scratch_floats = 4 * cfg->num_ndc_verts + 15 * cfg->num_world_verts;
@@ -1276,6 +1290,8 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
   a.p2f = (long long*)pix_to_face; a.zbuf = zbuf; a.bary = bary; a.dists = dists; a.images = images;
   a.hit_pixels = tile_hit;
   a.hit_counts = K > 1 ? tile_hit + 1 + (size_t)N * H * W : nullptr;
+  a.alpha_sum = sc.shader != TRB_SHADER_NONE
+                    ? reinterpret_cast<float*>(tile_hit + 1 + (size_t)N * H * W * (K > 1 ? 2 : 1)) : nullptr;
   a.view_params = view_params; a.verts_world = verts_world; a.normals = normals; a.colors = vert_colors;
   a.sigma = sc.sigma; a.gamma = sc.gamma; a.bg0 = sc.background[0]; a.bg1 = sc.background[1];
   a.bg2 = sc.background[2];

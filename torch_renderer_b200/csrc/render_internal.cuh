@@ -19,6 +19,7 @@ struct FineArgs {
   float sigma, gamma, bg0, bg1, bg2;
   UvTex uv;  // uv.map != nullptr: TexturesUV instead of per-vertex colours
   int sparse;  // trb_render_config::sparse_fragments: Fragments only for covered pixels (+ a -1 terminator layer)
+  float* alpha_sum;  // f32[N] behind the covered-pixel list: per-view sum of images[..., 3] (zeroed by prep_kernel)
 };
 
 // Appends the linear indices of the pixels of this CTA that got at least one face to the global

@@ -612,19 +612,28 @@ render_fine_kn_kernel(const FineArgs a) {
     }
   }
   const int cnt_total = total;
-  if (!live || slice != 0) return;
-  float4 out;
-  if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
-    out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
-  } else if (SHADER == TRB_SHADER_HARD_PHONG) {
-    out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt_total > 0 ? 1.0f : 0.0f);
-  } else {
-    const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
-    const float inv = 1.0f / (wsum + delta);
-    out = make_float4((acc.x + delta * a.bg0) * inv, (acc.y + delta * a.bg1) * inv,
-                      (acc.z + delta * a.bg2) * inv, 1.0f - alpha);
+  const bool writer = live && slice == 0;
+  float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (writer) {
+    if (SHADER == TRB_SHADER_SOFT_SILHOUETTE) {
+      out = make_float4(1.0f, 1.0f, 1.0f, 1.0f - alpha);
+    } else if (SHADER == TRB_SHADER_HARD_PHONG) {
+      out = make_float4(hard_c.x, hard_c.y, hard_c.z, cnt_total > 0 ? 1.0f : 0.0f);
+    } else {
+      const float delta = fmaxf(expf((eps - zmax) / a.gamma), eps);
+      const float inv = 1.0f / (wsum + delta);
+      out = make_float4((acc.x + delta * a.bg0) * inv, (acc.y + delta * a.bg1) * inv,
+                        (acc.z + delta * a.bg2) * inv, 1.0f - alpha);
+    }
+    st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
   }
-  st_cs(reinterpret_cast<float4*>(a.images) + pix, out);
+  if (a.alpha_sum != nullptr) {
+    // per-view sum of the alpha channel (every thread of the CTA is here)
+    float asum = writer ? out.w : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    if (lane == 0 && asum != 0.0f) atomicAdd(a.alpha_sum + n, asum);
+  }
 }
 
 template <int LT>

@@ -16,6 +16,7 @@ struct PrepArgs {
   int* zero_a; long long n_zero_a;       // binning counters (ints)
   float* zero_b; long long n_zero_b;     // raw vertex normals
   int* zero_c;                           // covered-pixel counter
+  float* zero_d; int n_zero_d;           // per-view alpha sums behind the covered-pixel list
 };
 
 // role 0: world -> NDC of every (view, vertex) + the camera centre of every view; role 1: zero the
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs p) {
   for (long long i = i0; i < p.n_zero_a; i += stride) p.zero_a[i] = 0;
   for (long long i = i0; i < p.n_zero_b; i += stride) p.zero_b[i] = 0.0f;
   if (i0 == 0 && p.zero_c) *p.zero_c = 0;
+  if (p.zero_d) for (long long i = i0; i < p.n_zero_d; i += stride) p.zero_d[i] = 0.0f;
 }
 
 struct BinArgs {
@@ -106,6 +108,9 @@ int run_forward_stages(const trb_render_config* cfg, const trb_view* views, cons
   p.zero_a = (int*)wsb; p.n_zero_a = (long long)(ws.offset / 4);  // header, tile_count, tile_fill
   p.zero_b = lit ? normals_raw : nullptr; p.n_zero_b = lit ? 3 * V : 0;
   p.zero_c = hit_pixels;
+  p.zero_d = (hit_pixels && sc.shader != TRB_SHADER_NONE)
+                 ? reinterpret_cast<float*>(hit_pixels + 1 + (size_t)N * sc.H * sc.W * (sc.K > 1 ? 2 : 1)) : nullptr;
+  p.n_zero_d = N;
   const long long zero_words = p.n_zero_a + p.n_zero_b;
   long long bz = ceil_div64(zero_words, 256 * 4);
   if (bz < 1) bz = 1;

@@ -638,10 +638,11 @@ class _RenderFn(torch.autograd.Function):
             for nb in sizes:
                 offs.append(total)
                 total += (nb + 255) & ~255
-            plan = table._plans[plan_key] = (cfg, ws_bytes.value, n_scratch.value, tuple(offs), max(total, 256))
+            plan = table._plans[plan_key] = (cfg, ws_bytes.value, n_scratch.value, tuple(offs), max(total, 256),
+                                             max(n_tiles.value, 1))
             if len(table._plans) > 64:      # settings that change every call must not grow the memo without bound
                 table._plans.pop(next(iter(table._plans)))
-        cfg, ws_nbytes, n_scratch, offs, total = plan
+        cfg, ws_nbytes, n_scratch, offs, total, n_hit_words = plan
         uv = None
         if tex_map is not None:
             verts_uvs, faces_uvs = spec["uv"]
@@ -684,13 +685,19 @@ class _RenderFn(torch.autograd.Function):
         ctx.table, ctx.cfg, ctx.n_scratch = table, cfg, n_scratch
         ctx.token = spec.get("_token")   # Fragments cache: set once a backward has consumed this graph
         ctx.set_materialize_grads(False)
+        # per-view sums of the alpha channel, accumulated by the fine kernel behind the covered-pixel list
+        alpha_sum = None
+        if shader != _lib.SHADER_NONE:
+            o_alpha = offs[4] + (n_hit_words - N) * 4
+            alpha_sum = aux[o_alpha:o_alpha + 4 * N].view(torch.float32)
+        # (one call: a second mark_non_differentiable replaces the first)
+        ctx.mark_non_differentiable(*[t for t in (p2f, alpha_sum) if t is not None])
         if sparse:
-            return images, None, None, None, None
-        ctx.mark_non_differentiable(p2f)
-        return images, p2f, zbuf, bary, dists
+            return images, None, None, None, None, alpha_sum
+        return images, p2f, zbuf, bary, dists, alpha_sum
 
     @staticmethod
-    def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists):
+    def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists, _g_alpha_sum=None):
         verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists, tex_map = ctx.saved_tensors[:13]
         o_ndc, o_nraw, o_nrm, o_hit, phong = ctx.aux_offsets
         base = aux.data_ptr()
@@ -770,7 +777,13 @@ def render(verts, colors, R, T, proj, view_params, faces, table: ViewTable, spec
     the texture is a UV map sampled in the kernels; ``spec["uv"]`` = (verts_uvs f32 [Vt,2], faces_uvs i32 [F,3])."""
     if spec["K"] > _lib.MAX_FACES_PER_PIXEL:
         raise ValueError(f"faces_per_pixel must be <= {_lib.MAX_FACES_PER_PIXEL}")
-    return _RenderFn.apply(verts, colors, tex_map, R, T, proj, view_params, faces, table, spec)
+    images, p2f, zbuf, bary, dists, alpha_sum = _RenderFn.apply(verts, colors, tex_map, R, T, proj, view_params, faces,
+                                                                table, spec)
+    if alpha_sum is not None:
+        # f32 [N]: images[n, :, :, 3].sum(), accumulated by the kernel that wrote the pixels (no second pass over the
+        # image; float atomics, so the last bits vary from run to run).  Not differentiable: a statistic, not a loss.
+        images.alpha_sum = alpha_sum
+    return images, p2f, zbuf, bary, dists
 
 
 # --------------------------------------------------------------------------------------------

@@ -765,9 +765,9 @@ def run_c5_spec(dev, world, rank, args, peak, barrier):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/);
 # filled in after each profiling pass, None until a capture of that kernel exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r02_ncu_c2_sparse.txt (ncu --set full, one launch each, 64 views of C2, sparse Fragments)
-    "render_fine_kernel": 231_038_464,      # 6.81 MB read + 224.23 MB written (the 268 MB image, tail still in L2)
-    "render_backward_kernel": 22_635_520,   # only covered pixels (1.9% of the image) are re-read
+    # profiles/r02_ncu_c2_head.txt (ncu --set full at HEAD, one launch each, 64 views of C2, sparse Fragments)
+    "render_fine_kernel": 228_833_024,      # 6.82 MB read + 222.02 MB written (the 268 MB image, tail still in L2)
+    "render_backward_kernel": 22_642_432,   # only covered pixels (1.9% of the image) are re-read
 }
 
 

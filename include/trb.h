@@ -42,7 +42,8 @@ extern "C" {
 #endif
 
 /* 5 (round 2): trb_render_backward_allreduce + trb_peer_sum (the all-reduce's push half inside the backward tail);
- * per-view alpha sums at the end of hit_pixels (trb_render_sizes reports the new length).
+ * per-view alpha sums at the end of hit_pixels (trb_render_sizes reports the new length); trb_render_extras
+ * (trb_render_forward takes one more argument).
  * 4 (round 2): trb_render_config.sparse_fragments (was `reserved`), layer counts appended to the covered-pixel list
  * (trb_render_sizes reports the new length), trb_points_raster_forward_binned / _workspace_bytes,
  * trb_allreduce_set_timing. */
@@ -84,7 +85,8 @@ typedef struct trb_view {
 int trb_abi_version(void);
 const char* trb_status_string(int status);
 int trb_last_cuda_error(void);
-/* sizeof(trb_view | trb_shade_config | trb_render_config | trb_uv_texture) for which = 0 | 1 | 2 | 3 as compiled into the
+/* sizeof(trb_view | trb_shade_config | trb_render_config | trb_uv_texture | trb_peer_sum | trb_render_extras) for
+ * which = 0 | 1 | 2 | 3 | 4 | 5 as compiled into the
  * library: bindings compare it with their own layout and refuse a stale build. */
 int trb_abi_struct_size(int which);
 
@@ -279,6 +281,18 @@ typedef struct trb_uv_texture {
   int32_t map_h, map_w;
 } trb_uv_texture;
 
+/* Optional work folded into the forward's FIRST kernel, so that a step has no copy / fill nodes of its own (host
+ * struct, device pointers; NULL / 0 switches a member off; host_extras itself may be NULL):
+ *   view_params_src  f32[N,20]: copied into `view_params` before anything reads it -- the caller keeps its (cached)
+ *                    parameter block untouched although the call writes the camera centres into `view_params`;
+ *   zero_buffer      f32[zero_count]: zero-filled -- meant for the ONE allocation that will hold the backward's
+ *                    gradient outputs and scratch (then trb_render_backward needs no memset before it). */
+typedef struct trb_render_extras {
+  const float* view_params_src;
+  float* zero_buffer;
+  int64_t zero_count;
+} trb_render_extras;
+
 int trb_render_sizes(const trb_render_config* host_cfg, size_t* workspace_bytes, int64_t* hit_pixels_len,
                      int64_t* backward_scratch_floats);
 /* view_params f32[N,20] is in/out (camera centre filled in when camera_center_from_rt).
@@ -296,7 +310,7 @@ int trb_render_forward(const trb_render_config* host_cfg, const trb_view* views,
                        float* zbuf, float* bary, float* dists, float* images, int32_t* hit_pixels,
                        void* workspace, size_t workspace_bytes, int32_t* stats,
                        const trb_uv_texture* host_uv /* NULL unless shade.texture_mode == TRB_TEX_UV */,
-                       int device, trb_stream_t stream);
+                       const trb_render_extras* host_extras /* may be NULL */, int device, trb_stream_t stream);
 /* grad_images may be NULL (shader NONE); grad_zbuf / grad_bary / grad_dists are optional extra
  * upstream gradients on the Fragments.  Every grad_* output is ACCUMULATED into (caller zeroes;
  * any may be NULL); `scratch` is zeroed by the call unless cfg->scratch_is_zeroed. */

@@ -247,9 +247,9 @@ def test_allreduce_and_uv_entry_points_reject_bad_arguments_without_gpu():
     cfg.shade.sigma = cfg.shade.gamma = 1e-4
     cfg.max_face_count = cfg.max_vert_count = 1
     args = [8] * 18
-    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, None, 0, None) == _lib.TRB_ERR_BAD_ARG
     cfg.shade.texture_mode = 7
-    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, 0, None) == _lib.TRB_ERR_BAD_ARG
+    assert L.trb_render_forward(ctypes.byref(cfg), *args, 1024, 8, None, None, 0, None) == _lib.TRB_ERR_BAD_ARG
     assert L.trb_abi_struct_size(3) == ctypes.sizeof(_lib.UvTexture)
 
 

@@ -49,6 +49,11 @@ class UvTexture(ctypes.Structure):
                 ("map_h", _c.c_int32), ("map_w", _c.c_int32)]
 
 
+class RenderExtras(ctypes.Structure):
+    """trb_render_extras: work folded into the forward's first kernel (parameter-block copy, zero fill)."""
+    _fields_ = [("view_params_src", _vp), ("zero_buffer", _vp), ("zero_count", _i64)]
+
+
 class PeerSum(ctypes.Structure):
     """trb_peer_sum: what trb_render_backward_allreduce needs to push the shared gradients to the peers."""
     _fields_ = [("host_peer_inbox", _vp), ("capacity_floats", _i64), ("rank", _c.c_int32), ("world", _c.c_int32),
@@ -75,7 +80,8 @@ _SIGNATURES = {
     "trb_shade_forward": [_c.POINTER(ShadeConfig)] + [_vp] * 12 + [_i, _vp],
     "trb_shade_backward": [_c.POINTER(ShadeConfig)] + [_vp] * 20 + [_i, _vp],
     "trb_render_sizes": [_c.POINTER(RenderConfig), _c.POINTER(_sz), _c.POINTER(_i64), _c.POINTER(_i64)],
-    "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _c.POINTER(UvTexture), _i, _vp],
+    "trb_render_forward": [_c.POINTER(RenderConfig)] + [_vp] * 18 + [_sz, _vp, _c.POINTER(UvTexture),
+                                                                    _c.POINTER(RenderExtras), _i, _vp],
     "trb_render_backward": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture), _i, _vp],
     "trb_render_backward_allreduce": [_c.POINTER(RenderConfig)] + [_vp] * 27 + [_c.POINTER(UvTexture),
                                                                                 _c.POINTER(PeerSum), _i, _vp],
@@ -126,7 +132,9 @@ def lib() -> ctypes.CDLL:
             raise TrbLibraryError("libtrb.so ABI version mismatch; rebuild it")
         for which, (name, size) in enumerate((("trb_view", 32), ("trb_shade_config", _c.sizeof(ShadeConfig)),
                                               ("trb_render_config", _c.sizeof(RenderConfig)),
-                                              ("trb_uv_texture", _c.sizeof(UvTexture)))):
+                                              ("trb_uv_texture", _c.sizeof(UvTexture)),
+                                              ("trb_peer_sum", _c.sizeof(PeerSum)),
+                                              ("trb_render_extras", _c.sizeof(RenderExtras)))):
             if handle.trb_abi_struct_size(which) != size:
                 raise TrbLibraryError(f"libtrb.so is stale: sizeof({name}) is {handle.trb_abi_struct_size(which)} in "
                                       f"the library but {size} in the binding; run python -m torch_renderer_b200.build")

@@ -53,6 +53,16 @@ def convert_to_tensors_and_broadcast(*args, dtype=torch.float32, device: Device 
 _MODULE_INTERNALS = frozenset(nn.Module().__dict__.keys())
 
 
+def unbind_batch(x: torch.Tensor):
+    """The rows of a padded (N, ...) tensor as a list of views.  ``x[i]`` records a SelectBackward node per row, whose
+    backward is a ``zeros`` + ``copy_`` kernel pair (the batch-of-one textures / vertices every reference script
+    builds -- ``TexturesVertex(verts_features=rgb[None])`` -- paid ~5 us per step for it); ``squeeze`` / ``unbind``
+    differentiate as views / one stack."""
+    if x.shape[0] == 1:
+        return [x.squeeze(0)]
+    return list(x.unbind(0))
+
+
 def named_tensors(obj) -> Dict[str, torch.Tensor]:
     """Every tensor-valued attribute of ``obj``: plain attributes AND the ones ``nn.Module.__setattr__`` files
     under ``_parameters`` / ``_buffers`` (``lights.location = nn.Parameter(...)``).  The memoised parameter blocks

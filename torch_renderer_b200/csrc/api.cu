@@ -16,6 +16,8 @@ extern "C" int trb_abi_struct_size(int which) {
     case 1: return (int)sizeof(trb_shade_config);
     case 2: return (int)sizeof(trb_render_config);
     case 3: return (int)sizeof(trb_uv_texture);
+    case 4: return (int)sizeof(trb_peer_sum);
+    case 5: return (int)sizeof(trb_render_extras);
     default: return -1;
   }
 }

@@ -1250,7 +1250,8 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
                                   float* verts_ndc, float* normals_raw, float* normals, int64_t* pix_to_face,
                                   float* zbuf, float* bary, float* dists, float* images, int32_t* tile_hit,
                                   void* workspace, size_t workspace_bytes, int32_t* stats,
-                                  const trb_uv_texture* uv, int device, trb_stream_t stream) {
+                                  const trb_uv_texture* uv, const trb_render_extras* extras, int device,
+                                  trb_stream_t stream) {
   int rc = check_render_cfg(cfg);
   if (rc != TRB_OK) return rc;
   const trb_shade_config& sc = cfg->shade;
@@ -1274,7 +1275,7 @@ extern "C" int trb_render_forward(const trb_render_config* cfg, const trb_view* 
 
   const bool lit = is_phong(sc.shader) && sc.light_kind != TRB_LIGHT_AMBIENT;
   rc = run_forward_stages(cfg, views, verts_world, faces, R, T, proj, view_params, verts_ndc, normals_raw, normals,
-                          tile_hit, workspace, tg, ws, lit, st);
+                          tile_hit, workspace, tg, ws, lit, st, extras);
   if (rc != TRB_OK) return rc;
   const float sqrt_blur = sqrtf(cfg->blur_radius);
   const float z_cull = fmaxf(cfg->z_clip_value, 0.0f);

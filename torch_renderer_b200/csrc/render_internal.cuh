@@ -80,7 +80,7 @@ int run_forward_stages(const trb_render_config* cfg, const trb_view* views, cons
                        const int32_t* faces, const float* R, const float* T, const float* proj,
                        float* view_params, float* verts_ndc, float* normals_raw, float* normals,
                        int32_t* hit_pixels, void* workspace, const TileGrid& tg, const WsLayout& ws, bool lit,
-                       cudaStream_t st);
+                       cudaStream_t st, const trb_render_extras* extras = nullptr);
 int run_backward_post(const trb_render_config* cfg, const trb_view* views, const float* verts_world,
                       const int32_t* faces, const float* R, const float* T, const float* proj,
                       const float* view_params, const float* g_view_params, const float* normals_raw,

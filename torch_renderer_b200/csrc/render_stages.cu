@@ -17,6 +17,8 @@ struct PrepArgs {
   float* zero_b; long long n_zero_b;     // raw vertex normals
   int* zero_c;                           // covered-pixel counter
   float* zero_d; int n_zero_d;           // per-view alpha sums behind the covered-pixel list
+  const float* vp_src; float* vp_dst;    // trb_render_extras: the parameter block is copied in here ...
+  float* zero_e; long long n_zero_e;     // ... and the backward's gradient + scratch allocation zeroed
 };
 
 // role 0: world -> NDC of every (view, vertex) + the camera centre of every view; role 1: zero the
@@ -29,7 +31,13 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs p) {
     const trb_view vd = p.views[n];
     const int lv = bx * 256 + threadIdx.x;
     if (lv < vd.vert_count) transform_vertex(p.verts, p.R, p.T, p.proj, vd, n, lv, p.perspective, p.verts_ndc);
-    if (p.view_params && bx == 0 && threadIdx.x == 0) camera_center_one(p.R, p.T, p.view_params, n);
+    if (bx == 0) {
+      const int t = threadIdx.x;
+      // (slots 13..15 are the camera centre: thread 0 writes them below when the kernel derives it)
+      if (p.vp_src && t < TRB_VIEW_PARAM_STRIDE && !(p.view_params && t >= 13 && t < 16))
+        p.vp_dst[(size_t)n * TRB_VIEW_PARAM_STRIDE + t] = p.vp_src[(size_t)n * TRB_VIEW_PARAM_STRIDE + t];
+      if (p.view_params && t == 0) camera_center_one(p.R, p.T, p.view_params, n);
+    }
     return;
   }
   const long long stride = (long long)(gridDim.x - p.blocks_transform) * 256;
@@ -38,6 +46,16 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs p) {
   for (long long i = i0; i < p.n_zero_b; i += stride) p.zero_b[i] = 0.0f;
   if (i0 == 0 && p.zero_c) *p.zero_c = 0;
   if (p.zero_d) for (long long i = i0; i < p.n_zero_d; i += stride) p.zero_d[i] = 0.0f;
+  if (p.zero_e) {
+    if ((reinterpret_cast<size_t>(p.zero_e) & 15) == 0) {
+      const long long n4 = p.n_zero_e >> 2;
+      float4* z4 = reinterpret_cast<float4*>(p.zero_e);
+      for (long long i = i0; i < n4; i += stride) z4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (long long i = (n4 << 2) + i0; i < p.n_zero_e; i += stride) p.zero_e[i] = 0.0f;
+    } else {
+      for (long long i = i0; i < p.n_zero_e; i += stride) p.zero_e[i] = 0.0f;
+    }
+  }
 }
 
 struct BinArgs {
@@ -91,7 +109,7 @@ int run_forward_stages(const trb_render_config* cfg, const trb_view* views, cons
                        const int32_t* faces, const float* R, const float* T, const float* proj,
                        float* view_params, float* verts_ndc, float* normals_raw, float* normals,
                        int32_t* hit_pixels, void* workspace, const TileGrid& tg, const WsLayout& ws, bool lit,
-                       cudaStream_t st) {
+                       cudaStream_t st, const trb_render_extras* extras) {
   const trb_shade_config& sc = cfg->shade;
   const int N = sc.N;
   unsigned char* wsb = (unsigned char*)workspace;
@@ -111,7 +129,11 @@ int run_forward_stages(const trb_render_config* cfg, const trb_view* views, cons
   p.zero_d = (hit_pixels && sc.shader != TRB_SHADER_NONE)
                  ? reinterpret_cast<float*>(hit_pixels + 1 + (size_t)N * sc.H * sc.W * (sc.K > 1 ? 2 : 1)) : nullptr;
   p.n_zero_d = N;
-  const long long zero_words = p.n_zero_a + p.n_zero_b;
+  p.vp_src = (extras && view_params) ? extras->view_params_src : nullptr; p.vp_dst = view_params;
+  p.zero_e = extras ? extras->zero_buffer : nullptr;
+  p.n_zero_e = (extras && extras->zero_buffer) ? extras->zero_count : 0;
+  if (p.n_zero_e <= 0) p.zero_e = nullptr;
+  const long long zero_words = p.n_zero_a + p.n_zero_b + p.n_zero_e / 4;
   long long bz = ceil_div64(zero_words, 256 * 4);
   if (bz < 1) bz = 1;
   if (bz > 4 * kNumSMs) bz = 4 * kNumSMs;

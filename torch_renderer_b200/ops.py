@@ -585,8 +585,9 @@ class _RenderFn(torch.autograd.Function):
         verts, R, T, proj = _f32c(verts), _f32c(R), _f32c(T), _f32c(proj)
         colors = None if colors is None else _f32c(colors)
         tex_map = None if tex_map is None else _f32c(tex_map)
-        # the kernel may write the camera centres into the block: never alias a cached tensor
-        vp = None if view_params is None else _f32c(view_params).clone()
+        # the kernel may write the camera centres into the block: it works on a copy that its first kernel makes
+        # (trb_render_extras.view_params_src) inside the internal buffer -- no clone node per render
+        vp_src = None if view_params is None else _f32c(view_params)
         N, (H, W), K = table.N, spec["image_size"], spec["K"]
         shader = spec["shader"]
         phong = shader in (_lib.SHADER_SOFT_PHONG, _lib.SHADER_HARD_PHONG)
@@ -633,7 +634,8 @@ class _RenderFn(torch.autograd.Function):
             P = N * H * W * K
             sizes = (ws_bytes.value, table.total_ndc_verts * 12, V3 if phong else 0, V3 if phong else 0,
                      max(n_tiles.value, 1) * 4, 16,
-                     8 * P if sparse else 0, 4 * P if sparse else 0, 12 * P if sparse else 0, 4 * P if sparse else 0)
+                     8 * P if sparse else 0, 4 * P if sparse else 0, 12 * P if sparse else 0, 4 * P if sparse else 0,
+                     N * _lib.VIEW_PARAM_STRIDE * 4)
             offs, total = [], 0
             for nb in sizes:
                 offs.append(total)
@@ -668,12 +670,25 @@ class _RenderFn(torch.autograd.Function):
             p_p2f, p_zbuf, p_bary, p_dists = p2f.data_ptr(), zbuf.data_ptr(), bary.data_ptr(), dists.data_ptr()
         images = (torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if shader != _lib.SHADER_NONE
                   else _empty_f32(dev))
+        vp = None
+        extras = _lib.RenderExtras(0, 0, 0)
+        if vp_src is not None:
+            vp = aux[offs[10]:offs[10] + N * _lib.VIEW_PARAM_STRIDE * 4].view(torch.float32).view(N, _lib.VIEW_PARAM_STRIDE)
+            extras.view_params_src = vp_src.data_ptr()
+        # The backward's one zero-filled allocation (gradient outputs + the kernels' float4 accumulators) is made
+        # here when a backward can follow, and zeroed by the forward's first kernel: no fill node in front of the
+        # backward.  `backward` takes it once; a second backward over the same graph allocates its own.
+        ctx.flat = None
+        if N > 0 and any(ctx.needs_input_grad[:7]):
+            ctx.flat = torch.empty((sum(_RenderFn._grad_sizes(ctx.needs_input_grad, n_scratch, N, verts.shape[0],
+                                                              tex_map)),), dtype=torch.float32, device=dev)
+            extras.zero_buffer, extras.zero_count = ctx.flat.data_ptr(), ctx.flat.numel()
         with _timed("render_forward", dev):
             check(L.trb_render_forward(
                 ctypes.byref(cfg), _ptr(table.views), _ptr(verts), _ptr(faces), _ptr(colors), _ptr(R), _ptr(T),
                 _ptr(proj), _ptr(vp), p_ndc, p_nraw, p_nrm, p_p2f, p_zbuf,
                 p_bary, p_dists, _ptr(images if shader != _lib.SHADER_NONE else None), p_hit,
-                p_ws, ws_nbytes, p_stats, None if uv is None else ctypes.byref(uv), dev.index,
+                p_ws, ws_nbytes, p_stats, None if uv is None else ctypes.byref(uv), ctypes.byref(extras), dev.index,
                 _stream(dev)), "render")
         _bump(5 + (1 if want_stats else 0))  # prep, count, alloc, fill, fine (+ stats)
         if want_stats:
@@ -697,6 +712,13 @@ class _RenderFn(torch.autograd.Function):
         return images, p2f, zbuf, bary, dists, alpha_sum
 
     @staticmethod
+    def _grad_sizes(needs_input_grad, n_scratch, N, V, tex_map):
+        """Float counts of the parts of the backward's single allocation: the kernels' scratch (first: 16-byte
+        aligned), then grad verts, colours, R, T, projection, view parameters, texture map."""
+        n_tex = tex_map.numel() if (tex_map is not None and needs_input_grad[2]) else 0
+        return [(max(n_scratch, 1) + 3) // 4 * 4, V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE, n_tex]
+
+    @staticmethod
     def backward(ctx, g_images, _g_p2f, g_zbuf, g_bary, g_dists, _g_alpha_sum=None):
         verts, colors, R, T, proj, vp, faces, aux, p2f, zbuf, bary, dists, tex_map = ctx.saved_tensors[:13]
         o_ndc, o_nraw, o_nrm, o_hit, phong = ctx.aux_offsets
@@ -717,12 +739,13 @@ class _RenderFn(torch.autograd.Function):
         shader = cfg.shade.shader
         if shader != _lib.SHADER_NONE and g_images is None:
             g_images = torch.zeros((N, cfg.shade.H, cfg.shade.W, 4), dtype=torch.float32, device=dev)
-        # one zero-filled buffer for every accumulated gradient
-        # ... and for the kernel's float4 accumulators (16-byte aligned: the scratch block comes first)
-        n_scratch = (max(ctx.n_scratch, 1) + 3) // 4 * 4
-        n_tex = tex_map.numel() if (tex_map is not None and need_tex) else 0
-        sizes = [n_scratch, V * 3, V * 3, N * 9, N * 3, N * 4, N * _lib.VIEW_PARAM_STRIDE, n_tex]
-        flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
+        # one zero-filled buffer for every accumulated gradient and for the kernels' float4 accumulators: the one
+        # the forward allocated and its first kernel zeroed, or (second backward over the same graph) a fresh one
+        sizes = _RenderFn._grad_sizes(ctx.needs_input_grad, ctx.n_scratch, N, V, tex_map)
+        n_tex = sizes[-1]
+        flat, ctx.flat = ctx.flat, None
+        if flat is None or flat.numel() != sum(sizes):
+            flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
         parts = list(flat.split(sizes))
         scratch, g_verts, g_cols, g_R, g_T, g_proj, g_vp, g_tex = parts
         uv = None

@@ -10,6 +10,7 @@ from typing import List, Optional, Sequence, Union
 import torch
 
 from . import ops
+from .common import unbind_batch
 
 _Input = Union[Sequence[torch.Tensor], torch.Tensor, None]
 
@@ -20,7 +21,7 @@ def _as_list(x: _Input, what: str, trailing: Optional[int] = None) -> Optional[L
     if torch.is_tensor(x):
         if x.dim() != 3:
             raise ValueError(f"{what} tensor has incorrect dimensions.")
-        x = [x[i] for i in range(x.shape[0])]
+        x = unbind_batch(x)
     out = []
     for t in x:
         if t.dim() != 2 or (trailing is not None and t.shape[1] != trailing):

@@ -18,6 +18,7 @@ from typing import List, Optional, Sequence, Union
 import torch
 
 from . import ops
+from .common import unbind_batch
 
 
 # Topology-only device data is shared between Meshes objects: optimisation loops build a new Meshes every
@@ -94,7 +95,7 @@ class Meshes:
             self.device = verts.device
             if faces.device != self.device:
                 raise ValueError("Verts and Faces tensors should be on same device.")
-            self._verts_list = [verts[i] for i in range(verts.shape[0])]
+            self._verts_list = unbind_batch(verts)
             self._faces_list = []
             for i in range(faces.shape[0]):
                 f = faces[i]

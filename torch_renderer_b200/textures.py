@@ -17,11 +17,12 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from .common import unbind_batch
 
 
 def _to_list(x, n_expected=None):
     if torch.is_tensor(x):
-        return [x[i] for i in range(x.shape[0])]
+        return unbind_batch(x)
     return list(x)
 
 
@@ -33,7 +34,7 @@ class TexturesVertex:
         elif torch.is_tensor(verts_features):
             if verts_features.dim() != 3:
                 raise ValueError("Expected verts_features to be of shape (N, V, C)")
-            self._feats = [verts_features[i] for i in range(verts_features.shape[0])]
+            self._feats = unbind_batch(verts_features)
         else:
             raise ValueError("verts_features must be a tensor or list of tensors")
         self._N = len(self._feats)

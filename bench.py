@@ -331,7 +331,42 @@ def run_ours(args):
     if ar_timing is not None:
         torch.cuda.synchronize()
         ar_timing.zero_()
+    # diagnostic builds only (libtrb built with -DTRB_STEP_STAMPS, selected through TRB_LIB_PATH): %globaltimer stamps
+    # of the step's first kernel, of the backward's tail kernel and of the all-reduce kernel, per step, in a ring
+    stamps = None
+    if os.environ.get("TRB_STEP_STAMPS_OUT"):
+        import ctypes
+        from torch_renderer_b200 import _lib as _l2
+        h = ctypes.CDLL(_l2.LIB_PATH)
+        if hasattr(h, "trb_debug_set_step_stamps"):
+            stamps = (torch.zeros(256 * 8, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+            torch.cuda.synchronize()
+            h.trb_debug_set_step_stamps(ctypes.c_void_p(stamps[0].data_ptr()), ctypes.c_void_p(stamps[1].data_ptr()))
     ms_total, ms_repeats = timed(run_device, args.steps)
+    if stamps is not None:
+        torch.cuda.synchronize()
+        h.trb_debug_set_step_stamps(None, None)
+        ring = stamps[0].cpu().view(256, 8).numpy().astype(np.int64)
+        last = int(stamps[1].item())
+        rows = [(k & 255) for k in range(max(last - 200, 1), last)]      # the newest 200 steps, oldest first
+        seg = {"fwd_bwd_until_tail_starts": [], "tail_kernel": [], "gap_tail_end_to_allreduce_start": [],
+               "allreduce_kernel": [], "gap_last_kernel_end_to_next_step": [], "step": []}
+        for a_, b_ in zip(rows[:-1], rows[1:]):
+            r0, r1 = ring[a_], ring[b_]
+            if r1[0] <= r0[0] or r1[0] - r0[0] > 2_000_000:   # a repeat boundary (barrier) between the two steps
+                continue
+            has_ar = r0[4] > 0
+            seg["fwd_bwd_until_tail_starts"].append(r0[1] - r0[0])
+            seg["tail_kernel"].append(r0[2] - r0[1])
+            if has_ar:
+                seg["gap_tail_end_to_allreduce_start"].append(r0[3] - r0[2])
+                seg["allreduce_kernel"].append(r0[4] - r0[3])
+            seg["gap_last_kernel_end_to_next_step"].append(r1[0] - (r0[4] if has_ar else r0[2]))
+            seg["step"].append(r1[0] - r0[0])
+        rep = {k: round(float(np.median(v)) / 1e3, 2) for k, v in seg.items() if v}
+        rep["unit"] = "us, median over %d consecutive steps of the timed region" % len(seg["step"])
+        with open(f"{os.environ['TRB_STEP_STAMPS_OUT']}_n{world}_rank{rank}.json", "w") as fh:
+            json.dump(rep, fh)
     ar_report = None
     if ar_timing is not None:
         t = ar_timing.clone()
@@ -364,6 +399,34 @@ def run_ours(args):
             collective_ab = {"fused_into_backward_tail_ms_per_step": round(ms_fused_again, 4),
                              "separate_kernel_ms_per_step": round(ms_sep, 4),
                              "what": "same process, both captured in the step graph, timed back to back after the headline"}
+
+    # Where the N-GPU step's extra time goes: every rank times its OWN step without the all-reduce (same views, same
+    # graph minus the collective, all ranks running at once, no synchronisation between them).  A step with the
+    # all-reduce ends on the slowest rank, so max - mean of these is the rank skew the collective exposes; what is
+    # left of (N-GPU step - slowest rank's own step) is the all-reduce itself (launch + push + NVLink + sum).
+    skew_report = None
+    if world > 1:
+        core_run, core_mode = graphed(core_device)
+        if core_mode == "cuda-graph":
+            for _ in range(200):
+                core_run()
+            own = []
+            for _ in range(args.repeats):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    core_run()
+                e1.record()
+                torch.cuda.synchronize()
+                own.append(e0.elapsed_time(e1) / args.steps)
+            mine = torch.tensor([statistics.median(own)], device=dev)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank = [round(float(t.item()), 4) for t in every]
+            skew_report = {"own_step_without_allreduce_ms_per_rank": per_rank,
+                           "slowest_minus_mean_us": round((max(per_rank) - sum(per_rank) / world) * 1e3, 2),
+                           "step_with_allreduce_minus_slowest_own_us": round((ms_step - max(per_rank)) * 1e3, 2)}
 
     # per-kernel durations: the same steps again, with CUDA events recorded by libtrb on the launching
     # stream right around its two dominant kernels (the fused fine pass and the fused backward), and
@@ -563,6 +626,8 @@ def run_ours(args):
         if collective_ab is not None:
             line["collective_ab"] = collective_ab
         if ar_report is not None:
+            if skew_report is not None:
+                ar_report["rank_skew"] = skew_report
             line["collective_timing"] = ar_report
         if other is not None:
             line["other_configs"] = other

@@ -30,12 +30,24 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+#ifdef TRB_STEP_STAMPS
+static __device__ StepStamps g_stamps_ar = {nullptr, nullptr};
+int set_step_stamps_allreduce(unsigned long long* ring, unsigned* step) {
+  StepStamps s = {ring, step};
+  return cudaMemcpyToSymbol(g_stamps_ar, &s, sizeof(s)) == cudaSuccess ? TRB_OK : TRB_ERR_CUDA;
+}
+#endif
+
 __global__ void __launch_bounds__(256)
 allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world, long long capacity,
                       unsigned* epochs, int* error, unsigned long long* timing) {
   constexpr int PER = kArChunk / 256;
   // launched as a programmatic dependent launch: resident while the producer of the gradients drains
   pdl_wait();
+#ifdef TRB_STEP_STAMPS
+  unsigned long long* stamp = g_stamps_ar.ring ? stamp_row(g_stamps_ar) : nullptr;
+  if (stamp && threadIdx.x == 0) atomicMin(stamp + 3, stamp_now());
+#endif
   const bool timed = timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   const unsigned long long t0 = timed ? global_ns() : 0ull;
   const unsigned epoch = epochs[blockIdx.x] + 1u;
@@ -99,6 +111,9 @@ allreduce_push_kernel(const ArSegments seg, const ArPeers p, int rank, int world
     const unsigned long long t2 = global_ns();
     timing[0] += t1 - t0; timing[1] += t2 - t1; timing[2] += 1ull;
   }
+#ifdef TRB_STEP_STAMPS
+  if (stamp && threadIdx.x == 0) atomicMax(stamp + 4, stamp_now());
+#endif
 }
 
 // The receive-and-sum half on its own: the push half ran inside post_backward_kernel (render_stages.cu), whose last
@@ -194,6 +209,15 @@ extern "C" int trb_allreduce_sum_f32(float* const* host_segments, const int64_t*
   TRB_LAUNCH_CHECK();
   return TRB_OK;
 }
+
+#ifdef TRB_STEP_STAMPS
+/* diagnostic builds: ring u64[256][8] + step counter u32[1] (device, zeroed by the caller); NULLs switch it off */
+extern "C" int trb_debug_set_step_stamps(uint64_t* ring, uint32_t* step) {
+  int rc = set_step_stamps_stages((unsigned long long*)ring, (unsigned*)step);
+  if (rc != TRB_OK) return rc;
+  return set_step_stamps_allreduce((unsigned long long*)ring, (unsigned*)step);
+}
+#endif
 
 /* diagnostics: `device_u64x3` (zeroed by the caller) accumulates block 0's push / wait-and-sum nanoseconds and the
  * call count of every later trb_allreduce_sum_f32 launch; NULL switches it off.  Process-wide. */

@@ -99,6 +99,24 @@ inline int ar_fill_tables(float* const* host_segments, const int64_t* host_count
   return TRB_OK;
 }
 
+#ifdef TRB_STEP_STAMPS
+// Diagnostic builds (TRB_EXTRA_NVCC_FLAGS=-DTRB_STEP_STAMPS): %globaltimer stamps of a step's kernels in a ring of
+// 256 rows x 8 words -- [0] prep_kernel block 0 start, [1] first / [2] last post_backward_kernel block start / exit,
+// [3] first all-reduce block past its griddepcontrol.wait / [4] last all-reduce block exit.  prep_kernel opens a row
+// per step.  Every translation unit keeps its own copy of the two pointers (trb_debug_set_step_stamps sets both).
+struct StepStamps { unsigned long long* ring; unsigned* step; };
+__device__ __forceinline__ unsigned long long stamp_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long* stamp_row(const StepStamps& s) {
+  return s.ring + (size_t)(*(volatile unsigned*)s.step & 255u) * 8;
+}
+int set_step_stamps_stages(unsigned long long* ring, unsigned* step);     // render_stages.cu
+int set_step_stamps_allreduce(unsigned long long* ring, unsigned* step);  // allreduce.cu
+#endif
+
 // Launches the receive-and-sum half on its own (allreduce.cu); the push half ran inside post_backward_kernel.
 int launch_allreduce_receive(const ArPush& a, cudaStream_t st);
 

@@ -8,6 +8,14 @@
 
 namespace trb {
 
+#ifdef TRB_STEP_STAMPS
+static __device__ StepStamps g_stamps_stages = {nullptr, nullptr};
+int set_step_stamps_stages(unsigned long long* ring, unsigned* step) {
+  StepStamps s = {ring, step};
+  return cudaMemcpyToSymbol(g_stamps_stages, &s, sizeof(s)) == cudaSuccess ? TRB_OK : TRB_ERR_CUDA;
+}
+#endif
+
 // ---- forward -----------------------------------------------------------------------------------------
 struct PrepArgs {
   const float* verts; const float* R; const float* T; const float* proj; const trb_view* views;
@@ -26,6 +34,15 @@ struct PrepArgs {
 __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs p) {
   pdl_wait();
   const int b = blockIdx.x;
+#ifdef TRB_STEP_STAMPS
+  if (b == 0 && threadIdx.x == 0 && g_stamps_stages.ring) {
+    const unsigned step = *g_stamps_stages.step + 1u;
+    unsigned long long* row = g_stamps_stages.ring + (size_t)(step & 255u) * 8;
+    row[0] = stamp_now(); row[1] = ~0ull; row[2] = 0ull; row[3] = ~0ull; row[4] = 0ull;
+    __threadfence();
+    *g_stamps_stages.step = step;
+  }
+#endif
   if (b < p.blocks_transform) {
     const int n = b / p.bpv, bx = b - n * p.bpv;
     const trb_view vd = p.views[n];
@@ -189,6 +206,13 @@ struct PostArgs {
 __global__ void __launch_bounds__(256) post_backward_kernel(const PostArgs p) {
   pdl_wait();
   const int b = blockIdx.x;
+#ifdef TRB_STEP_STAMPS
+  struct StampExit {   // every exit path of the block stamps "last block exit"
+    unsigned long long* row;
+    __device__ ~StampExit() { if (row && threadIdx.x == 0) atomicMax(row + 2, stamp_now()); }
+  } stamp_exit = {g_stamps_stages.ring ? stamp_row(g_stamps_stages) : nullptr};
+  if (stamp_exit.row && threadIdx.x == 0) atomicMin(stamp_exit.row + 1, stamp_now());
+#endif
   if (p.has_push && b >= p.b_push) {
     const unsigned epoch = p.push.epochs[b - p.b_push] + 1u;   // fetched while the counter is still moving
     if (threadIdx.x == 0) {

@@ -383,6 +383,21 @@ def run_ours(args):
                                 "push = issuing the remote stores"}
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
+    contexts = None
+    if world > 1 and rank == 0:
+        # which processes hold a CUDA context on which GPU (a rank that also opened a context on a neighbour's GPU
+        # would make that GPU switch between two contexts)
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-compute-apps=pid,gpu_bus_id,used_memory", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout
+            per_gpu = {}
+            for ln in out.strip().splitlines():
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) >= 2:
+                    per_gpu.setdefault(parts[1], []).append(parts[0])
+            contexts = {"processes_per_gpu": {k: len(v) for k, v in per_gpu.items()}}
+        except Exception:  # noqa: BLE001
+            contexts = None
     ms_step = ms_total / args.steps
     value = world * N / (ms_step / 1e3)
     # same box, same process: the step with the all-reduce as its own kernel after the backward (the other variant)
@@ -628,6 +643,8 @@ def run_ours(args):
         if ar_report is not None:
             if skew_report is not None:
                 ar_report["rank_skew"] = skew_report
+            if contexts is not None:
+                ar_report["cuda_contexts"] = contexts
             line["collective_timing"] = ar_report
         if other is not None:
             line["other_configs"] = other
@@ -635,7 +652,19 @@ def run_ours(args):
             line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The result is out: teardown must not outlive it.  (With the NCCL fallback captured in the step graph,
+        # destroy_process_group has been seen to stall for minutes; the peer-memory route exits cleanly.)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        bail = threading.Timer(20.0, lambda: os._exit(0))
+        bail.daemon = True
+        bail.start()
+        try:
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+        os._exit(0)
 
 
 # Warp instructions per launch of the K>1 fine kernel on the C5 chunk / C3, from the committed ncu captures

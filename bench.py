@@ -142,6 +142,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: torch_renderer_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    if world == 1 and os.environ.get("TRB_BENCH_INIT_NCCL"):
+        # control experiment: a single-GPU run that merely CREATES an NCCL communicator first (profiles/r02_scaling.md)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        dist.all_reduce(torch.ones(8, device=dev))
+        torch.cuda.synchronize()
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG") in ("VERSION", "WARN") else None  # "NCCL version ..." goes to stdout at those levels: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)

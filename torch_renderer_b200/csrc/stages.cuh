@@ -68,7 +68,8 @@ __device__ __forceinline__ void transform_vertex_backward(
       gxv = gx * fx; gyv = gy * fy;
       gfx = gx * xv; gfy = gy * yv;
     }
-    if (grad_verts) {
+    // (a vertex no covered sample touched in this view -- about half of a closed mesh -- has nothing to add)
+    if (grad_verts && (gx != 0.0f || gy != 0.0f || gz != 0.0f)) {
       float* gv = grad_verts + 3 * (size_t)(vd.world_vert_start + lv);
       atomicAdd(gv + 0, __ldg(r + 0) * gxv + __ldg(r + 1) * gyv + __ldg(r + 2) * gzv);
       atomicAdd(gv + 1, __ldg(r + 3) * gxv + __ldg(r + 4) * gyv + __ldg(r + 5) * gzv);

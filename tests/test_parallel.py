@@ -44,9 +44,15 @@ def _worker(rank, world, port, q):
         s, e = shard_views(n_views, rank, world)
         g_verts = per_view[s:e].sum(0)                 # partial gradient from this rank's views
         g_cols = (per_view[s:e] ** 2).sum(0)
-        allreduce_shared_grads([g_verts, None, g_cols])
+        # the fused form (push from the backward's tail kernel) needs NCCL + peer memory: on gloo the context yields
+        # False and changes nothing, and the caller reduces afterwards -- the pattern of its docstring
+        from torch_renderer_b200 import ops, parallel
+        with parallel.fused_backward_allreduce() as fused:
+            armed = ops._backward_peer_sum is not None
+        if not fused:
+            allreduce_shared_grads([g_verts, None, g_cols])
         ok = torch.allclose(g_verts, per_view.sum(0), atol=1e-5) and torch.allclose(g_cols, (per_view ** 2).sum(0), atol=1e-5)
-        q.put((rank, bool(ok)))
+        q.put((rank, bool(ok and not fused and not armed and ops._backward_peer_sum is None)))
     finally:
         dist.destroy_process_group()
 
@@ -68,6 +74,9 @@ def test_allreduce_shared_grads_gloo_world2():
 def test_allreduce_is_noop_without_process_group():
     g = torch.ones(3)
     assert allreduce_shared_grads([g]) is None and torch.equal(g, torch.ones(3))
+    from torch_renderer_b200 import ops, parallel
+    with parallel.fused_backward_allreduce() as fused:
+        assert fused is False and ops._backward_peer_sum is None
 
 
 def _peer_worker(rank, world, port, q):

@@ -218,3 +218,68 @@ def test_shading_ref_blend_identities():
     assert torch.allclose(sil[..., 3], img[..., 3])
     hard = sref.hard_rgb_blend(colors, p2f, (0.2, 0.3, 0.4))
     assert torch.equal(hard[..., 3] > 0, p2f[..., 0] >= 0)
+
+
+def test_phong_lighting_hand_values():
+    """Known answers worked by hand for the lighting restatement.  Surface point at the origin, normal +z.
+    (a) Point light at (0, 0, 2), camera at (0, 0, 5): n.l = 1, the reflection is +z = the view direction, so
+        colour = (ambient + diffuse) * texel + specular.
+    (b) Light at (2, 0, 2): l = (1, 0, 1)/sqrt2, n.l = 1/sqrt2; r = -l + 2 (n.l) n = (-1, 0, 1)/sqrt2; camera at
+        (0, 0, 5): v = +z, r.v = 1/sqrt2, specular = (1/sqrt2)^shininess.
+    (c) Light behind the surface: diffuse and specular vanish (the specular mask is n.l > 0).
+    (d) Directional light (0, 0, 1) equals (a) without the position dependence; ambient-only lights ignore both."""
+    pts = torch.zeros(1, 1, 1, 1, 3)
+    nrm = torch.tensor([0.0, 0.0, 1.0]).view(1, 1, 1, 1, 3)
+    tex = torch.tensor([0.5, 0.25, 1.0]).view(1, 1, 1, 1, 3)
+    one3 = lambda x: torch.tensor([[x, x, x]])
+    cam = torch.tensor([[0.0, 0.0, 5.0]])
+    shin = torch.tensor([4.0])
+
+    def colour(kind, vec, amb=0.3, dif=0.5, spec=0.2):
+        return sref.phong_colors(pts, nrm, tex, None, kind, torch.tensor([vec]), one3(amb), one3(dif), one3(spec),
+                                 one3(1.0), one3(1.0), one3(1.0), shin, cam).view(3)
+
+    a = colour("point", [0.0, 0.0, 2.0])
+    assert torch.allclose(a, (0.3 + 0.5) * tex.view(3) + 0.2, atol=1e-6)
+    b = colour("point", [2.0, 0.0, 2.0])
+    c = 2 ** -0.5
+    assert torch.allclose(b, (0.3 + 0.5 * c) * tex.view(3) + 0.2 * c ** 4, atol=1e-6)
+    behind = colour("point", [0.0, 0.0, -2.0])
+    assert torch.allclose(behind, 0.3 * tex.view(3), atol=1e-6)
+    d = colour("directional", [0.0, 0.0, 1.0])
+    assert torch.allclose(d, a, atol=1e-6)
+    assert torch.allclose(colour("ambient", [9.0, 9.0, 9.0]), 0.3 * tex.view(3), atol=1e-6)
+
+
+def test_vertex_normals_hand_values():
+    """Area-weighted vertex normals: a unit right triangle in the z = 0 plane and a twice-as-large one in
+    the x = 0 plane sharing the vertex at the origin.  Face normals (v2 - v1) x (v0 - v1): (0, 0, 1) * 1 for the
+    first, (1, 0, 0) * 4 for the second (|cross| = 2 * area), so the shared vertex gets normalize((4, 0, 1))."""
+    verts = torch.tensor([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 2, 0], [0, 0, 2]])
+    faces = torch.tensor([[0, 1, 2], [0, 3, 4]])
+    n = sref.vertex_normals(verts, faces)
+    assert torch.allclose(n[1], torch.tensor([0.0, 0.0, 1.0])) and torch.allclose(n[2], torch.tensor([0.0, 0.0, 1.0]))
+    assert torch.allclose(n[3], torch.tensor([1.0, 0.0, 0.0])) and torch.allclose(n[4], torch.tensor([1.0, 0.0, 0.0]))
+    assert torch.allclose(n[0], torch.tensor([4.0, 0.0, 1.0]) / 17 ** 0.5, atol=1e-6)
+
+
+def test_softmax_blend_hand_values():
+    """softmax_rgb_blend worked by hand with sigma = gamma = 1, znear = 1, zfar = 11, two layers:
+    layer 0: z = 3, signed distance -ln 3  => p0 = sigmoid(ln 3) = 3/4, z_inv = 0.8 (the maximum), weight 3/4;
+    layer 1: z = 6, signed distance  ln 3  => p1 = 1/4,              z_inv = 0.5, weight exp(-0.3) / 4;
+    background weight delta = exp(-0.8); alpha = 1 - (1/4)(3/4) = 13/16."""
+    import math
+    p2f = torch.tensor([[[[5, 9]]]])
+    z = torch.tensor([[[[3.0, 6.0]]]])
+    d = torch.tensor([[[[-math.log(3.0), math.log(3.0)]]]])
+    cols = torch.tensor([[[[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]]]])
+    out = sref.softmax_rgb_blend(cols, p2f, z, d, 1.0, 1.0, (0.0, 0.0, 1.0), 1.0, 11.0).view(4)
+    w0, w1, delta = 0.75, 0.25 * math.exp(-0.3), math.exp(-0.8)
+    den = w0 + w1 + delta
+    assert torch.allclose(out, torch.tensor([w0 / den, w1 / den, delta / den, 13.0 / 16.0]), atol=1e-6)
+    # one empty slot (-1) contributes nothing: same pixel with the second layer masked out
+    out1 = sref.softmax_rgb_blend(cols, torch.tensor([[[[5, -1]]]]), z, d, 1.0, 1.0, (0.0, 0.0, 1.0), 1.0, 11.0).view(4)
+    assert torch.allclose(out1, torch.tensor([w0 / (w0 + delta), 0.0, delta / (w0 + delta), 0.75]), atol=1e-6)
+    # the silhouette shader's alpha is the same product
+    sil = sref.sigmoid_alpha_blend(cols, p2f, d, 1.0).view(4)
+    assert abs(float(sil[3]) - 13.0 / 16.0) < 1e-6

@@ -2,8 +2,8 @@
 # The driver's N=2 command, verbatim flags (C5 at spec included), plus the reference arm under torchrun.
 tag=${1:-n2d}
 out=gpurun_out
-t0=$SECONDS; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 \
-  bench.py --gpus 2 --steps 20 --warmup 5 > $out/bench_n2_$tag.json 2> $out/bench_n2_$tag.err; echo "bench rc=$?"
+t0=$SECONDS; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${2:-2} --master-addr 127.0.0.1 --master-port 29519 \
+  bench.py --gpus ${2:-2} --steps 20 --warmup 5 > $out/bench_n2_$tag.json 2> $out/bench_n2_$tag.err; echo "bench rc=$?"
 echo "wall $((SECONDS - t0)) s"
 python - <<PY
 import json

@@ -435,3 +435,29 @@ def test_round2_host_pieces_without_gpu():
     from torch_renderer_b200 import ops
     import inspect
     assert "max_radius" in inspect.signature(ops.rasterize_points_ndc).parameters
+
+
+def test_padded_inputs_are_split_without_select_nodes():
+    """`TexturesVertex(rgb[None])` / `Meshes(verts=padded, faces=padded)` -- the batch-of-one pattern of every reference
+    script -- must not put a SelectBackward node (a zeros + copy_ kernel pair per backward) between the leaf and the
+    kernels: one row is squeezed, several are unbound; gradients still reach the leaf."""
+    import torch_renderer_b200 as trb
+    from torch_renderer_b200.common import unbind_batch
+    rgb = torch.rand(1, 5, 3, requires_grad=True)
+    tex = trb.TexturesVertex(rgb)
+    feats = tex.verts_features_packed()
+    assert type(feats.grad_fn).__name__.startswith("Squeeze")
+    feats.sum().backward()
+    assert torch.equal(rgb.grad, torch.ones_like(rgb))
+    verts = torch.rand(1, 4, 3, requires_grad=True)
+    faces = torch.tensor([[[0, 1, 2], [1, 2, 3]]])
+    mesh = trb.Meshes(verts=verts, faces=faces)
+    assert type(mesh.verts_list()[0].grad_fn).__name__.startswith("Squeeze")
+    (mesh.verts_packed() * 2).sum().backward()
+    assert torch.equal(verts.grad, torch.full_like(verts, 2.0))
+    many = torch.rand(3, 4, 3, requires_grad=True)
+    rows = unbind_batch(many)
+    assert len(rows) == 3 and all(type(r.grad_fn).__name__.startswith("Unbind") for r in rows)
+    (rows[0].sum() + 3 * rows[2].sum()).backward()
+    assert torch.equal(many.grad[0], torch.ones(4, 3)) and torch.equal(many.grad[1], torch.zeros(4, 3))
+    assert torch.equal(many.grad[2], torch.full((4, 3), 3.0))
